@@ -1,0 +1,138 @@
+/* tac_b200.h -- C ABI of the B200-native mel-spectrogram / mu-law path.
+ *
+ * The reference (keunwoochoi/torchaudio-contrib) has no FFI of its own: its operator
+ * surface is the Python functions in torchaudio_contrib/functional.py, each of which hands
+ * the arithmetic to a torch operator.  Every entry point below replaces one of those call
+ * sites (cited as functional.py:LINE); INTEGRATION.md shows the ctypes stub that binds it.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / CUDA types in the signatures
+ *     (`stream` is a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - "device" entry points take DEVICE pointers owned by the caller, enqueue work on
+ *     `stream` and return immediately; nothing is allocated that the caller must free;
+ *   - "host" entry points (tac_pipeline_*) take HOST pointers and do H2D, compute, D2H;
+ *   - return value: TAC_OK or a negative TAC_ERR_*; tac_last_error() gives the message for
+ *     the calling thread; nothing throws across the boundary;
+ *   - fp32 everywhere; mu-law codes are int64 (functional.py:334 `.long()`).
+ */
+#ifndef TAC_B200_H_
+#define TAC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAC_ABI_VERSION 1
+
+enum {
+  TAC_OK = 0,
+  TAC_ERR_INVALID = -1,      /* bad argument (shape, size, null pointer)                  */
+  TAC_ERR_UNSUPPORTED = -2,  /* valid for the reference, not implemented by these kernels */
+  TAC_ERR_CUDA = -3,         /* CUDA runtime / driver error (message has the cuda string) */
+  TAC_ERR_WORKSPACE = -4     /* workspace / plan buffer too small                         */
+};
+
+/* torch.nn.functional.pad modes accepted by torch.stft (functional.py:104) */
+enum { TAC_PAD_REFLECT = 0, TAC_PAD_CONSTANT = 1, TAC_PAD_REPLICATE = 2, TAC_PAD_CIRCULAR = 3 };
+
+int tac_version(void);
+const char* tac_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+int tac_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* frames = 1 + (T + 2*(n_fft/2)*center - n_fft) / hop   (torch.stft; tests/test_functional.py:14-15) */
+int64_t tac_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center);
+
+/* ---- a1: stft (functional.py:48-113, call site torch.stft :99-107) ---------------------
+ * x: (n_seq, n_samples) rows `seq_stride` floats apart.  window: n_fft floats, already
+ * centre-padded from win_length (torch.stft semantics).  n_fft: power of two, 32..8192.
+ * out: (n_seq, bins, frames, 2) contiguous, bins = n_fft/2+1 (onesided) or n_fft. */
+int tac_stft_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                 const float* window, int n_fft, int hop, int center, int pad_mode,
+                 int normalized, int onesided, float* out, void* stream);
+
+/* ---- a1+a2: Spectrogram = stft then complex_norm(power) (layers.py:294-304) -------------
+ * out: (n_seq, bins, frames) contiguous. */
+int tac_spectrogram_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                        const float* window, int n_fft, int hop, int center, int pad_mode,
+                        int normalized, int onesided, float power, float* out, void* stream);
+
+/* ---- a2: complex_norm (functional.py:116-128): z (n, 2) -> out (n) = |z|^power ---------- */
+int tac_complex_norm_f32(const float* z, int64_t n, float power, float* out, void* stream);
+
+/* ---- a5: amplitude_to_db (functional.py:277-296): 10*(log10(max(x^2, amin)) - log10(ref)) */
+int tac_amplitude_to_db_f32(const float* x, int64_t n, float ref, float amin, float* out,
+                            void* stream);
+
+/* ---- a3: apply_filterbank (functional.py:172-184) on tcgen05 tensor cores ---------------
+ * The (n_bins, n_bands) row-major matrix is first turned into a "plan": per 32-bin K slice
+ * the range of non-zero bands, plus the tf32 hi/lo split of that block laid out as the
+ * 128B-swizzled K-major UMMA operand image.  Built on the host once per matrix, then copied
+ * to the device by the caller (any 16-byte aligned device buffer). */
+int64_t tac_fbplan_bytes(int n_bins, int n_bands);                 /* upper bound, bytes   */
+int tac_fbplan_build_host(const float* fb_host, int n_bins, int n_bands,
+                          void* plan_host, int64_t plan_capacity, int64_t* plan_bytes_used);
+
+/* spec: (n_seq, n_bins, frames) real, or (n_seq, n_bins, frames, 2) complex when is_complex.
+ * Computes |.|^power first when is_complex (a2), contracts over bins with the plan (a3) and,
+ * when to_db, applies amplitude_to_db(ref, amin) in the epilogue (a5).
+ * out: (n_seq, n_bands, frames) contiguous. */
+int tac_power_mel_f32(const float* spec, int is_complex, float power,
+                      int64_t n_seq, int64_t frames, int n_bins,
+                      const void* plan_dev, int n_bands,
+                      int to_db, float ref, float amin, float* out, void* stream);
+
+/* ---- a6: the Melspectrogram pipeline (layers.py:307-347 [+ AmplitudeToDb :350-381]) ------
+ * stft -> |.|^power -> filterbank [-> dB] without materialising the complex spectrum: the
+ * power spectrum goes through an L2-sized workspace in frame-major layout.
+ * workspace: device buffer of at least tac_melspec_workspace_bytes(...) bytes. */
+int64_t tac_melspec_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center);
+int tac_melspec_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                    const float* window, int n_fft, int hop, int center, int pad_mode,
+                    int normalized, float power,
+                    const void* plan_dev, int n_bands, int to_db, float ref, float amin,
+                    void* workspace, int64_t workspace_bytes, float* out, void* stream);
+
+/* ---- a7: mu_law_encoding (functional.py:317-335) ----------------------------------------
+ * The quantiser is evaluated as a table of decision levels: thresholds[j] is the smallest
+ * float whose code is >= idx_min + j (thresholds[0] = -inf); |x| > x_limit or NaN gives
+ * INT64_MIN (what the reference's float->int64 conversion yields after overflow to inf). */
+int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantize,
+                             const float* thresholds_dev, int n_thresholds, int idx_min,
+                             float x_limit, int64_t* out, void* stream);
+
+/* ---- a8: mu_law_decoding (functional.py:338-354) ----------------------------------------
+ * lut_dev[i] = decoded value of code i for 0 <= i < n_quantize; other codes are evaluated
+ * with the closed form in the kernel. */
+int tac_mulaw_decode_i64_f32(const int64_t* codes, int64_t n, int n_quantize,
+                             const float* lut_dev, float* out, void* stream);
+int tac_mulaw_decode_f32_f32(const float* codes, int64_t n, int n_quantize,
+                             const float* lut_dev, float* out, void* stream);
+
+/* ---- host-buffer plugin surface (what a reference-side caller with CPU tensors binds) ---
+ * A pipeline owns its device staging buffers, plan, streams and events. */
+typedef struct tac_pipeline tac_pipeline;
+
+typedef struct tac_pipeline_config {
+  int n_fft, hop, center, pad_mode, normalized;
+  float power;           /* ComplexNorm power; Melspectrogram uses 2.0 (layers.py:346)      */
+  int n_bins, n_bands;   /* filterbank shape; n_bands == 0: Spectrogram only (no filterbank) */
+  int to_db;             /* append AmplitudeToDb(ref, amin)                                  */
+  float ref, amin;
+} tac_pipeline_config;
+
+/* window_host: n_fft floats (centre-padded); fb_host: (n_bins, n_bands) row-major or NULL. */
+int tac_pipeline_create(const tac_pipeline_config* cfg, const float* window_host,
+                        const float* fb_host, tac_pipeline** out);
+/* x_host: (n_seq, n_samples) contiguous; out_host: (n_seq, n_bands|bins, frames).
+ * Copies in, computes and copies out in overlapped slices; returns when out_host is valid. */
+int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64_t n_seq, int64_t n_samples,
+                          float* out_host);
+int tac_pipeline_destroy(tac_pipeline* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAC_B200_H_ */

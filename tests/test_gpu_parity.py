@@ -1,0 +1,320 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+Tolerances: BASELINE.json north star -- 1e-4 relative fp32 for the mel path (dB: 1e-3 dB absolute),
+bit-exact for mu-law codes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, pure_rel_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def tac():
+    import torchaudio_contrib_b200 as t
+    return t
+
+
+@pytest.fixture(scope="module")
+def oc():
+    from oracle import ref_chain
+    return ref_chain
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------------------ mu-law
+def test_mulaw_golden(tac):
+    g = golden("mulaw.npz")
+    x = dev(g["x"])
+    assert torch.equal(tac.mu_law_encoding(x, 256).cpu(), g["enc256"])
+    assert torch.equal(tac.mu_law_encoding(x, 64).cpu(), g["enc64"])
+    codes = dev(torch.arange(256))
+    dec = tac.mu_law_decoding(codes, 256)
+    assert torch.equal(dec.cpu(), g["dec256"])
+    assert torch.equal(tac.mu_law_encoding(dec, 256).cpu(), g["roundtrip256"])
+    assert torch.equal(tac.mu_law_decoding(dev(torch.arange(64)), 64).cpu(), g["dec64"])
+
+
+@pytest.mark.parametrize("shape", [(1, 100000), (1, 2, 100000), (7,), (3, 1, 1021)])
+def test_mulaw_reference_test_distribution(tac, oc, shape):
+    """tests/test_functional.py:161-203 restated: 2*(randn-0.5) is mostly out of [-1, 1]."""
+    torch.manual_seed(7)
+    w = 2 * (torch.randn(*shape) - 0.5)
+    assert torch.equal(tac.mu_law_encoding(dev(w), 256).cpu(), oc.mu_law_encoding(w, 256))
+    codes = torch.randint(0, 255, (1, 1024))
+    ref = oc.mu_law_decoding(codes.float(), 256)
+    assert torch.equal(tac.mu_law_decoding(dev(codes.float()), 256).cpu(), ref)
+    assert torch.equal(tac.mu_law_decoding(dev(codes), 256).cpu(), ref)
+    assert torch.equal(tac.mu_law_encoding(tac.mu_law_decoding(dev(codes), 256), 256).cpu(), codes)
+
+
+def test_mulaw_modules_and_edges(tac, oc):
+    enc, decm = tac.MuLawEncoding().cuda(), tac.MuLawDecoding().cuda()
+    x = torch.tensor([0.0, -0.0, 1.0, -1.0, 3.0, -3.0, 1e30, -1e30, float("inf"), float("-inf"), float("nan"),
+                      1e-40, 1.3344405e36, 1.3344407e36, 3.4e38])
+    got = enc(dev(x)).cpu()
+    want = oc.mu_law_encoding(x, 256)
+    assert torch.equal(got, want)
+    ints = torch.tensor([-3, 0, 5, 255, 256, 1000])
+    out = decm(dev(ints)).cpu()
+    ref = oc.mu_law_decoding(ints, 256)
+    assert torch.equal(out[1:4], ref[1:4])                       # table range: exact
+    assert pure_rel_err(out, ref) < 1e-5                          # closed form outside the table
+    assert enc(dev(torch.arange(-5, 5, dtype=torch.int32))).dtype == torch.int64
+
+
+@pytest.mark.parametrize("q", [2, 16, 1024, 65536])
+def test_mulaw_other_levels(tac, oc, q):
+    torch.manual_seed(q)
+    x = torch.cat([torch.rand(200000) * 2 - 1, torch.randn(50000) * 3])
+    assert torch.equal(tac.mu_law_encoding(dev(x), q).cpu(), oc.mu_law_encoding(x, q))
+    if q <= 1024:
+        codes = torch.arange(q)
+        assert torch.equal(tac.mu_law_decoding(dev(codes), q).cpu(), oc.mu_law_decoding(codes, q))
+
+
+@pytest.mark.slow
+def test_mulaw_exhaustive_all_floats(tac, oc):
+    """Every one of the 2^32 float bit patterns: CUDA codes == reference codes."""
+    chunk = 1 << 27
+    bad = 0
+    for start in range(0, 1 << 32, chunk):
+        bits = torch.arange(start, start + chunk, dtype=torch.int64)
+        bits = torch.where(bits >= (1 << 31), bits - (1 << 32), bits).to(torch.int32)
+        x = bits.view(torch.float32)
+        got = tac.mu_law_encoding(dev(x), 256).cpu()
+        want = oc.mu_law_encoding(x, 256)
+        bad += int((got != want).sum())
+    assert bad == 0
+
+
+# ------------------------------------------------------------------------------------------ pointwise
+def test_stages_golden(tac):
+    g = golden("stages.npz")
+    z = dev(g["z"])
+    assert rel_err(tac.complex_norm(z, 0.7).cpu(), g["norm_p07"]) < REL
+    mag = tac.complex_norm(z, 1.0)
+    assert rel_err(mag.cpu(), g["norm_p1"]) < 1e-6
+    out = tac.apply_filterbank(dev(g["norm_p1"]), dev(g["fb"])).cpu()
+    assert out.shape == g["filtered"].shape
+    assert rel_err(out, g["filtered"]) < REL
+    db = tac.amplitude_to_db(dev(g["norm_p1"]), ref=2.0, amin=1e-5).cpu()
+    assert (db - g["db"]).abs().max().item() < 1e-3
+
+
+def test_amplitude_db_known_answers(tac):
+    """tests/test_functional.py:144-158: power [1e-6..1e6] <-> dB [-60..60]."""
+    power = torch.tensor([0.000001, 0.0001, 0.1, 1.0, 10.0, 1000000.0])
+    db = torch.tensor([-60.0, -40.0, -10.0, 0.0, 10.0, 60.0])
+    got = tac.amplitude_to_db(dev(power.sqrt()), ref=1.0).cpu()
+    assert (got - db).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 1025, 400, 2), (1025, 400, 2)])
+@pytest.mark.parametrize("power", [1, 2, 0.7])
+def test_complex_norm(tac, shape, power):
+    """tests/test_functional.py:119-128."""
+    torch.manual_seed(3)
+    z = torch.randn(*shape)
+    want = z.pow(2).sum(-1).pow(power / 2)
+    assert (tac.complex_norm(dev(z), power).cpu() - want).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("new_len", [120, 36, 300])
+@pytest.mark.parametrize("shape", [(1, 257, 391), (1, 2, 257, 391)])
+def test_apply_filterbank_dense(tac, oc, shape, new_len):
+    """tests/test_functional.py:131-141 (shape) + values against the oracle matmul."""
+    torch.manual_seed(5)
+    spec, fb = torch.randn(*shape), torch.randn(shape[-2], new_len)
+    got = tac.apply_filterbank(dev(spec), dev(fb)).cpu()
+    want = oc.apply_filterbank(spec, fb)
+    assert got.shape == want.shape and got.shape[-2] == new_len and got.shape[-1] == spec.shape[-1]
+    assert rel_err(got, want) < REL
+
+
+# ------------------------------------------------------------------------------------------ stft
+def test_cfg1_spectrogram_golden(tac):
+    g = golden("cfg1_spectrogram_512_128.npz")
+    m = tac.Spectrogram(fft_length=512, hop_length=128).cuda()
+    out = m(dev(g["x"])).cpu()
+    assert out.shape == (1, 1, 257, 126)
+    assert rel_err(out, g["out"]) < REL
+
+
+def test_stft_reference_config_golden(tac):
+    g = golden("stft_512_256.npz")
+    out = tac.stft(dev(g["x"]), 512, 256, window=dev(torch.hann_window(512))).cpu()
+    assert out.shape == g["out"].shape
+    assert rel_err(out, g["out"]) < REL
+
+
+def test_stft_options_golden(tac):
+    g = golden("stft_options.npz")
+    x = dev(g["x"])
+    cases = {
+        "winlen": dict(fft_length=256, hop_length=64, win_length=200),
+        "normalized": dict(fft_length=256, hop_length=100, normalized=True),
+        "nocenter": dict(fft_length=512, hop_length=128, center=False),
+        "constant": dict(fft_length=256, hop_length=64, pad_mode='constant'),
+        "replicate": dict(fft_length=256, hop_length=64, pad_mode='replicate'),
+        "circular": dict(fft_length=256, hop_length=64, pad_mode='circular'),
+        "twosided": dict(fft_length=128, hop_length=32, onesided=False),
+        "defaulthop": dict(fft_length=1024),
+    }
+    for tag, kw in cases.items():
+        out = tac.STFT(**kw).cuda()(x).cpu()
+        assert out.shape == g["out_" + tag].shape, tag
+        assert rel_err(out, g["out_" + tag]) < REL, tag
+
+
+@pytest.mark.parametrize("shape", [(1, 100000), (1, 2, 100000)])
+def test_stft_vs_f64(tac, shape):
+    """tests/test_functional.py:26-66 with librosa.stft replaced by its float64 restatement."""
+    from oracle import f64_chain
+    torch.manual_seed(11)
+    x = torch.randn(*shape)
+    z = tac.stft(dev(x), fft_length=512, hop_length=256, window=dev(torch.hann_window(512))).cpu()
+    frames = (x.size(-1) + 2 * 256 - 512 + 256) // 256
+    assert z.shape == tuple(x.shape[:-1]) + (257, frames, 2)
+    want = f64_chain.stft(x.numpy(), 512, 256)
+    got = z.numpy()[..., 0] + 1j * z.numpy()[..., 1]
+    assert np.allclose(got, want, atol=1e-4)       # reference asserts 1e-5 on librosa's own fp32 output scale
+    assert np.abs(got - want).max() < 5e-5
+
+
+def test_stft_too_short_raises(tac):
+    """tests/test_functional.py:31: reflect padding needs more samples than the pad."""
+    with pytest.raises(RuntimeError):
+        tac.stft(dev(torch.randn(1, 100)), fft_length=512, hop_length=256)
+
+
+@pytest.mark.parametrize("fft", [2048])
+def test_stft_2048_fast_path(tac, oc, fft):
+    torch.manual_seed(13)
+    for shape in [(3, 1, 16000), (2, 2, 5000), (1, 4099)]:      # odd length -> gather path everywhere
+        x = torch.randn(*shape)
+        got = tac.stft(dev(x), fft, 512).cpu()
+        want = oc.stft(x, fft, 512)
+        assert got.shape == want.shape
+        assert rel_err(got, want) < REL
+    x = torch.randn(2, 16000)
+    xs = dev(torch.randn(2, 16003))[:, 3:]                      # misaligned view -> contiguous copy path
+    assert rel_err(tac.stft(xs, fft, 500).cpu(), oc.stft(xs.cpu(), fft, 500)) < REL
+    sp = tac.Spectrogram(fft, 512, power=2.0).cuda()(dev(x)).cpu()
+    assert rel_err(sp, oc.spectrogram(x, fft, 512, power=2.0)) < REL
+
+
+def test_spectrogram_db_vs_f64(tac):
+    """tests/test_layers.py:55-83 with librosa replaced by the float64 restatement (atol 1e-2)."""
+    from oracle import f64_chain
+    torch.manual_seed(17)
+    for shape in [(1, 100000), (1, 2, 100000)]:
+        x = torch.randn(*shape)
+        model = torch.nn.Sequential(*tac.Spectrogram(512, hop_length=256, window=torch.hann_window(512)),
+                                    tac.AmplitudeToDb(ref=1.0, amin=1e-7)).cuda()
+        got = model(dev(x)).cpu().numpy()
+        want = f64_chain.power_to_db(np.abs(f64_chain.stft(x.numpy(), 512, 256)) ** 2, 1.0, 1e-7)
+        assert np.allclose(got, want, atol=1e-2), np.abs(got - want).max()
+
+
+# ------------------------------------------------------------------------------------------ mel
+def test_mel_golden_16k(tac):
+    g = golden("mel_16k_2048_512.npz")
+    m = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512).cuda()
+    out = m(dev(g["x"])).cpu()
+    assert out.shape == g["out"].shape == (2, 1, 128, 32)
+    assert pure_rel_err(out, g["out"]) < REL
+    # unfused, child by child through a plain nn.Sequential: same numbers
+    plain = torch.nn.Sequential(*m)
+    assert pure_rel_err(plain(dev(g["x"])).cpu(), g["out"]) < REL
+
+
+def test_meldb_golden_48k(tac):
+    g = golden("meldb_48k_2048_512.npz")
+    m = tac.Sequential(*tac.Melspectrogram(num_mels=128, sample_rate=48000, fft_length=2048, hop_length=512),
+                       tac.AmplitudeToDb()).cuda()
+    out = m(dev(g["x"])).cpu()
+    assert out.shape == g["out"].shape
+    assert (out - g["out"]).abs().max().item() < 1e-3
+    plain = torch.nn.Sequential(*m)
+    assert (plain(dev(g["x"])).cpu() - g["out"]).abs().max().item() < 1e-3
+
+
+def test_mel_sweep_golden(tac):
+    g = golden("mel_sweep_16k.npz")
+    x = dev(g["x"])
+    for fft in (256, 512, 1024, 2048, 4096):
+        m = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=fft, hop_length=fft // 4).cuda()
+        out = m(x).cpu()
+        want = g["out_%d" % fft]
+        assert out.shape == want.shape
+        assert rel_err(out, want) < REL, fft
+        nz = want > 0
+        assert ((out[nz] - want[nz]).abs() / want[nz]).max().item() < REL, fft
+        assert (out[~nz] == 0).all()          # all-zero bands (fft 256 has 13) stay exactly zero
+
+
+@pytest.mark.parametrize("shape,sr", [((8, 1, 160000), 16000), ((2, 2, 48000), 48000), ((3, 50000), 22050)])
+def test_mel_vs_oracle_larger(tac, oc, shape, sr):
+    torch.manual_seed(19)
+    x = torch.randn(*shape)
+    m = tac.Melspectrogram(num_mels=128, sample_rate=sr, fft_length=2048, hop_length=512).cuda()
+    got = m(dev(x)).cpu()
+    want = oc.melspectrogram(x, 128, sr, fft_length=2048, hop_length=512)
+    assert got.shape == want.shape
+    assert pure_rel_err(got, want) < REL
+
+
+def test_mel_nonrandom_signals(tac, oc):
+    """uniform noise and sine+noise: near-zero bins and the amin clamp get exercised."""
+    torch.manual_seed(23)
+    t = torch.arange(64000) / 16000.0
+    sig = torch.stack([0.5 * torch.sin(2 * np.pi * 440 * t) + 1e-3 * torch.randn(64000),
+                       torch.rand(64000) * 2 - 1, torch.zeros(64000)]).unsqueeze(1)
+    m = tac.Sequential(*tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512),
+                       tac.AmplitudeToDb()).cuda()
+    got = m(dev(sig)).cpu()
+    want = oc.melspectrogram(sig, 128, 16000, to_db=True, fft_length=2048, hop_length=512)
+    assert (got - want).abs().max().item() < 2e-3
+    assert (got[2] == -70.0).all()
+
+
+def test_full_size_properties_cfg2(tac):
+    """BASELINE config 2 at full size: linearity and batch-independence (size-independent checks)."""
+    torch.manual_seed(29)
+    x = torch.randn(64, 1, 160000, device="cuda")
+    m = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512).cuda()
+    y = m(x)
+    assert y.shape == (64, 1, 128, 313)
+    assert torch.isfinite(y).all() and (y >= 0).all()
+    y2 = m(2.0 * x)
+    assert pure_rel_err(y2.cpu(), (4.0 * y).cpu()) < 1e-5           # power spectrum: scale^2
+    ysub = m(x[5:9])
+    assert torch.equal(ysub, y[5:9])                                 # a sequence does not see its neighbours
+    assert torch.equal(m(x), y)                                      # deterministic
+
+
+def test_host_pipeline_cfg1(tac):
+    g = golden("cfg1_spectrogram_512_128.npz")
+    hp = tac.HostPipeline(512, 128, power=1.0)
+    out = hp(g["x"])
+    assert rel_err(out, g["out"]) < REL
+    g2 = golden("meldb_48k_2048_512.npz")
+    fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=48000).get_filterbank()
+    hp2 = tac.HostPipeline(2048, 512, power=2.0, filterbank=fb, to_db=True)
+    assert (hp2(g2["x"]) - g2["out"]).abs().max().item() < 1e-3
+
+
+def test_melspectrogram_stretch_shapes(tac):
+    """tests/test_layers.py:86-106 without TimeStretch (out of scope): hand-composed chain on (4, T)."""
+    x = torch.randn(4, 100000, device="cuda")
+    fb = tac.MelFilterbank(num_freqs=257, num_mels=128, max_freq=1.0).get_filterbank()
+    model = torch.nn.Sequential(tac.STFT(512, hop_length=256), tac.ComplexNorm(power=2.0), tac.ApplyFilterbank(fb)).cuda()
+    y = model(x)
+    assert y.shape == (4, 128, (100000 + 512 - 512 + 256) // 256)

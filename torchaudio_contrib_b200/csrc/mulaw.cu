@@ -1,0 +1,186 @@
+// K4 / K5: mu-law companding (reference: torchaudio_contrib/functional.py:317-354).
+//
+// Both kernels are pure streaming kernels: 12 algorithmic bytes per sample (fp32 in + int64 out,
+// or int64 in + fp32 out), HBM-bound.  Bit-exactness with the reference's fp32 torch chain is
+// obtained by table, not by re-deriving its transcendental functions:
+//
+//  encode  The reference quantiser  idx(x) = trunc(((s*log1p(mu|x|)/log1p(mu) + 1)/2)*mu + 0.5)
+//          is monotone in x (checked exhaustively over all 2^32 floats), so it is fully
+//          described by its decision levels thr[k] = min{x : idx(x) >= k}.  The kernel computes a
+//          cheap estimate k0 = floor(v - 0.5) with the hardware lg2 and settles the last step with
+//          ONE table compare:  idx = k0 + (x >= thr[k0 + 1]).  The estimate only has to be within
+//          +-0.5 of the real-valued quantiser input, so the approximation error of lg2.approx
+//          (1e-6) is irrelevant to the result.
+//  decode  Codes 0..n_quantize-1 index a lookup table of the reference's decoded values; anything
+//          else goes through the closed form.
+//
+// The tables are produced by the host side of the package from the reference formula
+// (torchaudio_contrib_b200/_mulaw_tables.py) and passed in as device pointers.
+#include "tac_common.cuh"
+
+namespace tac {
+
+constexpr int kMuLawThreads = 256;
+constexpr int kMuLawSmemTableMax = 12288;   // floats (48 KB) -- n_quantize = 256 needs 4081
+
+template <bool kSmemTable>
+__global__ void __launch_bounds__(kMuLawThreads)
+mulaw_encode_kernel(const float* __restrict__ x, int64_t n, long long* __restrict__ out,
+                    const float* __restrict__ thr, int n_thr, int idx_min, float x_limit,
+                    float mu, float half_mu_over_log2) {
+  extern __shared__ float s_thr[];
+  const float* table = thr;
+  if (kSmemTable) {
+    for (int i = threadIdx.x; i < n_thr; i += kMuLawThreads) s_thr[i] = thr[i];
+    __syncthreads();
+    table = s_thr;
+  }
+  const float half_mu = 0.5f * mu;
+  const int j_max = n_thr - 1;
+
+  auto encode_one = [&](float v) -> long long {
+    const float a = fabsf(v);
+    if (!(a <= x_limit)) return (long long)0x8000000000000000ull;     // overflow / NaN in the reference
+    // real-valued quantiser input minus 0.5: mu/2 * (1 + sign * log(1+mu|x|)/log(1+mu))
+    const float l = __log2f(fmaf(mu, a, 1.0f)) * half_mu_over_log2;
+    const float est = half_mu + copysignf(l, v);
+    // the reference truncates toward zero: floor for v >= 0, ceil for v < 0 (only reached for x < -1)
+    int j = __float2int_rd(est) + (est < -0.5f ? 2 : 1) - idx_min;     // candidate index k0 + 1
+    j = max(0, min(j, j_max));
+    const float t = kSmemTable ? table[j] : __ldg(table + j);
+    return (long long)(idx_min + j - 1 + (v >= t ? 1 : 0));
+  };
+
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * kMuLawThreads;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n4; i += stride) {
+      const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
+      longlong2 lo, hi;
+      lo.x = encode_one(v.x);
+      lo.y = encode_one(v.y);
+      hi.x = encode_one(v.z);
+      hi.y = encode_one(v.w);
+      longlong2* o = reinterpret_cast<longlong2*>(out) + 2 * i;
+      __stcs(o, lo);
+      __stcs(o + 1, hi);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
+      out[i] = encode_one(x[i]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
+      out[i] = encode_one(x[i]);
+  }
+}
+
+__device__ __forceinline__ float mulaw_expand_closed_form(float code, float mu, float log1p_mu) {
+  // functional.py:352-353, evaluated with the device exp (only reached for codes outside the table)
+  const float y = (code / mu) * 2.0f - 1.0f;
+  const float m = (expf(fabsf(y) * log1p_mu) - 1.0f) / mu;
+  const float s = (y > 0.0f) ? 1.0f : ((y < 0.0f) ? -1.0f : 0.0f);
+  return s * m;
+}
+
+template <typename CodeT>
+__global__ void __launch_bounds__(kMuLawThreads)
+mulaw_decode_kernel(const CodeT* __restrict__ codes, int64_t n, float* __restrict__ out,
+                    const float* __restrict__ lut, int n_quantize, float mu, float log1p_mu) {
+  extern __shared__ float s_lut[];
+  for (int i = threadIdx.x; i < n_quantize; i += kMuLawThreads) s_lut[i] = lut[i];
+  __syncthreads();
+
+  auto decode_one = [&](CodeT c) -> float {
+    if constexpr (sizeof(CodeT) == 8) {
+      const long long k = (long long)c;
+      if (k >= 0 && k < n_quantize) return s_lut[(int)k];
+      return mulaw_expand_closed_form((float)k, mu, log1p_mu);
+    } else {
+      const float f = (float)c;
+      const int k = __float2int_rz(f);
+      if (f >= 0.0f && f < (float)n_quantize && (float)k == f) return s_lut[k];
+      return mulaw_expand_closed_form(f, mu, log1p_mu);
+    }
+  };
+
+  const int64_t stride = (int64_t)gridDim.x * kMuLawThreads;
+  const int64_t n4 = n >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(codes) & 31) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n4; i += stride) {
+      CodeT c[4];
+      if constexpr (sizeof(CodeT) == 8) {
+        const longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(codes) + 2 * i);
+        const longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(codes) + 2 * i + 1);
+        c[0] = (CodeT)a.x; c[1] = (CodeT)a.y; c[2] = (CodeT)b.x; c[3] = (CodeT)b.y;
+      } else {
+        const float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(codes) + i);
+        c[0] = (CodeT)a.x; c[1] = (CodeT)a.y; c[2] = (CodeT)a.z; c[3] = (CodeT)a.w;
+      }
+      float4 r;
+      r.x = decode_one(c[0]); r.y = decode_one(c[1]); r.z = decode_one(c[2]); r.w = decode_one(c[3]);
+      __stcs(reinterpret_cast<float4*>(out) + i, r);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
+      out[i] = decode_one(codes[i]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
+      out[i] = decode_one(codes[i]);
+  }
+}
+
+static int streaming_grid(int64_t n_vec) {
+  const int64_t want = (n_vec + kMuLawThreads - 1) / kMuLawThreads;
+  const int64_t cap = (int64_t)sm_count() * 8;          // 8 x 256 threads resident per SM
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace tac
+
+extern "C" int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantize, const float* thresholds_dev,
+                                        int n_thresholds, int idx_min, float x_limit, int64_t* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0 && n_quantize >= 2, TAC_ERR_INVALID, "mulaw_encode: n=%lld n_quantize=%d", (long long)n, n_quantize);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(x && out && thresholds_dev && n_thresholds >= 1, TAC_ERR_INVALID, "mulaw_encode: null pointer / empty table");
+  const float mu = (float)(n_quantize - 1);
+  const float half_mu_over_log2 = (float)(0.5 * (double)mu / log2(1.0 + (double)mu));
+  const int grid = streaming_grid((n + 3) / 4);
+  if (n_thresholds <= kMuLawSmemTableMax) {
+    const size_t smem = (size_t)n_thresholds * sizeof(float);
+    mulaw_encode_kernel<true><<<grid, kMuLawThreads, smem, as_stream(stream)>>>(
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
+  } else {
+    mulaw_encode_kernel<false><<<grid, kMuLawThreads, 0, as_stream(stream)>>>(
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
+  }
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+template <typename CodeT>
+static int launch_decode(const CodeT* codes, int64_t n, int n_quantize, const float* lut_dev, float* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0 && n_quantize >= 2, TAC_ERR_INVALID, "mulaw_decode: n=%lld n_quantize=%d", (long long)n, n_quantize);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(codes && out && lut_dev, TAC_ERR_INVALID, "mulaw_decode: null pointer");
+  TAC_REQUIRE(n_quantize <= kMuLawSmemTableMax, TAC_ERR_UNSUPPORTED, "mulaw_decode: n_quantize=%d exceeds the %d-entry table",
+              n_quantize, kMuLawSmemTableMax);
+  const float mu = (float)(n_quantize - 1);
+  const float log1p_mu = (float)log1p((double)mu);
+  const int grid = streaming_grid((n + 3) / 4);
+  mulaw_decode_kernel<CodeT><<<grid, kMuLawThreads, (size_t)n_quantize * sizeof(float), as_stream(stream)>>>(
+      codes, n, out, lut_dev, n_quantize, mu, log1p_mu);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_mulaw_decode_i64_f32(const int64_t* codes, int64_t n, int n_quantize, const float* lut_dev,
+                                        float* out, void* stream) {
+  return launch_decode<long long>(reinterpret_cast<const long long*>(codes), n, n_quantize, lut_dev, out, stream);
+}
+
+extern "C" int tac_mulaw_decode_f32_f32(const float* codes, int64_t n, int n_quantize, const float* lut_dev,
+                                        float* out, void* stream) {
+  return launch_decode<float>(codes, n, n_quantize, lut_dev, out, stream);
+}

@@ -1,0 +1,222 @@
+// Pipeline drivers.
+//
+//  tac_melspec_f32      device pointers: STFT+|.|^p (stft.cu) -> frame-major power rows in an L2-sized
+//                       workspace -> tensor-core filterbank + dB (melbank.cu), slice by slice so that the
+//                       rows written by one kernel are read by the next while still L2 resident.
+//  tac_pipeline_*       host pointers: H2D -> the same two kernels -> D2H in double-buffered slices on
+//                       two streams, so copies in both directions overlap compute.
+#include <stdlib.h>
+
+#include "stft_params.cuh"
+#include "tac_common.cuh"
+
+namespace tac {
+
+struct MelbankParams;   // melbank.cu
+int launch_melbank_rows(const float* rows, int64_t n_rows, int64_t g_base, int64_t frames, int n_bins, int kpad,
+                        const void* plan_dev, int n_bands, int to_db, float ref, float amin, float* out,
+                        cudaStream_t stream);
+
+// rows per slice: a multiple of (SMs x 16 warps) so that the STFT kernel's last wave is full, sized so the
+// slice (rows x kpad x 4 B) stays well inside the 126 MB L2 together with the input it is computed from.
+static int64_t slice_rows(int kpad) {
+  static int64_t override_rows = -1;
+  if (override_rows < 0) {
+    const char* e = getenv("TAC_MELSPEC_SLICE_ROWS");
+    override_rows = e ? atoll(e) : 0;
+  }
+  if (override_rows > 0) return override_rows;
+  const int64_t wave = (int64_t)sm_count() * 16;
+  const int64_t budget = (int64_t)48 << 20;                  // bytes of power rows per slice
+  int64_t waves = budget / (wave * kpad * 4);
+  if (waves < 1) waves = 1;
+  return waves * wave;
+}
+
+static int run_melspec(StftParams sp, float power, const void* plan_dev, int n_bands, int to_db, float ref, float amin,
+                       float* workspace, int64_t workspace_bytes, float* out, cudaStream_t stream) {
+  const int64_t total = sp.n_seq * sp.frames;
+  if (total == 0) return TAC_OK;
+  const int64_t row_bytes = (int64_t)sp.kpad * 4;
+  int64_t rows = slice_rows(sp.kpad);
+  if (rows > total) rows = total;
+  if (rows * row_bytes > workspace_bytes) rows = workspace_bytes / row_bytes;
+  TAC_REQUIRE(rows >= 1 && workspace, TAC_ERR_WORKSPACE, "melspec: workspace of %lld bytes cannot hold one row of %lld bytes",
+              (long long)workspace_bytes, (long long)row_bytes);
+  sp.out = workspace;
+  sp.out_mode = OUT_POWER_ROWS;
+  sp.power = power;
+  sp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  for (int64_t g0 = 0; g0 < total; g0 += rows) {
+    sp.g0 = g0;
+    sp.g1 = (g0 + rows < total) ? g0 + rows : total;
+    int rc = launch_stft(sp, stream);
+    if (rc != TAC_OK) return rc;
+    rc = launch_melbank_rows(workspace, sp.g1 - sp.g0, g0, sp.frames, sp.bins, sp.kpad, plan_dev, n_bands, to_db, ref, amin,
+                             out, stream);
+    if (rc != TAC_OK) return rc;
+  }
+  return TAC_OK;
+}
+
+}  // namespace tac
+
+extern "C" int64_t tac_melspec_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
+  using namespace tac;
+  if (n_fft <= 0) return 0;
+  const int kpad = kpad_for_bins(n_fft / 2 + 1);
+  const int64_t total = n_seq * tac_stft_num_frames(n_samples, n_fft, hop, center);
+  int64_t rows = slice_rows(kpad);
+  if (rows > total) rows = total;
+  if (rows < 1) rows = 1;
+  return rows * kpad * 4;
+}
+
+extern "C" int tac_melspec_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
+                               int n_fft, int hop, int center, int pad_mode, int normalized, float power,
+                               const void* plan_dev, int n_bands, int to_db, float ref, float amin, void* workspace,
+                               int64_t workspace_bytes, float* out, void* stream) {
+  using namespace tac;
+  StftParams sp;
+  const int rc = fill_stft_params(sp, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(plan_dev && n_bands > 0, TAC_ERR_INVALID, "melspec: missing filterbank plan");
+  TAC_REQUIRE(out || sp.g1 == 0, TAC_ERR_INVALID, "melspec: null output pointer");
+  return run_melspec(sp, power, plan_dev, n_bands, to_db, ref, amin, static_cast<float*>(workspace), workspace_bytes, out,
+                     as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline
+// ---------------------------------------------------------------------------------------------
+struct tac_pipeline {
+  tac_pipeline_config cfg;
+  int device;
+  float* d_window;
+  void* d_plan;
+  cudaStream_t stream[2];
+  float* d_x[2];
+  float* d_out[2];
+  float* d_ws[2];
+  int64_t cap_x, cap_out, cap_ws;       // bytes per slot
+};
+
+static int pipeline_reserve(tac_pipeline* p, int64_t x_bytes, int64_t out_bytes, int64_t ws_bytes) {
+  using namespace tac;
+  for (int i = 0; i < 2; ++i) {
+    if (x_bytes > p->cap_x) {
+      if (p->d_x[i]) TAC_CUDA_OK(cudaFree(p->d_x[i]));
+      p->d_x[i] = nullptr;
+      TAC_CUDA_OK(cudaMalloc(&p->d_x[i], (size_t)x_bytes));
+    }
+    if (out_bytes > p->cap_out) {
+      if (p->d_out[i]) TAC_CUDA_OK(cudaFree(p->d_out[i]));
+      p->d_out[i] = nullptr;
+      TAC_CUDA_OK(cudaMalloc(&p->d_out[i], (size_t)out_bytes));
+    }
+    if (ws_bytes > p->cap_ws) {
+      if (p->d_ws[i]) TAC_CUDA_OK(cudaFree(p->d_ws[i]));
+      p->d_ws[i] = nullptr;
+      TAC_CUDA_OK(cudaMalloc(&p->d_ws[i], (size_t)ws_bytes));
+    }
+  }
+  if (x_bytes > p->cap_x) p->cap_x = x_bytes;
+  if (out_bytes > p->cap_out) p->cap_out = out_bytes;
+  if (ws_bytes > p->cap_ws) p->cap_ws = ws_bytes;
+  return TAC_OK;
+}
+
+extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* window_host, const float* fb_host,
+                                   tac_pipeline** out) {
+  using namespace tac;
+  TAC_REQUIRE(cfg && window_host && out, TAC_ERR_INVALID, "pipeline_create: null pointer");
+  TAC_REQUIRE(is_pow2(cfg->n_fft) && cfg->n_fft >= 32 && cfg->n_fft <= 8192, TAC_ERR_UNSUPPORTED,
+              "pipeline_create: n_fft=%d is not a power of two in [32, 8192]", cfg->n_fft);
+  TAC_REQUIRE(cfg->n_bands == 0 || (fb_host && cfg->n_bins == cfg->n_fft / 2 + 1), TAC_ERR_INVALID,
+              "pipeline_create: filterbank must have n_fft/2+1 = %d rows (got %d)", cfg->n_fft / 2 + 1, cfg->n_bins);
+  tac_pipeline* p = static_cast<tac_pipeline*>(calloc(1, sizeof(tac_pipeline)));
+  TAC_REQUIRE(p, TAC_ERR_INVALID, "pipeline_create: out of host memory");
+  p->cfg = *cfg;
+  TAC_CUDA_OK(cudaGetDevice(&p->device));
+  TAC_CUDA_OK(cudaMalloc(&p->d_window, sizeof(float) * cfg->n_fft));
+  TAC_CUDA_OK(cudaMemcpy(p->d_window, window_host, sizeof(float) * cfg->n_fft, cudaMemcpyHostToDevice));
+  if (cfg->n_bands > 0) {
+    const int64_t cap = tac_fbplan_bytes(cfg->n_bins, cfg->n_bands);
+    void* host = malloc((size_t)cap);
+    TAC_REQUIRE(host, TAC_ERR_INVALID, "pipeline_create: out of host memory");
+    int64_t used = 0;
+    int rc = tac_fbplan_build_host(fb_host, cfg->n_bins, cfg->n_bands, host, cap, &used);
+    if (rc == TAC_OK) {
+      cudaError_t e = cudaMalloc(&p->d_plan, (size_t)used);
+      if (e == cudaSuccess) e = cudaMemcpy(p->d_plan, host, (size_t)used, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) rc = fail(TAC_ERR_CUDA, "pipeline_create: plan upload failed: %s", cudaGetErrorString(e));
+    }
+    free(host);
+    if (rc != TAC_OK) return rc;
+  }
+  for (int i = 0; i < 2; ++i) TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->stream[i], cudaStreamNonBlocking));
+  *out = p;
+  return TAC_OK;
+}
+
+extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64_t n_seq, int64_t n_samples,
+                                     float* out_host) {
+  using namespace tac;
+  TAC_REQUIRE(p && x_host && out_host, TAC_ERR_INVALID, "pipeline_run: null pointer");
+  TAC_REQUIRE(n_seq >= 0 && n_samples > 0, TAC_ERR_INVALID, "pipeline_run: bad shape");
+  if (n_seq == 0) return TAC_OK;
+  const tac_pipeline_config& c = p->cfg;
+  TAC_CUDA_OK(cudaSetDevice(p->device));
+  const int64_t frames = tac_stft_num_frames(n_samples, c.n_fft, c.hop, c.center);
+  const int out_rows = c.n_bands > 0 ? c.n_bands : c.n_fft / 2 + 1;
+  // slice = a few MB of input so that H2D(i+1), compute(i) and D2H(i-1) overlap
+  int64_t per = ((int64_t)4 << 20) / (n_samples * 4);
+  if (per < 1) per = 1;
+  if (per > n_seq) per = n_seq;
+  const int64_t x_bytes = per * n_samples * 4;
+  const int64_t o_bytes = per * out_rows * frames * 4;
+  const int64_t ws_bytes = c.n_bands > 0 ? tac_melspec_workspace_bytes(per, n_samples, c.n_fft, c.hop, c.center) : 0;
+  int rc = pipeline_reserve(p, x_bytes, o_bytes, ws_bytes);
+  if (rc != TAC_OK) return rc;
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n_seq; s0 += per, slot ^= 1) {
+    const int64_t ns = (s0 + per <= n_seq) ? per : n_seq - s0;
+    cudaStream_t st = p->stream[slot];
+    TAC_CUDA_OK(cudaMemcpyAsync(p->d_x[slot], x_host + s0 * n_samples, (size_t)(ns * n_samples * 4), cudaMemcpyHostToDevice, st));
+    StftParams sp;
+    rc = fill_stft_params(sp, p->d_x[slot], ns, n_samples, n_samples, p->d_window, c.n_fft, c.hop, c.center, c.pad_mode,
+                          c.normalized, 1);
+    if (rc != TAC_OK) return rc;
+    if (c.n_bands > 0) {
+      rc = run_melspec(sp, c.power, p->d_plan, c.n_bands, c.to_db, c.ref, c.amin, p->d_ws[slot], p->cap_ws, p->d_out[slot], st);
+    } else {
+      sp.out = p->d_out[slot];
+      sp.out_mode = OUT_POWER_PUBLIC;
+      sp.power = c.power;
+      sp.power_mode = c.power == 2.0f ? 2 : (c.power == 1.0f ? 1 : 0);
+      rc = launch_stft(sp, st);
+    }
+    if (rc != TAC_OK) return rc;
+    TAC_CUDA_OK(cudaMemcpyAsync(out_host + s0 * out_rows * frames, p->d_out[slot], (size_t)(ns * out_rows * frames * 4),
+                                cudaMemcpyDeviceToHost, st));
+  }
+  TAC_CUDA_OK(cudaStreamSynchronize(p->stream[0]));
+  TAC_CUDA_OK(cudaStreamSynchronize(p->stream[1]));
+  return TAC_OK;
+}
+
+extern "C" int tac_pipeline_destroy(tac_pipeline* p) {
+  using namespace tac;
+  if (!p) return TAC_OK;
+  cudaSetDevice(p->device);
+  for (int i = 0; i < 2; ++i) {
+    if (p->stream[i]) cudaStreamDestroy(p->stream[i]);
+    if (p->d_x[i]) cudaFree(p->d_x[i]);
+    if (p->d_out[i]) cudaFree(p->d_out[i]);
+    if (p->d_ws[i]) cudaFree(p->d_ws[i]);
+  }
+  if (p->d_window) cudaFree(p->d_window);
+  if (p->d_plan) cudaFree(p->d_plan);
+  free(p);
+  return TAC_OK;
+}

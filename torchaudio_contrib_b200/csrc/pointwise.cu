@@ -1,0 +1,109 @@
+// Stand-alone elementwise stages, used when the modules are composed by hand (e.g. with a
+// TimeStretch in between, reference tests/test_layers.py:98-101).  In the Spectrogram /
+// Melspectrogram pipelines these are fused into the STFT epilogue / the filterbank epilogue.
+//
+//   complex_norm     functional.py:116-128   (n, 2) -> (n):  sqrt(re^2 + im^2), then .pow(power)
+//   amplitude_to_db  functional.py:277-296   10 * (log10(max(x^2, amin)) - log10(ref))
+//
+// Pure streaming: 12 B / element (complex_norm) and 8 B / element (amplitude_to_db).
+#include "tac_common.cuh"
+
+namespace tac {
+
+constexpr int kPwThreads = 256;
+
+// same evaluation order as the reference: norm first, power second (quirk 2 in SURVEY section 0)
+__device__ __forceinline__ float norm_then_pow(float re, float im, float power, int mode) {
+  const float mag = sqrtf(fmaf(re, re, im * im));
+  if (mode == 1) return mag;                 // power == 1
+  if (mode == 2) return mag * mag;           // torch.pow(x, 2.) == x * x
+  if (mode == 3) return sqrtf(mag);          // power == 0.5
+  return powf(mag, power);
+}
+
+static inline int power_mode(float power) {
+  return power == 1.0f ? 1 : (power == 2.0f ? 2 : (power == 0.5f ? 3 : 0));
+}
+
+__global__ void __launch_bounds__(kPwThreads)
+complex_norm_kernel(const float2* __restrict__ z, int64_t n, float power, int mode, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kPwThreads;
+  const int64_t n2 = n >> 1;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(z) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n2; i += stride) {
+      const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(z) + i);
+      float2 r;
+      r.x = norm_then_pow(v.x, v.y, power, mode);
+      r.y = norm_then_pow(v.z, v.w, power, mode);
+      __stcs(reinterpret_cast<float2*>(out) + i, r);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const float2 v = z[n - 1];
+      out[n - 1] = norm_then_pow(v.x, v.y, power, mode);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride) {
+      const float2 v = z[i];
+      out[i] = norm_then_pow(v.x, v.y, power, mode);
+    }
+  }
+}
+
+__device__ __forceinline__ float to_db(float x, float amin, float log10_ref) {
+  float s = x * x;
+  s = (s < amin) ? amin : s;                 // torch.clamp(min=): NaN stays NaN
+  return 10.0f * (log10f(s) - log10_ref);
+}
+
+__global__ void __launch_bounds__(kPwThreads)
+amplitude_to_db_kernel(const float* __restrict__ x, int64_t n, float amin, float log10_ref, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kPwThreads;
+  const int64_t n4 = n >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n4; i += stride) {
+      const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
+      float4 r;
+      r.x = to_db(v.x, amin, log10_ref);
+      r.y = to_db(v.y, amin, log10_ref);
+      r.z = to_db(v.z, amin, log10_ref);
+      r.w = to_db(v.w, amin, log10_ref);
+      __stcs(reinterpret_cast<float4*>(out) + i, r);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride)
+      out[i] = to_db(x[i], amin, log10_ref);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride)
+      out[i] = to_db(x[i], amin, log10_ref);
+  }
+}
+
+static int pw_grid(int64_t n_vec) {
+  const int64_t want = (n_vec + kPwThreads - 1) / kPwThreads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace tac
+
+extern "C" int tac_complex_norm_f32(const float* z, int64_t n, float power, float* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "complex_norm: n=%lld", (long long)n);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(z && out, TAC_ERR_INVALID, "complex_norm: null pointer");
+  complex_norm_kernel<<<pw_grid((n + 1) / 2), kPwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(z), n, power, power_mode(power), out);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_amplitude_to_db_f32(const float* x, int64_t n, float ref, float amin, float* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "amplitude_to_db: n=%lld", (long long)n);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(x && out, TAC_ERR_INVALID, "amplitude_to_db: null pointer");
+  amplitude_to_db_kernel<<<pw_grid((n + 3) / 4), kPwThreads, 0, as_stream(stream)>>>(x, n, amin, log10f(ref), out);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}

@@ -1,0 +1,393 @@
+// K1: framing + padding + window + real FFT (+ optional |.|^p epilogue).
+// Replaces the torch.stft call at reference functional.py:99-107 (and complex_norm :126-128 when
+// the caller is the Spectrogram / Melspectrogram pipeline).
+//
+// Two kernels:
+//
+//  stft2048_kernel   n_fft = 2048, onesided.  One warp owns one frame at a time.  The frame's 2048
+//      samples (8 KB, contiguous in HBM) arrive in the warp's private shared-memory slab through a
+//      1-D bulk async copy (TMA engine, mbarrier completion); frames that touch the padding, or
+//      unaligned inputs, are gathered with plain loads instead.  The real FFT is computed as a
+//      1024-point complex FFT of z[n] = x[2n] + i x[2n+1], factored 32 x 32: each lane runs a
+//      32-point FFT in registers, the 32x32 transpose goes through the same slab (row stride 33
+//      -> conflict free), each lane runs the second 32-point FFT, and the real-FFT untangling
+//      X[k] = E + W^k O pairs bin k with bin 1024-k by one shuffle exchange.  The slab is free
+//      again after the transpose read, so the next frame's bulk copy overlaps the second half.
+//  stft_generic_kernel   any power-of-two n_fft in [32, 8192], any padding mode, one- or two-sided:
+//      one CTA per frame, radix-2 Stockham passes through shared memory.  Correct-first fallback.
+//
+// Output modes (OUT_*): the public layouts of the reference, and the frame-major power rows that
+// feed the filterbank kernel (melbank.cu) inside the Melspectrogram pipeline.
+#include "fft_regs.cuh"
+#include "stft_params.cuh"
+#include "tac_common.cuh"
+
+namespace tac {
+
+// ---------------------------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int64_t s, int64_t n, int pad_mode) {
+  if (s >= 0 && s < n) return __ldg(row + s);
+  switch (pad_mode) {
+    case TAC_PAD_REFLECT:
+      s = (s < 0) ? -s : 2 * (n - 1) - s;
+      break;
+    case TAC_PAD_REPLICATE:
+      s = (s < 0) ? 0 : n - 1;
+      break;
+    case TAC_PAD_CIRCULAR:
+      s = (s < 0) ? s + n : s - n;
+      break;
+    default:
+      return 0.0f;
+  }
+  return (s >= 0 && s < n) ? __ldg(row + s) : 0.0f;
+}
+
+__device__ __forceinline__ float spectral_power(float re, float im, float power, int mode) {
+  const float s = fmaf(re, re, im * im);
+  if (mode == 2) return s;
+  if (mode == 1) return sqrtf(s);
+  return s > 0.0f ? powf(s, 0.5f * power) : (power == 0.0f ? 1.0f : 0.0f);
+}
+
+__device__ __forceinline__ void emit_bin(const StftParams& p, int64_t seq, int64_t t, int64_t row, int k,
+                                         float re, float im) {
+  if (p.out_mode == OUT_POWER_ROWS) {
+    p.out[row * p.kpad + k] = spectral_power(re, im, p.power, p.power_mode);
+  } else if (p.out_mode == OUT_POWER_PUBLIC) {
+    p.out[(seq * p.bins + k) * p.frames + t] = spectral_power(re, im, p.power, p.power_mode);
+  } else {
+    reinterpret_cast<float2*>(p.out)[(seq * p.bins + k) * p.frames + t] = make_float2(re, im);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast path: n_fft = 2048
+// ---------------------------------------------------------------------------------------------
+constexpr int kFastWarps = 16;
+constexpr int kFastThreads = kFastWarps * 32;
+constexpr int kSlabComplex = 32 * 33;                        // transposition slab, row stride 33
+constexpr size_t kFastSmemBytes = 3 * 1024 * sizeof(float2)  // window pairs, tw1, tw2
+                                  + kFastWarps * sizeof(uint64_t) + kFastWarps * kSlabComplex * sizeof(float2);
+
+__global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_win = reinterpret_cast<float2*>(smem_raw);      // [1024]   (w[2n], w[2n+1]) * 0.5 * scale
+  float2* s_tw1 = s_win + 1024;                             // [k2][n1] W_1024^(n1 k2)
+  float2* s_tw2 = s_tw1 + 1024;                             // [k1][l]  W_2048^(32 k1 + l)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + 1024);
+  float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < 1024; i += kFastThreads) {
+    const float g = 0.5f * p.scale;
+    s_win[i] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
+    float sn, cs;
+    sincospif(-2.0f * (float)((i & 31) * (i >> 5)) / 1024.0f, &sn, &cs);
+    s_tw1[i] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)i / 2048.0f, &sn, &cs);
+    s_tw2[i] = make_float2(cs, sn);
+  }
+  uint64_t* bar = s_bar + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  float2* slab = s_slab + warp * kSlabComplex;
+  float* slab_f = reinterpret_cast<float*>(slab);
+  const int64_t step = (int64_t)gridDim.x * kFastWarps;
+  uint32_t parity = 0;
+
+  // a frame can use the bulk copy when it lies inside the sequence and everything is 16B aligned
+  auto frame_origin = [&](int64_t g, int64_t& seq, int64_t& t, int64_t& start) {
+    seq = g / p.frames;
+    t = g - seq * p.frames;
+    start = t * p.hop - p.pad;
+  };
+  auto stage_frame = [&](int64_t g) -> bool {    // returns true when a bulk copy is in flight
+    int64_t seq, t, start;
+    frame_origin(g, seq, t, start);
+    const float* row = p.x + seq * p.seq_stride;
+    const bool bulk = p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples;
+    if (bulk) {
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, 2048 * sizeof(float));
+        bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);
+      }
+    } else {
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const int j = lane + 32 * i;
+        slab_f[j] = fetch_padded(row, start + j, p.n_samples, p.pad_mode);
+      }
+    }
+    return bulk;
+  };
+
+  int64_t g = p.g0 + (int64_t)blockIdx.x * kFastWarps + warp;
+  bool in_flight = false;
+  if (g < p.g1) in_flight = stage_frame(g);
+
+  for (; g < p.g1; g += step) {
+    if (in_flight) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    } else {
+      __syncwarp();
+    }
+
+    // ---- pass 1: lane = n1, register r <-> n = n1 + 32 r --------------------------------------
+    float2 v[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float2 xs = slab[lane + 32 * r];
+      const float2 w = s_win[lane + 32 * r];
+      v[r] = make_float2(xs.x * w.x, xs.y * w.y);
+    }
+    __syncwarp();                                  // samples consumed; slab becomes the transpose buffer
+    dif_fft<32>(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+      float2 a = v[bit_reverse<32>(k2)];
+      if (k2 > 0) {
+        const float2 w = s_tw1[k2 * 32 + lane];
+        a = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+      }
+      slab[k2 * 33 + lane] = a;
+    }
+    __syncwarp();
+    // ---- pass 2: lane = k2, register <-> n1 ------------------------------------------------------
+    float2 u[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) u[n1] = slab[lane * 33 + n1];
+    __syncwarp();                                  // slab free again: prefetch the next frame
+    const int64_t g_next = g + step;
+    in_flight = (g_next < p.g1) ? stage_frame(g_next) : false;
+
+    dif_fft<32>(u);                                // u[bit_reverse(k1)] = Z[32 k1 + lane] / 2
+
+    // ---- real-FFT untangling: bin k = 32 k1 + lane pairs with 1024 - k -------------------------
+    int64_t seq, t, start;
+    frame_origin(g, seq, t, start);
+    const int64_t row = g - p.g0;
+    const int partner = (32 - lane) & 31;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const float2 z = u[bit_reverse<32>(k1)];
+      float2 q;
+      q.x = __shfl_sync(0xffffffffu, u[bit_reverse<32>(31 - k1)].x, partner);
+      q.y = __shfl_sync(0xffffffffu, u[bit_reverse<32>(31 - k1)].y, partner);
+      if (lane == 0) q = u[bit_reverse<32>((32 - k1) & 31)];
+      const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+      const float2 w = s_tw2[k1 * 32 + lane];      // (c, d), W = c + i d
+      const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
+      const float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
+      emit_bin(p, seq, t, row, 32 * k1 + lane, xr, xi);
+    }
+    // Nyquist bin (and zero fill of the row padding in frame-major mode)
+    {
+      const float2 z0 = u[0];
+      const float nyq = 2.0f * (z0.x - z0.y);
+      if (p.out_mode == OUT_POWER_ROWS) {
+        if (1024 + lane < p.kpad)
+          p.out[row * p.kpad + 1024 + lane] = (lane == 0) ? spectral_power(nyq, 0.0f, p.power, p.power_mode) : 0.0f;
+      } else if (lane == 0) {
+        emit_bin(p, seq, t, row, 1024, nyq, 0.0f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic path: one CTA per frame, Stockham radix-2 in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kGenThreads = 256;
+
+static size_t generic_smem_bytes(int n_fft) {
+  const size_t c = (size_t)n_fft / 2;
+  return sizeof(float2) * (2 * c + c / 2 + c + 1) + sizeof(float) * (size_t)n_fft + 16;
+}
+
+__global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n_fft = p.n_fft, C = n_fft >> 1;
+  float2* buf_a = reinterpret_cast<float2*>(smem_raw);
+  float2* buf_b = buf_a + C;
+  float2* tw_c = buf_b + C;               // W_C^m, m < C/2
+  float2* tw_n = tw_c + (C >> 1);         // W_N^k, k <= C
+  float* win = reinterpret_cast<float*>(tw_n + C + 1);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < n_fft; i += kGenThreads) win[i] = p.window[i] * (0.5f * p.scale);
+  for (int i = tid; i < (C >> 1); i += kGenThreads) {
+    float sn, cs;
+    sincospif(-2.0f * (float)i / (float)C, &sn, &cs);
+    tw_c[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i <= C; i += kGenThreads) {
+    float sn, cs;
+    sincospif(-2.0f * (float)i / (float)n_fft, &sn, &cs);
+    tw_n[i] = make_float2(cs, sn);
+  }
+  __syncthreads();
+
+  for (int64_t g = p.g0 + blockIdx.x; g < p.g1; g += gridDim.x) {
+    const int64_t seq = g / p.frames, t = g - seq * p.frames, start = t * p.hop - p.pad;
+    const float* row = p.x + seq * p.seq_stride;
+    for (int n = tid; n < C; n += kGenThreads) {
+      const float x0 = fetch_padded(row, start + 2 * n, p.n_samples, p.pad_mode);
+      const float x1 = fetch_padded(row, start + 2 * n + 1, p.n_samples, p.pad_mode);
+      buf_a[n] = make_float2(x0 * win[2 * n], x1 * win[2 * n + 1]);
+    }
+    __syncthreads();
+    float2* src = buf_a;
+    float2* dst = buf_b;
+    for (int ns = 1; ns < C; ns <<= 1) {
+      const int tw_stride = C / (2 * ns);
+      for (int j = tid; j < (C >> 1); j += kGenThreads) {
+        const int k = j & (ns - 1);
+        const float2 w = tw_c[k * tw_stride];
+        const float2 a = src[j];
+        const float2 b0 = src[j + (C >> 1)];
+        const float2 b = make_float2(fmaf(b0.x, w.x, -b0.y * w.y), fmaf(b0.x, w.y, b0.y * w.x));
+        const int j0 = ((j - k) << 1) + k;
+        dst[j0] = make_float2(a.x + b.x, a.y + b.y);
+        dst[j0 + ns] = make_float2(a.x - b.x, a.y - b.y);
+      }
+      __syncthreads();
+      float2* tmp = src;
+      src = dst;
+      dst = tmp;
+    }
+    const int64_t out_row = g - p.g0;
+    for (int k = tid; k <= C; k += kGenThreads) {
+      const float2 z = src[k & (C - 1)];
+      const float2 q = src[(C - k) & (C - 1)];
+      const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+      const float2 w = tw_n[k];
+      const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
+      float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
+      if (k == 0 || k == C) xi = 0.0f;
+      emit_bin(p, seq, t, out_row, k, xr, xi);
+      if (!p.onesided && k > 0 && k < C) emit_bin(p, seq, t, out_row, n_fft - k, xr, -xi);
+    }
+    if (p.out_mode == OUT_POWER_ROWS)
+      for (int k = C + 1 + tid; k < p.kpad; k += kGenThreads) p.out[out_row * p.kpad + k] = 0.0f;
+    __syncthreads();
+  }
+}
+
+int launch_stft(const StftParams& p, cudaStream_t stream) {
+  const int64_t n_frames = p.g1 - p.g0;
+  if (n_frames <= 0) return TAC_OK;
+  if (p.n_fft == 2048 && p.onesided) {
+    static bool configured = false;
+    if (!configured) {
+      TAC_CUDA_OK(cudaFuncSetAttribute(stft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes));
+      configured = true;
+    }
+    const int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
+    const int grid = (int)(want < sm_count() ? want : sm_count());
+    stft2048_kernel<<<grid, kFastThreads, kFastSmemBytes, stream>>>(p);
+  } else {
+    const size_t smem = generic_smem_bytes(p.n_fft);
+    static size_t configured_smem = 0;
+    if (smem > 48 * 1024 && smem > configured_smem) {
+      TAC_CUDA_OK(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_smem = smem;
+    }
+    const int per_sm = (int)((200 * 1024) / (smem + 1024));
+    const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    const int grid = (int)(n_frames < cap ? n_frames : cap);
+    stft_generic_kernel<<<grid, kGenThreads, smem, stream>>>(p);
+  }
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                     const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
+                     int onesided) {
+  TAC_REQUIRE(x && window, TAC_ERR_INVALID, "stft: null input or window pointer");
+  TAC_REQUIRE(n_seq >= 0 && n_samples >= 0 && seq_stride >= n_samples, TAC_ERR_INVALID,
+              "stft: bad shape n_seq=%lld n_samples=%lld stride=%lld", (long long)n_seq, (long long)n_samples,
+              (long long)seq_stride);
+  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32 && n_fft <= 8192, TAC_ERR_UNSUPPORTED,
+              "stft: n_fft=%d is not a power of two in [32, 8192] (the sm_100a kernels cover those sizes only)", n_fft);
+  TAC_REQUIRE(hop >= 1, TAC_ERR_INVALID, "stft: hop_length=%d must be positive", hop);
+  TAC_REQUIRE(pad_mode >= TAC_PAD_REFLECT && pad_mode <= TAC_PAD_CIRCULAR, TAC_ERR_INVALID, "stft: unknown pad_mode %d", pad_mode);
+  const int pad = center ? n_fft / 2 : 0;
+  if (center && pad_mode == TAC_PAD_REFLECT)
+    TAC_REQUIRE(pad < n_samples, TAC_ERR_INVALID,
+                "stft: Padding size should be less than the corresponding input dimension (reflect pad %d, time %lld)", pad,
+                (long long)n_samples);
+  if (center && pad_mode == TAC_PAD_CIRCULAR)
+    TAC_REQUIRE(pad <= n_samples, TAC_ERR_INVALID, "stft: circular padding %d wraps more than once (time %lld)", pad,
+                (long long)n_samples);
+  TAC_REQUIRE(n_samples + 2 * pad >= n_fft, TAC_ERR_INVALID, "stft: input of %lld samples is shorter than n_fft=%d",
+              (long long)n_samples, n_fft);
+  p.x = x;
+  p.window = window;
+  p.n_seq = n_seq;
+  p.n_samples = n_samples;
+  p.seq_stride = seq_stride;
+  p.n_fft = n_fft;
+  p.hop = hop;
+  p.pad = pad;
+  p.pad_mode = pad_mode;
+  p.onesided = onesided ? 1 : 0;
+  p.bins = onesided ? n_fft / 2 + 1 : n_fft;
+  p.frames = tac_stft_num_frames(n_samples, n_fft, hop, center);
+  p.scale = normalized ? (float)(1.0 / sqrt((double)n_fft)) : 1.0f;
+  p.g0 = 0;
+  p.g1 = n_seq * p.frames;
+  p.kpad = kpad_for_bins(p.bins);
+  p.bulk_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (seq_stride & 3) == 0 && (hop & 3) == 0 && (pad & 3) == 0) ? 1 : 0;
+  p.power = 1.0f;
+  p.power_mode = 1;
+  p.out_mode = OUT_COMPLEX_PUBLIC;
+  p.out = nullptr;
+  return TAC_OK;
+}
+
+}  // namespace tac
+
+extern "C" int64_t tac_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center) {
+  if (hop <= 0 || n_fft <= 0) return 0;
+  const int64_t padded = n_samples + (center ? 2 * (int64_t)(n_fft / 2) : 0);
+  return padded < n_fft ? 0 : 1 + (padded - n_fft) / hop;
+}
+
+extern "C" int tac_stft_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
+                            int n_fft, int hop, int center, int pad_mode, int normalized, int onesided, float* out,
+                            void* stream) {
+  using namespace tac;
+  StftParams p;
+  const int rc = fill_stft_params(p, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(out || p.g1 == 0, TAC_ERR_INVALID, "stft: null output pointer");
+  p.out = out;
+  p.out_mode = OUT_COMPLEX_PUBLIC;
+  return launch_stft(p, as_stream(stream));
+}
+
+extern "C" int tac_spectrogram_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                                   const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
+                                   int onesided, float power, float* out, void* stream) {
+  using namespace tac;
+  StftParams p;
+  const int rc = fill_stft_params(p, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(out || p.g1 == 0, TAC_ERR_INVALID, "spectrogram: null output pointer");
+  p.out = out;
+  p.out_mode = OUT_POWER_PUBLIC;
+  p.power = power;
+  p.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  return launch_stft(p, as_stream(stream));
+}

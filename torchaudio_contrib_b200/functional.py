@@ -1,0 +1,344 @@
+"""Functional surface of torchaudio_contrib (reference: torchaudio_contrib/functional.py) on
+hand-written sm_100a kernels.
+
+Same names, argument meaning and shapes as the reference; every function documents the reference
+lines it stands in for.  Tensors must live on a CUDA device and be float32 (mu-law codes int64):
+each call enqueues kernels of libtac_b200.so on the current stream.  There is no CPU path.  The
+kernels are forward-only; an input that requires grad raises instead of silently detaching.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi, _mulaw_tables
+
+__all__ = [
+    "stft", "complex_norm", "create_mel_filter", "apply_filterbank", "amplitude_to_db",
+    "mu_law_encoding", "mu_law_decoding", "spectrogram", "melspectrogram", "FilterbankPlan",
+]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _forward_only(t, name):
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError("%s: the B200 kernels are forward-only; call under torch.no_grad() or detach "
+                           "the input (the reference is differentiable through torch, this path is not)" % name)
+
+
+def _as_f32_cuda(t, name):
+    _cabi.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise NotImplementedError("%s has dtype %s: the B200 kernels compute in float32 only" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _frame_window(window, win_length, fft_length, device):
+    """The n_fft-long window torch.stft effectively multiplies by: Hann(win_length) when none is
+    given (functional.py:93-97), zero-padded on both sides to sit in the middle of the frame."""
+    if win_length is None:
+        win_length = fft_length
+    if window is None:
+        window = torch.hann_window(win_length, device=device)
+    if window.dim() != 1 or window.size(0) != win_length:
+        raise RuntimeError("stft: expected a 1-D window of size win_length=%d, got %s"
+                           % (win_length, tuple(window.shape)))
+    if not (0 < win_length <= fft_length):
+        raise RuntimeError("stft: expected 0 < win_length <= n_fft, got win_length=%d n_fft=%d"
+                           % (win_length, fft_length))
+    window = window.to(device=device, dtype=torch.float32)
+    if win_length < fft_length:
+        left = (fft_length - win_length) // 2
+        window = torch.nn.functional.pad(window, (left, fft_length - win_length - left))
+    return window.contiguous()
+
+
+def _stft_geometry(waveforms, fft_length, hop_length, center):
+    hop = fft_length // 4 if hop_length is None else int(hop_length)
+    lead = waveforms.shape[:-1]
+    n_samples = waveforms.size(-1)
+    flat = waveforms.reshape(-1, n_samples)
+    frames = int(_cabi.lib().tac_stft_num_frames(n_samples, fft_length, hop, int(bool(center))))
+    return hop, lead, flat, frames
+
+
+def _stft_args(flat, window, fft_length, hop, center, pad_mode, normalized):
+    if pad_mode not in _cabi.PAD_MODES:
+        raise NotImplementedError("stft: pad_mode=%r (supported: %s)" % (pad_mode, sorted(_cabi.PAD_MODES)))
+    return [_cabi.ptr(flat), flat.size(0), flat.size(1), flat.stride(0) if flat.size(0) > 1 else flat.size(1),
+            _cabi.ptr(window), int(fft_length), hop, int(bool(center)), _cabi.PAD_MODES[pad_mode],
+            int(bool(normalized))]
+
+
+# ------------------------------------------------------------------------------------------------
+# a1: stft
+# ------------------------------------------------------------------------------------------------
+def stft(waveforms, fft_length, hop_length=None, win_length=None, window=None,
+         center=True, pad_mode='reflect', normalized=False, onesided=True):
+    """Short-time Fourier transform, `(*, channel, time) -> (*, channel, num_freqs, frames, 2)`.
+
+    Reference: functional.py:48-113 (a reshape around `torch.stft`, :99-107).  Here: one fused
+    framing + padding + window + real-FFT kernel (csrc/stft.cu).  `fft_length` must be a power
+    of two in [32, 8192].  Unlike the reference, a missing `window` is created on the input's
+    device.  The result is a contiguous tensor of the reference's logical shape.
+    """
+    _forward_only(waveforms, "stft")
+    x = _as_f32_cuda(waveforms, "waveforms")
+    hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
+    win = _frame_window(window, win_length, fft_length, x.device)
+    bins = fft_length // 2 + 1 if onesided else fft_length
+    out = torch.empty((flat.size(0), bins, max(frames, 0), 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().tac_stft_f32(
+            *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
+            int(bool(onesided)), _cabi.ptr(out), _cabi.stream_ptr(x.device)))
+    return out.reshape(lead + out.shape[1:])
+
+
+def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=None, center=True,
+                pad_mode='reflect', normalized=False, onesided=True, power=1.):
+    """`Spectrogram(...)(x)` in one kernel: stft then `|.|^power` (layers.py:294-304), the complex
+    spectrum never reaches HBM.  Returns `(*, channel, num_freqs, frames)`."""
+    _forward_only(waveforms, "spectrogram")
+    x = _as_f32_cuda(waveforms, "waveforms")
+    hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
+    win = _frame_window(window, win_length, fft_length, x.device)
+    bins = fft_length // 2 + 1 if onesided else fft_length
+    out = torch.empty((flat.size(0), bins, max(frames, 0)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().tac_spectrogram_f32(
+            *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
+            int(bool(onesided)), float(power), _cabi.ptr(out), _cabi.stream_ptr(x.device)))
+    return out.reshape(lead + out.shape[1:])
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: complex_norm
+# ------------------------------------------------------------------------------------------------
+def complex_norm(complex_tensor, power=1.0):
+    """`(*, 2) -> (*)`: sqrt(re^2 + im^2), then `.pow(power)` (functional.py:116-128)."""
+    _forward_only(complex_tensor, "complex_norm")
+    z = _as_f32_cuda(complex_tensor, "complex_tensor")
+    if z.dim() < 1 or z.size(-1) != 2:
+        raise RuntimeError("complex_norm: expected a (*, 2) tensor, got %s" % (tuple(z.shape),))
+    out = torch.empty(z.shape[:-1], dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _cabi.check(_cabi.lib().tac_complex_norm_f32(_cabi.ptr(z), out.numel(), float(power), _cabi.ptr(out),
+                                                     _cabi.stream_ptr(z.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a4: mel filterbank (construction time, torch ops in the reference's order -> bit-identical matrix)
+# ------------------------------------------------------------------------------------------------
+def _hertz_to_mel(hz, htk):
+    """functional.py:26-45."""
+    hz = torch.as_tensor(hz).type(torch.get_default_dtype())
+    if htk:
+        return 2595. * torch.log10(torch.tensor(1., dtype=torch.get_default_dtype()) + (hz / 700.))
+    slope = 200.0 / 3
+    knee_hz = 1000.0
+    knee_mel = (knee_hz - 0.0) / slope
+    logstep = math.log(6.4) / 27.0
+    return torch.where(hz >= knee_hz, knee_mel + torch.log(hz / knee_hz) / logstep, (hz - 0.0) / slope)
+
+
+def _mel_to_hertz(mel, htk):
+    """functional.py:5-23."""
+    mel = torch.as_tensor(mel).type(torch.get_default_dtype())
+    if htk:
+        return 700. * (10 ** (mel / 2595.) - 1.)
+    slope = 200.0 / 3
+    knee_hz = 1000.0
+    knee_mel = (knee_hz - 0.0) / slope
+    logstep = math.log(6.4) / 27.0
+    return torch.where(mel >= knee_mel, knee_hz * torch.exp(logstep * (mel - knee_mel)), 0.0 + slope * mel)
+
+
+def create_mel_filter(num_freqs, num_mels, min_freq, max_freq, htk):
+    """Triangular mel weights `(num_freqs, num_mels)`, Slaney scale unless `htk`, no area
+    normalisation (functional.py:131-169).  Runs once per module on the host with the same fp32
+    torch operators in the same order as the reference, so the matrix is bit-identical to the
+    reference's (tests assert `torch.equal` against golden matrices)."""
+    lo_mel = _hertz_to_mel(min_freq, htk)
+    hi_mel = _hertz_to_mel(max_freq, htk)
+    bin_hz = torch.linspace(min_freq, max_freq, num_freqs)                    # :155
+    edge_hz = _mel_to_hertz(torch.linspace(lo_mel, hi_mel, num_mels + 2), htk)   # :158-159
+    width = edge_hz[1:] - edge_hz[:-1]                                        # :160
+    offset = edge_hz.unsqueeze(0) - bin_hz.unsqueeze(1)                       # :163  (num_freqs, num_mels + 2)
+    falling = (-1. * offset[:, :-2]) / width[:-1]                             # :165
+    rising = offset[:, 2:] / width[1:]                                        # :166
+    return torch.clamp(torch.min(falling, rising), min=0.)                    # :167
+
+
+# ------------------------------------------------------------------------------------------------
+# a3: apply_filterbank (tcgen05)
+# ------------------------------------------------------------------------------------------------
+class FilterbankPlan(object):
+    """Device image of a `(num_freqs, num_bands)` matrix prepared for the tensor-core kernel:
+    tf32 hi/lo split, 128B-swizzled K-major operand blocks per 32-bin slice, zero blocks skipped
+    (tac_fbplan_build_host).  Built once per matrix per device and cached by the caller."""
+
+    def __init__(self, filterbank, device):
+        fb = filterbank.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        if fb.dim() != 2:
+            raise RuntimeError("apply_filterbank: filterbank must be (num_freqs, num_bands), got %s"
+                               % (tuple(fb.shape),))
+        self.num_freqs, self.num_bands = int(fb.size(0)), int(fb.size(1))
+        lib = _cabi.lib()
+        cap = int(lib.tac_fbplan_bytes(self.num_freqs, self.num_bands))
+        if cap <= 0:
+            raise RuntimeError("apply_filterbank: unsupported filterbank shape %s" % (tuple(fb.shape),))
+        host = torch.empty(cap, dtype=torch.uint8)
+        used = ctypes.c_int64(0)
+        _cabi.check(lib.tac_fbplan_build_host(_cabi.ptr(fb), self.num_freqs, self.num_bands, _cabi.ptr(host), cap,
+                                              ctypes.byref(used)))
+        self.blob = host[:used.value].to(device)
+        self.device = self.blob.device
+        self.key = FilterbankPlan.key_of(filterbank)
+
+    @staticmethod
+    def key_of(filterbank):
+        return (filterbank.data_ptr(), filterbank._version, tuple(filterbank.shape), str(filterbank.device))
+
+
+def _plan_for(filterbank, device, cache=None):
+    key = FilterbankPlan.key_of(filterbank)
+    if cache is not None:
+        plan = cache.get("plan")
+        if plan is not None and plan.key == key and plan.device == torch.device(device):
+            return plan
+    plan = FilterbankPlan(filterbank, device)
+    if cache is not None:
+        cache["plan"] = plan
+    return plan
+
+
+def _power_mel(spec, is_complex, power, plan, to_db, ref, amin):
+    shape = spec.shape[:-1] if is_complex else spec.shape
+    if len(shape) < 2:
+        raise RuntimeError("apply_filterbank: expected (*, num_freqs, time%s), got %s"
+                           % (", 2" if is_complex else "", tuple(spec.shape)))
+    n_bins, frames = int(shape[-2]), int(shape[-1])
+    if n_bins != plan.num_freqs:
+        raise RuntimeError("apply_filterbank: spectrogram has %d frequency bins, filterbank has %d rows"
+                           % (n_bins, plan.num_freqs))
+    lead = tuple(shape[:-2])
+    n_seq = 1
+    for d in lead:
+        n_seq *= int(d)
+    out = torch.empty(lead + (plan.num_bands, frames), dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        _cabi.check(_cabi.lib().tac_power_mel_f32(
+            _cabi.ptr(spec), int(is_complex), float(power), n_seq, frames, n_bins, _cabi.ptr(plan.blob),
+            plan.num_bands, int(bool(to_db)), float(ref), float(amin), _cabi.ptr(out), _cabi.stream_ptr(spec.device)))
+    return out
+
+
+def apply_filterbank(mag_specgrams, filterbank, _cache=None):
+    """`(*, num_freqs, time) x (num_freqs, num_bands) -> (*, num_bands, time)`: contraction over
+    the frequency axis (functional.py:172-184) on the tcgen05 tensor cores with 3xTF32 split
+    accumulation (csrc/melbank.cu).  Any dense matrix is accepted; zero blocks are skipped."""
+    _forward_only(mag_specgrams, "apply_filterbank")
+    spec = _as_f32_cuda(mag_specgrams, "mag_specgrams")
+    plan = _plan_for(filterbank, spec.device, _cache)
+    return _power_mel(spec, False, 1.0, plan, False, 1.0, 1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# a5: amplitude_to_db
+# ------------------------------------------------------------------------------------------------
+def amplitude_to_db(x, ref=1.0, amin=1e-7):
+    """`10 * (log10(max(x^2, amin)) - log10(ref))` (functional.py:277-296; note the square)."""
+    _forward_only(x, "amplitude_to_db")
+    a = _as_f32_cuda(x, "x")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _cabi.check(_cabi.lib().tac_amplitude_to_db_f32(_cabi.ptr(a), a.numel(), float(ref), float(amin), _cabi.ptr(out),
+                                                        _cabi.stream_ptr(a.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a6: fused Melspectrogram pipeline
+# ------------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Per-device scratch for the frame-major power rows (sized to stay L2 resident)."""
+    buf = _workspaces.get(str(device))
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[str(device)] = buf
+    return buf
+
+
+def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_length=None, window=None,
+                   center=True, pad_mode='reflect', normalized=False, power=2.0,
+                   to_db=False, ref=1.0, amin=1e-7, _cache=None):
+    """`Melspectrogram(...)(x)` (layers.py:307-347), optionally with `AmplitudeToDb` appended
+    (layers.py:350-381), as two back-to-back kernels: stft + |.|^power into frame-major rows that
+    stay in L2, then the tensor-core filterbank with the dB clamp in its epilogue.
+    `(*, channel, time) -> (*, channel, num_bands, frames)`."""
+    _forward_only(waveforms, "melspectrogram")
+    x = _as_f32_cuda(waveforms, "waveforms")
+    hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
+    win = _frame_window(window, win_length, fft_length, x.device)
+    plan = _plan_for(filterbank, x.device, _cache)
+    if plan.num_freqs != fft_length // 2 + 1:
+        raise RuntimeError("melspectrogram: filterbank has %d rows, stft yields %d bins"
+                           % (plan.num_freqs, fft_length // 2 + 1))
+    lib = _cabi.lib()
+    ws_bytes = int(lib.tac_melspec_workspace_bytes(flat.size(0), flat.size(1), int(fft_length), hop, int(bool(center))))
+    ws = _workspace(x.device, ws_bytes)
+    out = torch.empty((flat.size(0), plan.num_bands, max(frames, 0)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.tac_melspec_f32(
+            *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
+            float(power), _cabi.ptr(plan.blob), plan.num_bands, int(bool(to_db)), float(ref), float(amin),
+            _cabi.ptr(ws), ws.numel(), _cabi.ptr(out), _cabi.stream_ptr(x.device)))
+    return out.reshape(lead + out.shape[1:])
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 / a8: mu-law
+# ------------------------------------------------------------------------------------------------
+def mu_law_encoding(x, n_quantize=256):
+    """mu-law companding to int64 codes, no clamping of the input (functional.py:317-335).
+    Bit-exact with the reference's fp32 CPU chain for every finite float (see _mulaw_tables)."""
+    _forward_only(x, "mu_law_encoding")
+    _cabi.require_cuda(x, "x")
+    if not x.dtype.is_floating_point:
+        x = x.to(torch.float)                              # functional.py:329-330
+    a = _as_f32_cuda(x, "x")
+    thr, idx_min, x_limit = _mulaw_tables.on_device("enc", n_quantize, a.device)
+    out = torch.empty(a.shape, dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _cabi.check(_cabi.lib().tac_mulaw_encode_f32_i64(
+            _cabi.ptr(a), a.numel(), int(n_quantize), _cabi.ptr(thr), thr.numel(), int(idx_min), float(x_limit),
+            _cabi.ptr(out), _cabi.stream_ptr(a.device)))
+    return out
+
+
+def mu_law_decoding(x_mu, n_quantize=256, dtype=torch.float32):
+    """mu-law expansion of codes to float32 (functional.py:338-354)."""
+    _cabi.require_cuda(x_mu, "x_mu")
+    if dtype != torch.float32:
+        raise NotImplementedError("mu_law_decoding: only float32 output is implemented")
+    (lut,) = _mulaw_tables.on_device("dec", n_quantize, x_mu.device)
+    lib = _cabi.lib()
+    if x_mu.dtype.is_floating_point:
+        _forward_only(x_mu, "mu_law_decoding")
+        codes = _as_f32_cuda(x_mu, "x_mu")
+        fn = lib.tac_mulaw_decode_f32_f32
+    else:
+        codes = x_mu.to(torch.int64).contiguous()
+        fn = lib.tac_mulaw_decode_i64_f32
+    out = torch.empty(codes.shape, dtype=torch.float32, device=codes.device)
+    with torch.cuda.device(codes.device):
+        _cabi.check(fn(_cabi.ptr(codes), codes.numel(), int(n_quantize), _cabi.ptr(lut), _cabi.ptr(out),
+                       _cabi.stream_ptr(codes.device)))
+    return out

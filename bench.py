@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- mel-spectrogram frames/sec (fft 2048 / hop 512) on N B200s, with roofline evidence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|mulaw]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of `Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048,
+hop_length=512)` over one (64, 1, 160000) fp32 batch per GPU (BASELINE.json configs[1]).
+
+Printed (rank 0, ONE JSON line):
+  value        frames/s, all ranks, inputs already in HBM, CUDA events, max over ranks
+  e2e          same metric through the host-buffer C-ABI entry (tac_pipeline_run_host): pinned host
+               input -> H2D -> kernels -> D2H of the full result inside the timed region
+  roofline     dominant kernel (stft2048_kernel): algorithmic bytes / its event-timed duration / measured HBM peak
+  cpu_baseline the oracle (reference's torch CPU chain, restated) timed on this box's host cores
+  clocks       nvidia-smi samples taken during the timed region
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, torch.stft shim only) on the host CPU.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch, channels, samples, sample_rate, to_db)
+    "cfg2": (64, 1, 160000, 16000, False),
+    "cfg3": (256, 2, 480000, 48000, True),
+}
+N_FFT, HOP, N_MELS = 2048, 512, 128
+L2_BYTES = 126 << 20
+
+
+def frames_of(samples):
+    return 1 + samples // HOP
+
+
+def algorithmic_bytes(batch, channels, samples):
+    """read every input sample once + write every output value once."""
+    n = batch * channels
+    return 4 * n * samples + 4 * n * N_MELS * frames_of(samples)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = max(smax, float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / oracle on the host CPU
+# ------------------------------------------------------------------------------------------------
+def load_cpu_chain():
+    """-> (callable(x, sample_rate, to_db) -> mel, kind).  The unmodified reference from
+    baseline/_ref when it is installed there (torch.stft legacy-layout shim only), else the oracle."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "torchaudio_contrib")):
+        sys.path.insert(0, ref_dir)
+        native = torch.stft
+
+        def legacy_stft(*a, **k):
+            k["return_complex"] = True
+            return torch.view_as_real(native(*a, **k))
+
+        import torchaudio_contrib as ref
+        cache = {}
+
+        def run(x, sample_rate, to_db):
+            key = (sample_rate, to_db)
+            if key not in cache:
+                mods = list(ref.Melspectrogram(num_mels=N_MELS, sample_rate=sample_rate, fft_length=N_FFT, hop_length=HOP))
+                if to_db:
+                    mods.append(ref.AmplitudeToDb())
+                cache[key] = torch.nn.Sequential(*mods)
+            torch.stft = legacy_stft
+            try:
+                with torch.no_grad():
+                    return cache[key](x)
+            finally:
+                torch.stft = native
+
+        return run, "reference"
+    from oracle import ref_chain
+
+    def run(x, sample_rate, to_db):
+        with torch.no_grad():
+            return ref_chain.melspectrogram(x, N_MELS, sample_rate, to_db=to_db, fft_length=N_FFT, hop_length=HOP)
+
+    return run, "port"
+
+
+def cpu_sample_batch(batch, channels, samples):
+    """Sequences per CPU step: the whole batch when it is config-2 sized, else ~10 M samples' worth
+    (the reference materialises ~60 KB of intermediates per frame)."""
+    return max(1, min(batch, (64 * 160000) // (channels * samples)))
+
+
+def time_cpu_chain(batch, channels, samples, sample_rate, to_db, budget_s):
+    """Bounded sample of the workload on the host cores: frames/s of the CPU chain."""
+    run, kind = load_cpu_chain()
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)
+    nb = cpu_sample_batch(batch, channels, samples)
+    x = torch.randn(nb, channels, samples, generator=g)
+    run(x, sample_rate, to_db)                       # warm-up (thread pool, MKL plans)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        run(x, sample_rate, to_db)
+        done += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or done >= 200:
+            break
+    frames = done * nb * channels * frames_of(samples)
+    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d passes of (%d,%d,%d) in %.1f s" % (done, nb, channels, samples, dt)}
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation, rank 0 only."""
+    if rank != 0:
+        return
+    batch, channels, samples, sr, to_db = WORKLOADS[args.workload]
+    run, kind = load_cpu_chain()
+    torch.set_num_threads(os.cpu_count() or 1)
+    nb = cpu_sample_batch(batch, channels, samples)
+    x = torch.randn(nb, channels, samples, generator=torch.Generator().manual_seed(1234))
+    for _ in range(max(args.warmup, 1)):
+        run(x, sr, to_db)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(x, sr, to_db)
+    dt = time.perf_counter() - t0
+    frames = args.steps * nb * channels * frames_of(samples)
+    value = frames / dt
+    line = {
+        "impl": "reference", "metric": "mel-spectrogram frames/sec (fft=2048/hop=512)", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: Melspectrogram(128 mels, %d Hz, fft 2048, hop 512)%s, reference on host CPU, "
+                               "bounded sample (%d,%d,%d) per step" % (args.workload, sr, "+AmplitudeToDb" if to_db else "",
+                                                                        nb, channels, samples)},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": "%d steps of (%d,%d,%d)" % (args.steps, nb, channels, samples)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    import torchaudio_contrib_b200 as tac
+    from torchaudio_contrib_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch, channels, samples, sr, to_db = WORKLOADS[args.workload]
+    frames = frames_of(samples)
+    frames_per_step = batch * channels * frames
+    in_bytes = 4 * batch * channels * samples
+    out_bytes = 4 * batch * channels * N_MELS * frames
+    lib = _cabi.lib()
+
+    mods = list(tac.Melspectrogram(num_mels=N_MELS, sample_rate=sr, fft_length=N_FFT, hop_length=HOP))
+    if to_db:
+        mods.append(tac.AmplitudeToDb())
+    model = tac.Sequential(*mods).to(dev)
+
+    # inputs larger than L2: rotate over enough distinct batches that each step reads its input from HBM
+    n_sets = max(2, -(-2 * L2_BYTES // in_bytes)) if in_bytes < 2 * L2_BYTES else 2
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    inputs = [torch.randn(batch, channels, samples, device=dev, generator=gen) for _ in range(n_sets)]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            out = model(inputs[i % n_sets])
+        barrier()
+        launches0 = int(lib.tac_launch_count())
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            start.record()
+            for i in range(args.steps):
+                out = model(inputs[i % n_sets])
+            stop.record()
+            barrier()
+        ms = start.elapsed_time(stop)
+        launches = int(lib.tac_launch_count()) - launches0
+
+        # per-kernel durations: same loop again with every launch bracketed by events on its stream
+        lib.tac_profile_enable(1)
+        for i in range(args.steps):
+            model(inputs[i % n_sets])
+        torch.cuda.synchronize(dev)
+        kind_ms = (ctypes.c_double * 4)()
+        kind_n = (ctypes.c_int64 * 4)()
+        lib.tac_profile_read(kind_ms, kind_n)
+        lib.tac_profile_enable(0)
+
+        # e2e: host buffers through the C-ABI host entry (H2D + kernels + D2H inside the timed region)
+        fb = mods[2].filterbank
+        hp = tac.HostPipeline(N_FFT, HOP, power=2.0, filterbank=fb, to_db=to_db, device=dev)
+        host_in = [torch.randn(batch, channels, samples).pin_memory() for _ in range(2)]
+        host_out = torch.empty(batch, channels, N_MELS, frames).pin_memory()
+        e2e_steps = max(3, min(args.steps, 20))
+        for i in range(3):
+            hp(host_in[i % 2], out=host_out)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            hp(host_in[i % 2], out=host_out)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        hbm_peak = float(peaks["hbm_gbs"])
+        stft_ms = kind_ms[0] / max(kind_n[0], 1)               # average launch duration
+        frames_per_stft_launch = args.steps * frames_per_step / max(kind_n[0], 1)
+        alg_per_frame = algorithmic_bytes(batch, channels, samples) / frames_per_step
+        achieved = alg_per_frame * frames_per_stft_launch / (stft_ms * 1e-3) / 1e9 if stft_ms > 0 else 0.0
+        value = world * args.steps * frames_per_step / (ms * 1e-3)
+        cpu = time_cpu_chain(batch, channels, samples, sr, to_db, budget_s=args.cpu_seconds)
+        line = {
+            "metric": "mel-spectrogram frames/sec (fft=2048/hop=512)",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "%s: Melspectrogram(num_mels=128, sample_rate=%d, fft_length=2048, hop_length=512)%s on "
+                            "(%d,%d,%d) fp32 per GPU" % (args.workload, sr, "+AmplitudeToDb" if to_db else "", batch, channels, samples),
+                "parallelism": "batch split, %d rank(s), no data-path collective" % world,
+                "l2_policy": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (n_sets, n_sets * in_bytes / 1e6),
+                "precision": "fp32 FFT on CUDA cores; filterbank 3xTF32 on tcgen05 (fp32 accumulate)",
+            },
+            "hbm_roofline_frac_step": (algorithmic_bytes(batch, channels, samples) / (ms / args.steps * 1e-3) / 1e9) / hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "stft2048_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                         "avg_launch_ms": stft_ms, "launches_timed": int(kind_n[0]),
+                         "algorithmic_bytes_per_frame": alg_per_frame},
+            "kernel_ms_per_step": {"stft2048_kernel": kind_ms[0] / args.steps, "melbank_kernel": kind_ms[1] / args.steps},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * e2e_steps * frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "tac_pipeline_run_host (HostPipeline), pinned host buffers"},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "r01_stft2048_dram_bytes.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as fh:
+                line["roofline"]["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the in-run CPU baseline")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if args.gpus > 1 and world == 1:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

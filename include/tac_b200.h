@@ -132,6 +132,15 @@ int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64_t n_seq, i
                           float* out_host);
 int tac_pipeline_destroy(tac_pipeline* p);
 
+/* ---- instrumentation (used by bench.py; off by default) -----------------------------------
+ * tac_launch_count: kernels launched by this library in this process so far.
+ * tac_profile_enable(1): bracket every kernel launch with CUDA events on its own stream;
+ * tac_profile_read: synchronise those events, return the summed milliseconds and launch counts
+ * per kernel kind (0 = stft, 1 = filterbank, 2 = mu-law, 3 = pointwise) and clear the log. */
+int64_t tac_launch_count(void);
+int tac_profile_enable(int on);
+int tac_profile_read(double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,9 @@ SIGNATURES = {
     "tac_pipeline_create": (_int, [_ptr, _ptr, _ptr, _c.POINTER(_ptr)]),
     "tac_pipeline_run_host": (_int, [_ptr, _ptr, _i64, _i64, _ptr]),
     "tac_pipeline_destroy": (_int, [_ptr]),
+    "tac_launch_count": (_i64, []),
+    "tac_profile_enable": (_int, [_int]),
+    "tac_profile_read": (_int, [_c.POINTER(_c.c_double), _c.POINTER(_i64)]),
 }
 
 

@@ -2,6 +2,10 @@
 // kernels (mulaw.cu, pointwise.cu, stft.cu, melbank.cu, pipeline.cu).
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "tac_common.cuh"
 
 namespace tac {
@@ -31,7 +35,62 @@ int sm_count() {
   return cached[dev];
 }
 
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_profile{0};
+struct ProbeRecord {
+  int kind;
+  cudaEvent_t start, stop;
+};
+static std::mutex g_probe_mutex;
+static std::vector<ProbeRecord> g_probe_log;
+
+LaunchProbe::LaunchProbe(int kind, cudaStream_t stream) : kind_(kind), stream_(stream), slot_(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  ProbeRecord r;
+  r.kind = kind;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, stream);
+  std::lock_guard<std::mutex> lock(g_probe_mutex);
+  g_probe_log.push_back(r);
+  slot_ = (int)g_probe_log.size() - 1;
+}
+
+LaunchProbe::~LaunchProbe() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lock(g_probe_mutex);
+  if (slot_ < (int)g_probe_log.size()) cudaEventRecord(g_probe_log[slot_].stop, stream_);
+}
+
 }  // namespace tac
+
+extern "C" int64_t tac_launch_count(void) { return tac::g_launches.load(); }
+
+extern "C" int tac_profile_enable(int on) {
+  tac::g_profile.store(on ? 1 : 0);
+  return TAC_OK;
+}
+
+extern "C" int tac_profile_read(double* ms_by_kind, int64_t* launches_by_kind) {
+  using namespace tac;
+  std::lock_guard<std::mutex> lock(g_probe_mutex);
+  for (int k = 0; k < 4; ++k) {
+    if (ms_by_kind) ms_by_kind[k] = 0.0;
+    if (launches_by_kind) launches_by_kind[k] = 0;
+  }
+  for (ProbeRecord& r : g_probe_log) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.stop);
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess && r.kind >= 0 && r.kind < 4) {
+      if (ms_by_kind) ms_by_kind[r.kind] += ms;
+      if (launches_by_kind) launches_by_kind[r.kind] += 1;
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  g_probe_log.clear();
+  return TAC_OK;
+}
 
 extern "C" int tac_version(void) { return TAC_ABI_VERSION; }
 

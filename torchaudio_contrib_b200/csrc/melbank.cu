@@ -325,6 +325,7 @@ int launch_melbank(MelbankParams p, cudaStream_t stream) {
   p.rows_per_tile = rpt;
   const int bblocks = (p.n_bands + kMbBandBlock - 1) / kMbBandBlock;
   dim3 grid((unsigned)tiles, (unsigned)bblocks);
+  LaunchProbe probe(KIND_MELBANK, stream);
   melbank_kernel<<<grid, kMbThreads, kMbSmemBytes, stream>>>(p);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;

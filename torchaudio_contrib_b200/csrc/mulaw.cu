@@ -146,6 +146,7 @@ extern "C" int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantiz
   const float mu = (float)(n_quantize - 1);
   const float half_mu_over_log2 = (float)(0.5 * (double)mu / log2(1.0 + (double)mu));
   const int grid = streaming_grid((n + 3) / 4);
+  LaunchProbe probe(KIND_MULAW, as_stream(stream));
   if (n_thresholds <= kMuLawSmemTableMax) {
     const size_t smem = (size_t)n_thresholds * sizeof(float);
     mulaw_encode_kernel<true><<<grid, kMuLawThreads, smem, as_stream(stream)>>>(
@@ -169,6 +170,7 @@ static int launch_decode(const CodeT* codes, int64_t n, int n_quantize, const fl
   const float mu = (float)(n_quantize - 1);
   const float log1p_mu = (float)log1p((double)mu);
   const int grid = streaming_grid((n + 3) / 4);
+  LaunchProbe probe(KIND_MULAW, as_stream(stream));
   mulaw_decode_kernel<CodeT><<<grid, kMuLawThreads, (size_t)n_quantize * sizeof(float), as_stream(stream)>>>(
       codes, n, out, lut_dev, n_quantize, mu, log1p_mu);
   TAC_CUDA_OK(cudaGetLastError());

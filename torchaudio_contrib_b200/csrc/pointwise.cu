@@ -92,6 +92,7 @@ extern "C" int tac_complex_norm_f32(const float* z, int64_t n, float power, floa
   TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "complex_norm: n=%lld", (long long)n);
   if (n == 0) return TAC_OK;
   TAC_REQUIRE(z && out, TAC_ERR_INVALID, "complex_norm: null pointer");
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
   complex_norm_kernel<<<pw_grid((n + 1) / 2), kPwThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const float2*>(z), n, power, power_mode(power), out);
   TAC_CUDA_OK(cudaGetLastError());
@@ -103,6 +104,7 @@ extern "C" int tac_amplitude_to_db_f32(const float* x, int64_t n, float ref, flo
   TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "amplitude_to_db: n=%lld", (long long)n);
   if (n == 0) return TAC_OK;
   TAC_REQUIRE(x && out, TAC_ERR_INVALID, "amplitude_to_db: null pointer");
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
   amplitude_to_db_kernel<<<pw_grid((n + 3) / 4), kPwThreads, 0, as_stream(stream)>>>(x, n, amin, log10f(ref), out);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;

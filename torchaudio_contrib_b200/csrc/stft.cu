@@ -287,24 +287,25 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
   if (p.n_fft == 2048 && p.onesided) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    TAC_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
       TAC_CUDA_OK(cudaFuncSetAttribute(stft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes));
-      configured = true;
+      configured[dev] = true;
     }
     const int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());
+    LaunchProbe probe(KIND_STFT, stream);
     stft2048_kernel<<<grid, kFastThreads, kFastSmemBytes, stream>>>(p);
   } else {
     const size_t smem = generic_smem_bytes(p.n_fft);
-    static size_t configured_smem = 0;
-    if (smem > 48 * 1024 && smem > configured_smem) {
+    if (smem > 48 * 1024)
       TAC_CUDA_OK(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_smem = smem;
-    }
     const int per_sm = (int)((200 * 1024) / (smem + 1024));
     const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
     const int grid = (int)(n_frames < cap ? n_frames : cap);
+    LaunchProbe probe(KIND_STFT, stream);
     stft_generic_kernel<<<grid, kGenThreads, smem, stream>>>(p);
   }
   TAC_CUDA_OK(cudaGetLastError());

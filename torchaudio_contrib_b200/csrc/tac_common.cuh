@@ -32,6 +32,16 @@ int fail(int code, const char* fmt, ...);
 
 int sm_count();                      // cached per current device
 
+// launch accounting / optional event bracketing (abi.cu)
+enum KernelKind { KIND_STFT = 0, KIND_MELBANK = 1, KIND_MULAW = 2, KIND_POINTWISE = 3 };
+struct LaunchProbe {                 // construct right before a launch, destroy right after it
+  LaunchProbe(int kind, cudaStream_t stream);
+  ~LaunchProbe();
+  int kind_;
+  cudaStream_t stream_;
+  int slot_;
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }

@@ -281,7 +281,17 @@ def test_mel_nonrandom_signals(tac, oc):
                        tac.AmplitudeToDb()).cuda()
     got = m(dev(sig)).cpu()
     want = oc.melspectrogram(sig, 128, 16000, to_db=True, fft_length=2048, hop_length=512)
-    assert (got - want).abs().max().item() < 2e-3
+    # bands 60 dB below the tone are rounding noise of the FFT relative to the peak: there the reference's
+    # own fp32 result is only good to a few 1e-3 dB, so judge both against the float64 truth
+    from oracle import f64_chain
+    fb = oc.mel_filterbank_for(128, 16000, fft_length=2048).numpy()
+    truth = f64_chain.power_to_db(f64_chain.melspectrogram(sig.numpy(), fb, 2048, 512) ** 2, 1.0, 1e-7)
+    err_ours = np.abs(got.numpy() - truth).max()
+    err_ref = np.abs(want.numpy() - truth).max()
+    assert err_ours < max(2.0 * err_ref, 1e-3), (err_ours, err_ref)
+    assert (got - want).abs().max().item() < 1e-2          # the reference's own dB tolerance (tests/test_layers.py:83)
+    loud = want > -20.0
+    assert (got[loud] - want[loud]).abs().max().item() < 1e-3
     assert (got[2] == -70.0).all()
 
 

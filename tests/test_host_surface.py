@@ -1,0 +1,227 @@
+"""Host-side logic without a GPU: the C ABI loads and exports what include/tac_b200.h declares, the
+host-built constant tables (filterbank plan, mu-law levels) are right, and the module surface matches the
+reference's (signatures, defaults, repr, state_dict, exceptions).  No compute call is made."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+
+@pytest.fixture(scope="module")
+def tac():
+    import torchaudio_contrib_b200 as t
+    return t
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "tac_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tac_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(tac):
+    names = _header_functions()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(tac._cabi.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), "libtac_b200.so lacks %s declared in include/tac_b200.h" % name
+    assert sorted(tac._cabi.SIGNATURES) == names            # the ctypes table binds exactly the header
+    assert tac._cabi.lib().tac_version() == 1
+
+
+def test_num_frames_formula(tac):
+    f = tac._cabi.lib().tac_stft_num_frames
+    for T, n_fft, hop in [(16000, 512, 128), (160000, 2048, 512), (100000, 512, 256), (480000, 2048, 512), (100, 64, 16)]:
+        assert f(T, n_fft, hop, 1) == (T + 2 * (n_fft // 2) - n_fft + hop) // hop == 1 + T // hop
+        assert f(T, n_fft, hop, 0) == 1 + (T - n_fft) // hop
+    assert f(10, 64, 16, 0) == 0
+
+
+# ---------------------------------------------------------------------------------------- plan
+def _unpack_plan(blob, n_bins, n_bands):
+    """Rebuild the dense matrix from the operand images; also returns the per-slice (band_lo, n)."""
+    raw = blob.numpy().tobytes()
+    hdr = np.frombuffer(raw, dtype=np.int32, count=8)
+    assert hdr[1] == n_bins and hdr[2] == n_bands
+    n_chunks, n_bblocks, max_n = int(hdr[3]), int(hdr[4]), int(hdr[5])
+    table = np.frombuffer(raw, dtype=np.int32, count=4 * n_chunks * n_bblocks, offset=32).reshape(n_bblocks, n_chunks, 4)
+    fb = np.zeros((n_chunks * 32, n_bblocks * 128), dtype=np.float64)
+    hi_only = np.zeros_like(fb)
+    spans = []
+    for bb in range(n_bblocks):
+        for c in range(n_chunks):
+            lo, n, off, _ = (int(v) for v in table[bb, c])
+            spans.append((bb, c, lo, n))
+            if n == 0:
+                continue
+            assert n % 16 == 0 and lo % 16 == 0 and lo + n <= 128 and off % 128 == 0 and n <= max_n
+            img = np.frombuffer(raw, dtype=np.float32, count=2 * n * 32, offset=off).reshape(2, n // 8, 8, 8, 4)
+            for j in range(n):
+                for kk in range(32):
+                    a, r = divmod(j, 8)
+                    h = img[0, a, r, (kk >> 2) ^ r, kk & 3]
+                    l = img[1, a, r, (kk >> 2) ^ r, kk & 3]
+                    assert (np.float32(h).view(np.uint32) & 0x1FFF) == 0          # hi is an exact tf32
+                    fb[c * 32 + kk, bb * 128 + lo + j] = float(h) + float(l)
+                    hi_only[c * 32 + kk, bb * 128 + lo + j] = float(h)
+    return fb[:n_bins, :n_bands], hi_only[:n_bins, :n_bands], spans
+
+
+@pytest.mark.parametrize("which", ["mel16k", "dense", "wide"])
+def test_filterbank_plan_images(tac, which):
+    if which == "mel16k":
+        fb = golden("filterbanks.npz")["fb_16k_1025x128"]
+    elif which == "dense":
+        fb = torch.randn(257, 36, generator=torch.Generator().manual_seed(4))
+    else:
+        fb = torch.randn(70, 300, generator=torch.Generator().manual_seed(5)) * (torch.rand(70, 300) > 0.9)
+    lib = tac._cabi.lib()
+    cap = lib.tac_fbplan_bytes(fb.size(0), fb.size(1))
+    buf = torch.zeros(cap, dtype=torch.uint8)
+    used = ctypes.c_int64()
+    fbc = fb.contiguous()
+    assert lib.tac_fbplan_build_host(fbc.data_ptr(), fb.size(0), fb.size(1), buf.data_ptr(), cap, ctypes.byref(used)) == 0
+    assert 0 < used.value <= cap
+    rebuilt, hi_only, spans = _unpack_plan(buf[:used.value], fb.size(0), fb.size(1))
+    assert np.array_equal(rebuilt.astype(np.float32), fb.numpy())       # hi + lo is the matrix, exactly
+    assert np.abs(hi_only - fb.numpy()).max() <= np.abs(fb.numpy()).max() * 2.0 ** -10
+    if which == "mel16k":
+        widths = [n for _, _, _, n in spans if n]
+        assert max(widths) <= 48 and sum(widths) < 0.3 * 128 * len(widths)   # block skipping pays on a mel matrix
+    # too-small buffer is refused, not overrun
+    assert lib.tac_fbplan_build_host(fbc.data_ptr(), fb.size(0), fb.size(1), buf.data_ptr(), 64, ctypes.byref(used)) == -4
+    assert b"too small" in lib.tac_last_error()
+
+
+# ---------------------------------------------------------------------------------------- mu-law tables
+@pytest.mark.parametrize("q", [256, 64, 2, 1024])
+def test_mulaw_tables_describe_the_reference_quantiser(tac, q):
+    from oracle import ref_chain as oc
+    from torchaudio_contrib_b200 import _mulaw_tables as mt
+    thr, idx_min, x_limit = mt.encode_tables(q)
+    assert thr[0] == float("-inf") and bool((thr[1:] > thr[:-1]).all())
+    g = torch.Generator().manual_seed(q)
+    bits = torch.randint(-(1 << 31), (1 << 31) - 1, (300000,), generator=g, dtype=torch.int64).to(torch.int32)
+    x = bits.view(torch.float32)
+    x = torch.cat([x[torch.isfinite(x)], torch.rand(300000, generator=g) * 2 - 1, thr[1:], torch.nextafter(thr[1:], thr[1:] - 1)])
+    want = oc.mu_law_encoding(x, q)
+    got = torch.searchsorted(thr, x, right=True) - 1 + idx_min
+    got = torch.where(x.abs() <= x_limit, got, torch.full_like(got, -(1 << 63)))
+    assert torch.equal(got, want)
+    assert torch.equal(mt.decode_table(q), oc.mu_law_decoding(torch.arange(q), q))
+
+
+# ---------------------------------------------------------------------------------------- module surface
+def test_signatures_match_the_reference(tac):
+    def params(fn):
+        return [(n, p.default) for n, p in inspect.signature(fn).parameters.items() if n != "self"]
+
+    E = inspect.Parameter.empty
+    assert params(tac.STFT.__init__) == [("fft_length", E), ("hop_length", None), ("win_length", None), ("window", None),
+                                         ("center", True), ("pad_mode", "reflect"), ("normalized", False), ("onesided", True)]
+    assert params(tac.stft) == [("waveforms", E)] + params(tac.STFT.__init__)
+    assert params(tac.ComplexNorm.__init__) == [("power", 1.0)]
+    assert params(tac.ApplyFilterbank.__init__) == [("filterbank", E)]
+    assert params(tac.MelFilterbank.__init__) == [("num_freqs", 1025), ("num_mels", 128), ("min_freq", 0.0), ("max_freq", None),
+                                                  ("sample_rate", None), ("htk", False)]
+    assert params(tac.Spectrogram) == params(tac.STFT.__init__) + [("power", 1.0)]
+    assert params(tac.Melspectrogram)[:7] == [("num_mels", 128), ("sample_rate", 22050), ("min_freq", 0.0), ("max_freq", None),
+                                              ("num_freqs", None), ("htk", False), ("mel_filterbank", None)]
+    assert params(tac.AmplitudeToDb.__init__) == [("ref", 1.0), ("amin", 1e-7)]
+    assert params(tac.MuLawEncoding.__init__) == params(tac.MuLawDecoding.__init__) == [("n_quantize", 256)]
+    assert params(tac.complex_norm) == [("complex_tensor", E), ("power", 1.0)]
+    assert params(tac.create_mel_filter) == [(n, E) for n in ("num_freqs", "num_mels", "min_freq", "max_freq", "htk")]
+    assert params(tac.apply_filterbank)[:2] == [("mag_specgrams", E), ("filterbank", E)]
+    assert params(tac.amplitude_to_db) == [("x", E), ("ref", 1.0), ("amin", 1e-7)]
+    assert params(tac.mu_law_encoding) == [("x", E), ("n_quantize", 256)]
+    assert params(tac.mu_law_decoding)[:2] == [("x_mu", E), ("n_quantize", 256)]
+
+
+def test_module_structure_and_state(tac):
+    mel = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512, num_freqs=7)
+    assert isinstance(mel, torch.nn.Sequential)
+    kinds = [type(m) for m in mel]                                  # iterable children (layers.py:346, test_layers.py:69)
+    assert kinds == [tac.STFT, tac.ComplexNorm, tac.ApplyFilterbank]
+    assert mel[1].power == 2.0 and mel[2].filterbank.shape == (1025, 128)   # num_freqs argument ignored (layers.py:330-332)
+    with pytest.raises(TypeError):
+        tac.Melspectrogram()                 # like the reference: Spectrogram(**kwargs) needs fft_length (layers.py:346)
+    assert mel.state_dict() == {} and tac.STFT(512).state_dict() == {}
+    mel.load_state_dict({}, strict=True)
+    with_db = torch.nn.Sequential(*mel, tac.AmplitudeToDb())
+    assert with_db.state_dict() == {}
+    spec = tac.Spectrogram(512, hop_length=128)
+    assert [type(m) for m in spec] == [tac.STFT, tac.ComplexNorm] and spec[1].power == 1.0
+    # tests/test_layers.py:18-38
+    layer = tac.STFT(fft_length=512, hop_length=256, pad_mode='reflect')
+    assert torch.is_tensor(layer.window) and not layer.window.requires_grad and layer.window.size(0) <= layer.fft_length
+    assert "window" in dict(layer.named_buffers())
+    assert tac.STFT(512, win_length=400).window.shape == (400,)
+
+    class Flat(tac.Filterbank):
+        def __init__(self, num_freqs, num_mels, **kw):
+            self.shape = (num_freqs, num_mels)
+
+        def get_filterbank(self):
+            return torch.ones(self.shape)
+
+    custom = tac.Melspectrogram(num_mels=10, mel_filterbank=Flat, fft_length=256)
+    assert custom[2].filterbank.shape == (129, 10)
+    with pytest.raises(NotImplementedError):
+        tac.Filterbank().get_filterbank()
+
+
+def test_repr_strings(tac):
+    assert repr(tac.STFT(512, 128)) == ("STFT(fft_length=512, hop_length=128, win_length=None)"
+                                        "(center=True, pad_mode=reflect, normalized=False, onesided=True)")
+    assert repr(tac.ComplexNorm(2.0)) == "ComplexNorm(power=2.0)"
+    assert repr(tac.MelFilterbank(sample_rate=16000)) == ("MelFilterbank(num_freqs=1025, snum_mels=128, min_freq=0.0, "
+                                                          "max_freq=8000), htk=False")
+    assert repr(tac.AmplitudeToDb()) == "AmplitudeToDb(ref=1.0, amin=1e-07)"
+    assert repr(tac.MuLawEncoding()) == "MuLawEncoding(n_quantize=256)" and repr(tac.MuLawDecoding(64)) == "MuLawDecoding(n_quantize=64)"
+
+
+def test_constructor_errors(tac):
+    with pytest.raises(ValueError):
+        tac.MelFilterbank()                                      # layers.py:188-190
+    with pytest.raises(AssertionError):
+        tac.AmplitudeToDb(ref=1e-8, amin=1e-7)                   # layers.py:366-367
+    assert tac.MelFilterbank(sample_rate=22050).max_freq == 11025 and isinstance(tac.MelFilterbank(sample_rate=22050).max_freq, int)
+
+
+def test_mel_matrix_is_bit_identical_to_the_reference(tac):
+    g = golden("filterbanks.npz")
+    assert torch.equal(tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank(), g["fb_16k_1025x128"])
+    assert torch.equal(tac.Melspectrogram(num_mels=128, sample_rate=48000, fft_length=2048)[2].filterbank, g["fb_48k_1025x128"])
+    for fft in (256, 512, 1024, 4096):
+        assert torch.equal(tac.create_mel_filter(fft // 2 + 1, 128, 0.0, 8000, False), g["fb_16k_%dx128" % (fft // 2 + 1)])
+    assert torch.equal(tac.MelFilterbank(1025, 40, 30.0, None, 22050, True).get_filterbank(), g["fb_htk_22k_1025x40"])
+    assert torch.equal(tac.MelFilterbank(num_freqs=257, num_mels=128, max_freq=1.0).get_filterbank(), g["fb_maxfreq1_257x128"])
+
+
+def test_no_cpu_fallback(tac):
+    x = torch.randn(1, 1, 4000)
+    for call in (lambda: tac.Spectrogram(512, 128)(x), lambda: tac.stft(x, 512), lambda: tac.mu_law_encoding(x),
+                 lambda: tac.mu_law_decoding(torch.arange(4)), lambda: tac.amplitude_to_db(x),
+                 lambda: tac.complex_norm(torch.randn(4, 2)), lambda: tac.apply_filterbank(torch.randn(1, 257, 9), torch.randn(257, 5)),
+                 lambda: tac.Melspectrogram(fft_length=2048)(x)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            tac.HostPipeline(512, 128)
+
+
+def test_missing_library_fails_loudly(tac, tmp_path):
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        saved = tac._cabi._lib
+        tac._cabi._lib = None
+        try:
+            tac._cabi.load(str(tmp_path / "absent.so"))
+        finally:
+            tac._cabi._lib = saved

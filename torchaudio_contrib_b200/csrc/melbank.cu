@@ -24,26 +24,35 @@ namespace tac {
 
 constexpr int kMbRows = 128;
 constexpr int kMbBK = 32;
-constexpr int kMbStages = 3;
+constexpr int kMbMaxStages = 8;
 constexpr int kMbProducerWarps = 8;
 constexpr int kMbProducerThreads = kMbProducerWarps * 32;
 constexpr int kMbThreads = kMbProducerThreads + 64;
 constexpr int kMbBandBlock = 128;
 constexpr int kMbTileBytes = kMbRows * kMbBK * 4;          // 16 KB: one operand tile
-constexpr int kMbStageBytes = 4 * kMbTileBytes;            // A_hi, A_lo, B_hi, B_lo
-constexpr size_t kMbSmemBytes = (size_t)kMbStages * kMbStageBytes + 1024;   // + alignment slack
+// Stage = {A_hi, A_lo, B_hi, B_lo}.  Slots are sized at launch: A by the tile height, B by the widest
+// band block of the plan, so a mel matrix (<= 48 bands per slice) gets 6-8 stages in flight instead of 3.
+constexpr size_t kMbStageBudget = 192 * 1024;
+constexpr size_t kMbSmemBytes = kMbStageBudget + kMbTileBytes + 1024;   // + over-read slack (UMMA M = 128) + alignment
 constexpr uint32_t kPlanMagic = 0x7ac0fb01u;
 
 struct FbPlanHeader {
   uint32_t magic;
   int32_t n_bins, n_bands, n_chunks, n_bblocks;
-  int32_t reserved[3];
+  int32_t max_n;      // widest block (bands) over all K slices
+  int32_t reserved[2];
 };
 struct FbPlanChunk {
   int32_t band_lo;    // first band of the block, relative to the band block, multiple of 16
   int32_t n;          // bands in the block, multiple of 16, 0 = nothing to do for this K slice
   int32_t blob_off;   // byte offset of the hi image from the start of the plan (lo image follows)
   int32_t reserved;
+};
+
+enum MelbankSource {
+  SRC_TILES = 0,           // power tiles written by the STFT kernel (stft_params.cuh: power_tile_index)
+  SRC_PUBLIC_REAL = 1,     // (n_seq, bins, frames)     reference layout of a magnitude / power spectrogram
+  SRC_PUBLIC_COMPLEX = 2   // (n_seq, bins, frames, 2)  reference layout of a complex spectrogram
 };
 
 struct MelbankParams {
@@ -53,12 +62,10 @@ struct MelbankParams {
   int64_t rows;          // frames handled by this launch
   int64_t g_base;        // flattened frame index (seq * frames + t) of row 0
   int64_t frames;        // frames per sequence
-  int layout;            // 0: frame-major rows src[row * kpad + bin]; 1: public src[((seq*bins)+bin)*frames + t]
-  int is_complex;        // public layout only: src holds (re, im) pairs
   int power_mode;        // complex input: 2 -> re^2+im^2, 1 -> sqrt, 0 -> pow(., power/2)
-  float power;
-  int n_bins, n_bands, kpad;
-  int rows_per_tile;
+  float half_power;
+  int n_bins, n_bands;
+  int rows_per_tile;     // <= 128; SRC_TILES: the tile height the STFT kernel wrote (multiple of 8)
   int to_db;
   float amin, log10_ref;
 };
@@ -87,16 +94,17 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& l
   lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
-__device__ __forceinline__ float power_of(float re, float im, float power, int mode) {
+__device__ __forceinline__ float power_of(float re, float im, float half_power, int mode) {
   const float s = fmaf(re, re, im * im);
   if (mode == 2) return s;
   if (mode == 1) return sqrtf(s);
-  return s > 0.0f ? powf(s, 0.5f * power) : (power == 0.0f ? 1.0f : 0.0f);
+  return s > 0.0f ? exp2f(half_power * __log2f(s)) : (half_power == 0.0f ? 1.0f : 0.0f);
 }
 
+template <int SRC>
 __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  __shared__ uint64_t s_full_b[kMbStages], s_a_ready[kMbStages], s_empty[kMbStages], s_accum;
+  __shared__ uint64_t s_full[kMbMaxStages], s_a_ready[kMbMaxStages], s_empty[kMbMaxStages], s_accum;
   __shared__ uint32_t s_tmem;
 
   // 1024-byte aligned stage buffers (swizzle atoms must not straddle 1 KB boundaries)
@@ -107,13 +115,20 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   const int n_chunks = hdr->n_chunks;
   const FbPlanChunk* chunks = reinterpret_cast<const FbPlanChunk*>(p.plan + sizeof(FbPlanHeader)) + (size_t)blockIdx.y * n_chunks;
 
-  const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_tile;
-  const int valid = (int)min((int64_t)p.rows_per_tile, p.rows - row0);
+  const int tile_rows = p.rows_per_tile;
+  const int64_t row0 = (int64_t)blockIdx.x * tile_rows;
+  const int valid = (int)min((int64_t)tile_rows, p.rows - row0);
+  const uint32_t a_tile_bytes = (uint32_t)tile_rows * 128u;
+  // stage geometry from the tile height and the widest block recorded in the plan header
+  const uint32_t a_slot = (a_tile_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)max(hdr->max_n, 16) * 128u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = 2 * a_slot + 2 * b_slot;
+  const int n_stages = max(2, min(kMbMaxStages, (int)(kMbStageBudget / stage_bytes)));
 
   if (warp == kMbProducerWarps && lane == 0) {
-    for (int s = 0; s < kMbStages; ++s) {
-      mbar_init(&s_full_b[s], 1);
-      mbar_init(&s_a_ready[s], kMbProducerThreads);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_a_ready[s], kMbProducerWarps);
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_accum, 1);
@@ -140,42 +155,62 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   __syncthreads();
   tc_fence_after();
 
-  if (warp < kMbProducerWarps) {
-    // =========================== P-tile producers ===============================================
-    // layout 0: thread -> rows r = tid/8 + 32 i, 16-byte column c16 = tid % 8   (coalesced 128 B rows)
-    // layout 1: thread -> row m = tid % 128, columns c16 = 4 * (tid / 128) + i  (coalesced along time)
-    const int64_t g_first = p.g_base + row0;
-    float4 cur[4], nxt[4];
+  auto next_active = [&](int c) {
+    while (c < n_chunks && chunks[c].n == 0) ++c;
+    return c;
+  };
 
-    auto load_chunk = [&](int c, float4 (&v)[4]) {
-      const int k0 = c * kMbBK;
-      if (p.layout == 0) {
-        const int c16 = tid & 7;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (tid >> 3) + 32 * i;
-          v[i] = (r < valid) ? ldg_stream_f4(reinterpret_cast<const float4*>(p.src + (row0 + r) * p.kpad + k0) + c16)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp < kMbProducerWarps) {
+    const int64_t g_first = p.g_base + row0;
+    if constexpr (SRC == SRC_TILES) {
+      // ====================== in-place hi/lo split of TMA-delivered tiles ==========================
+      // The STFT kernel already wrote the rows in the swizzled operand layout, so a tile is one
+      // contiguous block: the loader warp bulk-copies it into the A_hi slot; here every 16-byte unit
+      // is split v -> (hi, lo) at the same offset of the A_hi / A_lo slots (layout preserving).
+      int it = 0;
+      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+        mbar_wait(&s_full[s], ph);
+        float4* a_hi = reinterpret_cast<float4*>(stage0 + (size_t)s * stage_bytes);
+        float4* a_lo = reinterpret_cast<float4*>(stage0 + (size_t)s * stage_bytes + a_slot);
+        const int units = tile_rows * 8;
+        for (int u = tid; u < units; u += kMbProducerThreads) {
+          float4 hi, lo;
+          split_tf32(a_hi[u], hi, lo);
+          a_hi[u] = hi;
+          a_lo[u] = lo;
         }
-      } else {
-        const int m = tid & 127;
-        const bool ok = m < valid;
-        const int64_t g = g_first + m;
-        const int64_t seq = g / p.frames, t = g - seq * p.frames;
-        const int64_t base = seq * p.n_bins * p.frames + t;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_a_ready[s]);
+      }
+    } else {
+      // ====================== P-tile producers for the reference layouts ===========================
+      // thread -> row m = tid % 128 (lanes run along the contiguous time axis), 16-byte columns
+      // c16 = 4 * (tid / 128) + i.  Two register buffers alternate so that the loads of slice c+1
+      // are in flight while slice c is converted and stored.
+      const int m = tid & 127;
+      const bool ok = m < valid;
+      const int64_t g = g_first + m;
+      const int64_t seq = g / p.frames, t = g - seq * p.frames;
+      const int64_t base = seq * p.n_bins * p.frames + t;
+      const int c16_0 = 4 * (tid >> 7);
+
+      auto load_chunk = [&](int c, float4 (&v)[4]) {
+        const int k0 = c * kMbBK + 4 * c16_0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int kk = k0 + 4 * (4 * (tid >> 7) + i);
           float e[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int k = kk + j;
+            const int k = k0 + 4 * i + j;
             float val = 0.0f;
             if (ok && k < p.n_bins) {
               const int64_t idx = base + (int64_t)k * p.frames;
-              if (p.is_complex) {
+              if constexpr (SRC == SRC_PUBLIC_COMPLEX) {
                 const float2 z = __ldg(reinterpret_cast<const float2*>(p.src) + idx);
-                val = power_of(z.x, z.y, p.power, p.power_mode);
+                val = power_of(z.x, z.y, p.half_power, p.power_mode);
               } else {
                 val = ldg_stream_f1(p.src + idx);
               }
@@ -184,47 +219,40 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
           }
           v[i] = make_float4(e[0], e[1], e[2], e[3]);
         }
-      }
-    };
-    auto store_chunk = [&](unsigned char* a_hi, unsigned char* a_lo, const float4 (&v)[4]) {
+      };
+      int it = 0;
+      auto store_chunk = [&](const float4 (&v)[4]) {
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+        mbar_wait(&s_empty[s], ph ^ 1u);
+        unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
+        unsigned char* a_lo = a_hi + a_slot;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int r, c16;
-        if (p.layout == 0) {
-          r = (tid >> 3) + 32 * i;
-          c16 = tid & 7;
-        } else {
-          r = tid & 127;
-          c16 = 4 * (tid >> 7) + i;
+        for (int i = 0; i < 4; ++i) {
+          float4 hi, lo;
+          split_tf32(v[i], hi, lo);
+          const uint32_t off = swz_off(m, c16_0 + i);
+          *reinterpret_cast<float4*>(a_hi + off) = hi;
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
         }
-        float4 hi, lo;
-        split_tf32(v[i], hi, lo);
-        const uint32_t off = swz_off(r, c16);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_a_ready[s]);
+        ++it;
+      };
+      float4 buf_a[4], buf_b[4];
+      int c0 = next_active(0);
+      if (c0 < n_chunks) load_chunk(c0, buf_a);
+      while (c0 < n_chunks) {
+        const int c1 = next_active(c0 + 1);
+        if (c1 < n_chunks) load_chunk(c1, buf_b);
+        store_chunk(buf_a);
+        if (c1 >= n_chunks) break;
+        const int c2 = next_active(c1 + 1);
+        if (c2 < n_chunks) load_chunk(c2, buf_a);
+        store_chunk(buf_b);
+        c0 = c2;
       }
-    };
-
-    // first active slice
-    int c = 0;
-    while (c < n_chunks && chunks[c].n == 0) ++c;
-    if (c < n_chunks) load_chunk(c, cur);
-    int it = 0;
-    while (c < n_chunks) {
-      int c_next = c + 1;
-      while (c_next < n_chunks && chunks[c_next].n == 0) ++c_next;
-      if (c_next < n_chunks) load_chunk(c_next, nxt);
-      const int s = it % kMbStages;
-      const uint32_t ph = (uint32_t)(it / kMbStages) & 1u;
-      mbar_wait(&s_empty[s], ph ^ 1u);
-      unsigned char* st = stage0 + (size_t)s * kMbStageBytes;
-      store_chunk(st, st + kMbTileBytes, cur);
-      fence_proxy_async();
-      mbar_arrive(&s_a_ready[s]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-      c = c_next;
-      ++it;
     }
 
     // =========================== epilogue =======================================================
@@ -259,17 +287,16 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     // =========================== MMA issuer =====================================================
     if (lane == 0) {
       int it = 0;
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
         const int n = chunks[c].n;
-        if (n == 0) continue;
-        const int s = it % kMbStages;
-        const uint32_t ph = (uint32_t)(it / kMbStages) & 1u;
-        mbar_wait(&s_full_b[s], ph);
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+        mbar_wait(&s_full[s], ph);
         mbar_wait(&s_a_ready[s], ph);
         tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + (size_t)s * kMbStageBytes);
-        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kMbTileBytes);
-        const uint64_t b_hi = umma_desc_sw128(st + 2 * kMbTileBytes), b_lo = umma_desc_sw128(st + 3 * kMbTileBytes);
+        const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
+        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + a_slot);
+        const uint64_t b_hi = umma_desc_sw128(st + 2 * a_slot), b_lo = umma_desc_sw128(st + 2 * a_slot + b_slot);
         const uint32_t idesc = umma_idesc_tf32(n);
         const uint32_t d = tmem + (uint32_t)chunks[c].band_lo;
 #pragma unroll
@@ -279,26 +306,30 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
           tc_mma_tf32(d, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
         }
         tc_commit(&s_empty[s]);
-        ++it;
       }
       tc_commit(&s_accum);
     }
   } else {
-    // =========================== plan block loader ==============================================
+    // =========================== bulk-copy loader ===============================================
     if (lane == 0) {
       int it = 0;
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
         const int n = chunks[c].n;
-        if (n == 0) continue;
-        const int s = it % kMbStages;
-        const uint32_t ph = (uint32_t)(it / kMbStages) & 1u;
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         mbar_wait(&s_empty[s], ph ^ 1u);
-        unsigned char* st = stage0 + (size_t)s * kMbStageBytes;
+        unsigned char* st = stage0 + (size_t)s * stage_bytes;
         const uint32_t bytes = (uint32_t)n * 128u;
-        mbar_arrive_expect_tx(&s_full_b[s], 2 * bytes);
-        bulk_g2s(st + 2 * kMbTileBytes, p.plan + chunks[c].blob_off, bytes, &s_full_b[s]);
-        bulk_g2s(st + 3 * kMbTileBytes, p.plan + chunks[c].blob_off + bytes, bytes, &s_full_b[s]);
-        ++it;
+        if constexpr (SRC == SRC_TILES) {
+          mbar_arrive_expect_tx(&s_full[s], 2 * bytes + a_tile_bytes);
+          const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.src) +
+                                       ((size_t)blockIdx.x * n_chunks + c) * a_tile_bytes;
+          bulk_g2s(st, a_src, a_tile_bytes, &s_full[s]);
+        } else {
+          mbar_arrive_expect_tx(&s_full[s], 2 * bytes);
+        }
+        bulk_g2s(st + 2 * a_slot, p.plan + chunks[c].blob_off, bytes, &s_full[s]);
+        bulk_g2s(st + 2 * a_slot + b_slot, p.plan + chunks[c].blob_off + bytes, bytes, &s_full[s]);
       }
     }
   }
@@ -308,52 +339,51 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   if (warp == kMbProducerWarps + 1) tmem_dealloc(tmem, kMbBandBlock);
 }
 
-int launch_melbank(MelbankParams p, cudaStream_t stream) {
-  if (p.rows <= 0) return TAC_OK;
-  static bool configured[64] = {false};
-  int dev = 0;
-  TAC_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    TAC_CUDA_OK(cudaFuncSetAttribute(melbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMbSmemBytes));
-    configured[dev] = true;
-  }
-  const int sms = sm_count();
-  int64_t tiles = (p.rows + kMbRows - 1) / kMbRows;
-  if (tiles > sms) tiles = ((tiles + sms - 1) / sms) * sms;      // even out the last wave
-  const int rpt = (int)((p.rows + tiles - 1) / tiles);
-  tiles = (p.rows + rpt - 1) / rpt;
-  p.rows_per_tile = rpt;
+template <int SRC>
+static int launch_melbank(MelbankParams p, int64_t tiles, cudaStream_t stream) {
+  TAC_CUDA_OK(cudaFuncSetAttribute(melbank_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMbSmemBytes));
   const int bblocks = (p.n_bands + kMbBandBlock - 1) / kMbBandBlock;
   dim3 grid((unsigned)tiles, (unsigned)bblocks);
   LaunchProbe probe(KIND_MELBANK, stream);
-  melbank_kernel<<<grid, kMbThreads, kMbSmemBytes, stream>>>(p);
+  melbank_kernel<SRC><<<grid, kMbThreads, kMbSmemBytes, stream>>>(p);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
 }
 
-// frame-major rows written by the STFT kernel (pipeline path)
-int launch_melbank_rows(const float* rows, int64_t n_rows, int64_t g_base, int64_t frames, int n_bins, int kpad,
-                        const void* plan_dev, int n_bands, int to_db, float ref, float amin, float* out,
-                        cudaStream_t stream) {
-  TAC_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0 && (kpad & 31) == 0, TAC_ERR_INVALID,
-              "melbank: power rows must be 16-byte aligned with a row length that is a multiple of 32");
+// power tiles written by the STFT kernel (pipeline path); tile_rows is the height it used
+int launch_melbank_tiles(const float* tiles_ws, int64_t n_rows, int tile_rows, int64_t g_base, int64_t frames, int n_bins,
+                         const void* plan_dev, int n_bands, int to_db, float ref, float amin, float* out,
+                         cudaStream_t stream) {
+  if (n_rows <= 0) return TAC_OK;
+  TAC_REQUIRE((reinterpret_cast<uintptr_t>(tiles_ws) & 127) == 0 && tile_rows >= 8 && tile_rows <= kMbRows && (tile_rows & 7) == 0,
+              TAC_ERR_INVALID, "melbank: power tiles must be 128-byte aligned, tile height a multiple of 8 in [8, 128]");
   TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melbank: plan must be 16-byte aligned");
   MelbankParams p;
   memset(&p, 0, sizeof(p));
-  p.src = rows;
+  p.src = tiles_ws;
   p.plan = static_cast<const unsigned char*>(plan_dev);
   p.out = out;
   p.rows = n_rows;
   p.g_base = g_base;
   p.frames = frames;
-  p.layout = 0;
   p.n_bins = n_bins;
   p.n_bands = n_bands;
-  p.kpad = kpad;
+  p.rows_per_tile = tile_rows;
   p.to_db = to_db ? 1 : 0;
   p.amin = amin;
   p.log10_ref = log10f(ref);
-  return launch_melbank(p, stream);
+  return launch_melbank<SRC_TILES>(p, (n_rows + tile_rows - 1) / tile_rows, stream);
+}
+
+// rows per tile that spreads `rows` frames evenly over the SMs (<= 128, multiple of 8)
+int balanced_tile_rows(int64_t rows) {
+  const int sms = sm_count();
+  const int64_t waves = (rows + (int64_t)sms * kMbRows - 1) / ((int64_t)sms * kMbRows);
+  int64_t tr = (rows + waves * sms - 1) / (waves * sms);
+  tr = ((tr + 7) / 8) * 8;
+  if (tr < 8) tr = 8;
+  if (tr > kMbRows) tr = kMbRows;
+  return (int)tr;
 }
 
 }  // namespace tac
@@ -410,6 +440,7 @@ extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, v
       const int n = rel_hi - rel_lo;
       e.band_lo = rel_lo;
       e.n = n;
+      if (n > hdr->max_n) hdr->max_n = n;
       e.blob_off = (int32_t)off;
       float* img_hi = reinterpret_cast<float*>(base + off);
       float* img_lo = reinterpret_cast<float*>(base + off + (int64_t)n * 128);
@@ -451,15 +482,15 @@ extern "C" int tac_power_mel_f32(const float* spec, int is_complex, float power,
   p.rows = n_seq * frames;
   p.g_base = 0;
   p.frames = frames;
-  p.layout = 1;
-  p.is_complex = is_complex ? 1 : 0;
-  p.power = power;
+  p.half_power = 0.5f * power;
   p.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
   p.n_bins = n_bins;
   p.n_bands = n_bands;
-  p.kpad = kpad_for_bins(n_bins);
+  p.rows_per_tile = balanced_tile_rows(p.rows);
   p.to_db = to_db ? 1 : 0;
   p.amin = amin;
   p.log10_ref = log10f(ref);
-  return launch_melbank(p, as_stream(stream));
+  const int64_t tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
+  return is_complex ? launch_melbank<SRC_PUBLIC_COMPLEX>(p, tiles, as_stream(stream))
+                    : launch_melbank<SRC_PUBLIC_REAL>(p, tiles, as_stream(stream));
 }

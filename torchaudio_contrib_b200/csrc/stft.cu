@@ -55,7 +55,7 @@ __device__ __forceinline__ float spectral_power(float re, float im, float power,
 __device__ __forceinline__ void emit_bin(const StftParams& p, int64_t seq, int64_t t, int64_t row, int k,
                                          float re, float im) {
   if (p.out_mode == OUT_POWER_ROWS) {
-    p.out[row * p.kpad + k] = spectral_power(re, im, p.power, p.power_mode);
+    p.out[power_tile_index(row, k, p.tile_rows, p.kpad)] = spectral_power(re, im, p.power, p.power_mode);
   } else if (p.out_mode == OUT_POWER_PUBLIC) {
     p.out[(seq * p.bins + k) * p.frames + t] = spectral_power(re, im, p.power, p.power_mode);
   } else {
@@ -72,10 +72,25 @@ constexpr int kSlabComplex = 32 * 33;                        // transposition sl
 constexpr size_t kFastSmemBytes = 3 * 1024 * sizeof(float2)  // window pairs, tw1, tw2
                                   + kFastWarps * sizeof(uint64_t) + kFastWarps * kSlabComplex * sizeof(float2);
 
+// |X|^p with the exponent resolved at compile time (PMODE 2: p = 2, 1: p = 1, 0: runtime p through
+// the hardware lg2 / ex2 units -- ~1e-6 relative, far inside the parity budget)
+template <int PMODE>
+__device__ __forceinline__ float fast_power(float re, float im, float half_power) {
+  const float s = fmaf(re, re, im * im);
+  if constexpr (PMODE == 2) return s;
+  if constexpr (PMODE == 1) return sqrtf(s);
+  return s > 0.0f ? exp2f(half_power * __log2f(s)) : (half_power == 0.0f ? 1.0f : 0.0f);
+}
+
+// The kernel is specialised on the output mode and the exponent: the frame loop is ~2k fully
+// unrolled instructions and has to stay resident in the instruction caches while 16 warps run
+// through it at different phases (a first version that branched on these at run time was 12k
+// instructions and spent most of its time stalled on instruction fetch).
+template <int OUT_MODE, int PMODE>
 __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_win = reinterpret_cast<float2*>(smem_raw);      // [1024]   (w[2n], w[2n+1]) * 0.5 * scale
-  float2* s_tw1 = s_win + 1024;                             // [k2][n1] W_1024^(n1 k2)
+  float2* s_tw1 = s_win + 1024;                             // [n1][k2] W_1024^(n1 k2)
   float2* s_tw2 = s_tw1 + 1024;                             // [k1][l]  W_2048^(32 k1 + l)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + 1024);
   float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
@@ -101,17 +116,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   float2* slab = s_slab + warp * kSlabComplex;
   float* slab_f = reinterpret_cast<float*>(slab);
   const int64_t step = (int64_t)gridDim.x * kFastWarps;
+  const float half_power = 0.5f * p.power;
   uint32_t parity = 0;
 
   // a frame can use the bulk copy when it lies inside the sequence and everything is 16B aligned
-  auto frame_origin = [&](int64_t g, int64_t& seq, int64_t& t, int64_t& start) {
-    seq = g / p.frames;
-    t = g - seq * p.frames;
-    start = t * p.hop - p.pad;
-  };
   auto stage_frame = [&](int64_t g) -> bool {    // returns true when a bulk copy is in flight
-    int64_t seq, t, start;
-    frame_origin(g, seq, t, start);
+    const int64_t seq = g / p.frames;
+    const int64_t start = (g - seq * p.frames) * p.hop - p.pad;
     const float* row = p.x + seq * p.seq_stride;
     const bool bulk = p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples;
     if (bulk) {
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
         bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);
       }
     } else {
-#pragma unroll 8
+#pragma unroll 4
       for (int i = 0; i < 64; ++i) {
         const int j = lane + 32 * i;
         slab_f[j] = fetch_padded(row, start + j, p.n_samples, p.pad_mode);
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   bool in_flight = false;
   if (g < p.g1) in_flight = stage_frame(g);
 
+#pragma unroll 1
   for (; g < p.g1; g += step) {
     if (in_flight) {
       mbar_wait(bar, parity);
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       __syncwarp();
     }
 
-    // ---- pass 1: lane = n1, register r <-> n = n1 + 32 r --------------------------------------
+    // ---- load: lane = n1, register r <-> z[n], n = n1 + 32 r, windowed ------------------------------
     float2 v[32];
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
@@ -151,54 +163,72 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       v[r] = make_float2(xs.x * w.x, xs.y * w.y);
     }
     __syncwarp();                                  // samples consumed; slab becomes the transpose buffer
-    dif_fft<32>(v);
+
+    // ---- two 32-point passes sharing one copy of the butterfly code ----------------------------------
+#pragma unroll 1
+    for (int pass = 0;; ++pass) {
+      dif_fft<32>(v);
+      if (pass == 1) break;
+      // transpose through the slab: row k2 gets this lane's k2-th output, then lane k2 reads its row
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      float2 a = v[bit_reverse<32>(k2)];
-      if (k2 > 0) {
-        const float2 w = s_tw1[k2 * 32 + lane];
-        a = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+      for (int k2 = 0; k2 < 32; ++k2) slab[k2 * 33 + lane] = v[bit_reverse<32>(k2)];
+      __syncwarp();
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const float2 a = slab[lane * 33 + n1];
+        const float2 w = s_tw1[n1 * 32 + lane];    // W_1024^(n1 * k2), k2 = lane
+        v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
       }
-      slab[k2 * 33 + lane] = a;
+      __syncwarp();                                // slab free again: prefetch the next frame
+      const int64_t g_next = g + step;
+      in_flight = (g_next < p.g1) ? stage_frame(g_next) : false;
     }
-    __syncwarp();
-    // ---- pass 2: lane = k2, register <-> n1 ------------------------------------------------------
-    float2 u[32];
-#pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) u[n1] = slab[lane * 33 + n1];
-    __syncwarp();                                  // slab free again: prefetch the next frame
-    const int64_t g_next = g + step;
-    in_flight = (g_next < p.g1) ? stage_frame(g_next) : false;
+    // now v[bit_reverse(k1)] = Z[32 k1 + lane] / 2
 
-    dif_fft<32>(u);                                // u[bit_reverse(k1)] = Z[32 k1 + lane] / 2
-
-    // ---- real-FFT untangling: bin k = 32 k1 + lane pairs with 1024 - k -------------------------
-    int64_t seq, t, start;
-    frame_origin(g, seq, t, start);
-    const int64_t row = g - p.g0;
+    // ---- real-FFT untangling: bin k = 32 k1 + lane pairs with 1024 - k ------------------------------
+    const int64_t seq = g / p.frames, t = g - seq * p.frames;
+    float* dst;
+    int64_t dst_stride;                            // floats between consecutive k1 (bins 32 apart)
+    if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+      const int64_t row = g - p.g0;               // power tiles: one 128-byte swizzled row segment per slice
+      dst = p.out + power_tile_index(row, lane, p.tile_rows, p.kpad);
+      dst_stride = 32 * p.tile_rows;
+    } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
+      dst = p.out + (seq * p.bins + lane) * p.frames + t;
+      dst_stride = 32 * p.frames;
+    } else {
+      dst = p.out + 2 * ((seq * p.bins + lane) * p.frames + t);
+      dst_stride = 64 * p.frames;
+    }
     const int partner = (32 - lane) & 31;
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) {
-      const float2 z = u[bit_reverse<32>(k1)];
+      const float2 z = v[bit_reverse<32>(k1)];
       float2 q;
-      q.x = __shfl_sync(0xffffffffu, u[bit_reverse<32>(31 - k1)].x, partner);
-      q.y = __shfl_sync(0xffffffffu, u[bit_reverse<32>(31 - k1)].y, partner);
-      if (lane == 0) q = u[bit_reverse<32>((32 - k1) & 31)];
+      q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].x, partner);
+      q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].y, partner);
+      if (lane == 0) q = v[bit_reverse<32>((32 - k1) & 31)];
       const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
       const float2 w = s_tw2[k1 * 32 + lane];      // (c, d), W = c + i d
       const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
       const float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
-      emit_bin(p, seq, t, row, 32 * k1 + lane, xr, xi);
+      if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
+        *reinterpret_cast<float2*>(dst) = make_float2(xr, xi);
+      } else {
+        *dst = fast_power<PMODE>(xr, xi, half_power);
+      }
+      dst += dst_stride;
     }
-    // Nyquist bin (and zero fill of the row padding in frame-major mode)
+    // Nyquist bin (and zero fill of the row padding in frame-major mode); dst now points at bin 1024 + lane
     {
-      const float2 z0 = u[0];
+      const float2 z0 = v[0];
       const float nyq = 2.0f * (z0.x - z0.y);
-      if (p.out_mode == OUT_POWER_ROWS) {
-        if (1024 + lane < p.kpad)
-          p.out[row * p.kpad + 1024 + lane] = (lane == 0) ? spectral_power(nyq, 0.0f, p.power, p.power_mode) : 0.0f;
-      } else if (lane == 0) {
-        emit_bin(p, seq, t, row, 1024, nyq, 0.0f);
+      if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+        if (1024 + lane < p.kpad) *dst = (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f;
+      } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
+        if (lane == 0) *dst = fast_power<PMODE>(nyq, 0.0f, half_power);
+      } else {
+        if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(nyq, 0.0f);
       }
     }
   }
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
       if (!p.onesided && k > 0 && k < C) emit_bin(p, seq, t, out_row, n_fft - k, xr, -xi);
     }
     if (p.out_mode == OUT_POWER_ROWS)
-      for (int k = C + 1 + tid; k < p.kpad; k += kGenThreads) p.out[out_row * p.kpad + k] = 0.0f;
+      for (int k = C + 1 + tid; k < p.kpad; k += kGenThreads) p.out[power_tile_index(out_row, k, p.tile_rows, p.kpad)] = 0.0f;
     __syncthreads();
   }
 }
@@ -287,17 +317,18 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
   if (p.n_fft == 2048 && p.onesided) {
-    static bool configured[64] = {false};
-    int dev = 0;
-    TAC_CUDA_OK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-      TAC_CUDA_OK(cudaFuncSetAttribute(stft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes));
-      configured[dev] = true;
-    }
     const int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());
+    using Kernel = void (*)(const StftParams);
+    Kernel k = nullptr;
+    if (p.out_mode == OUT_COMPLEX_PUBLIC) k = stft2048_kernel<OUT_COMPLEX_PUBLIC, 1>;
+    else if (p.out_mode == OUT_POWER_PUBLIC)
+      k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_PUBLIC, 1> : stft2048_kernel<OUT_POWER_PUBLIC, 0>);
+    else
+      k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_ROWS, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_ROWS, 1> : stft2048_kernel<OUT_POWER_ROWS, 0>);
+    TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes));
     LaunchProbe probe(KIND_STFT, stream);
-    stft2048_kernel<<<grid, kFastThreads, kFastSmemBytes, stream>>>(p);
+    k<<<grid, kFastThreads, kFastSmemBytes, stream>>>(p);
   } else {
     const size_t smem = generic_smem_bytes(p.n_fft);
     if (smem > 48 * 1024)
@@ -349,6 +380,7 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.g0 = 0;
   p.g1 = n_seq * p.frames;
   p.kpad = kpad_for_bins(p.bins);
+  p.tile_rows = 128;
   p.bulk_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (seq_stride & 3) == 0 && (hop & 3) == 0 && (pad & 3) == 0) ? 1 : 0;
   p.power = 1.0f;
   p.power_mode = 1;

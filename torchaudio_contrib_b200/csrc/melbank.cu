@@ -14,10 +14,13 @@
 //   only that [band_lo, band_lo + n) block is stored, copied and multiplied (UMMA N = n).  A mel
 //   matrix touches 16-32 of 128 bands per slice; a dense matrix degenerates to the full range.
 //
-// Warp roles (320 threads): warps 0-7 convert P tiles (global -> |.|^p -> hi/lo -> swizzled smem)
-// and later run the epilogue (TMEM -> registers -> dB -> global); warp 8 lane 0 issues the MMAs;
-// warp 9 lane 0 streams the plan blocks with 1-D bulk async copies.  Three 64 KB stages, mbarrier
-// full/empty handshakes, tcgen05.commit releases a stage when its MMAs have read it.
+// Warp roles (320 threads): warps 0-7 produce the A operand (power tile from smem, or |.|^p of values read
+// from global memory -> tf32 hi/lo split -> tcgen05.st into the stage's TMEM columns) and later run the
+// epilogue (TMEM -> registers -> dB -> global); warp 8 issues the MMAs (A from TMEM, B from smem) through one
+// elected lane; warp 9 streams the plan blocks (and the power tiles) with 1-D bulk async copies.  Up to six
+// stages, mbarrier full/ready/empty handshakes, tcgen05.commit releases a stage when its MMAs retired.
+#include <stdlib.h>
+
 #include "tac_common.cuh"
 
 namespace tac {
@@ -25,6 +28,7 @@ namespace tac {
 constexpr int kMbRows = 128;
 constexpr int kMbBK = 32;
 constexpr int kMbMaxStages = 8;
+constexpr int kMbMaxChunks = 512;                    // slice table held in shared memory: up to 16384 bins
 constexpr int kMbProducerWarps = 8;
 constexpr int kMbProducerThreads = kMbProducerWarps * 32;
 constexpr int kMbThreads = kMbProducerThreads + 64;
@@ -68,6 +72,7 @@ struct MelbankParams {
   int rows_per_tile;     // <= 128; SRC_TILES: the tile height the STFT kernel wrote (multiple of 8)
   int to_db;
   float amin, log10_ref;
+  int debug;             // TAC_MB_DEBUG bit field for timing experiments (0 in production)
 };
 
 // offset of element (row r, 16-byte column c16) inside a 128B-swizzled K-major tile
@@ -101,11 +106,25 @@ __device__ __forceinline__ float power_of(float re, float im, float half_power, 
   return s > 0.0f ? exp2f(half_power * __log2f(s)) : (half_power == 0.0f ? 1.0f : 0.0f);
 }
 
+__device__ long long g_mb_trace[4][80];     // TAC_MB_DEBUG & 8: clock64 stamps of block 0 (loader, producer, mma, misc)
+#define MB_TRACE(role, idx) do { if ((p.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 80) g_mb_trace[role][idx] = clock64(); } while (0)
+
+// TMEM map (512 columns allocated): [0, 128) accumulator D (lane = frame, column = band);
+// [128 + 64 s, 128 + 64 s + 64): A operand of pipeline stage s, columns 0-31 = hi, 32-63 = lo of the
+// 32 bins of the slice (lane = frame, column = bin).  Feeding A from tensor memory matters here: with
+// N = 16..48 bands an MMA does little math per operand byte, and an A operand read from shared memory
+// (128 rows x 32 B per instruction, three times per k-step) made each UTCHMMA cost ~55 cycles of
+// shared-memory bandwidth (measured); from TMEM only the small B block is read from shared memory.
+constexpr uint32_t kMbTmemCols = 512;
+constexpr uint32_t kMbTmemA0 = 128;
+constexpr int kMbTmemStages = 6;
+
 template <int SRC>
 __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ uint64_t s_full[kMbMaxStages], s_a_ready[kMbMaxStages], s_empty[kMbMaxStages], s_accum;
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) FbPlanChunk s_chunks[kMbMaxChunks];   // this band block's slice table (global reads here cost ~500 cycles per step)
 
   // 1024-byte aligned stage buffers (swizzle atoms must not straddle 1 KB boundaries)
   unsigned char* stage0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -113,17 +132,21 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
 
   const FbPlanHeader* hdr = reinterpret_cast<const FbPlanHeader*>(p.plan);
   const int n_chunks = hdr->n_chunks;
-  const FbPlanChunk* chunks = reinterpret_cast<const FbPlanChunk*>(p.plan + sizeof(FbPlanHeader)) + (size_t)blockIdx.y * n_chunks;
+  {
+    const int4* src = reinterpret_cast<const int4*>(p.plan + sizeof(FbPlanHeader)) + (size_t)blockIdx.y * n_chunks;
+    for (int i = threadIdx.x; i < n_chunks; i += kMbThreads) reinterpret_cast<int4*>(s_chunks)[i] = __ldg(src + i);
+  }
+  const FbPlanChunk* chunks = s_chunks;
 
   const int tile_rows = p.rows_per_tile;
   const int64_t row0 = (int64_t)blockIdx.x * tile_rows;
   const int valid = (int)min((int64_t)tile_rows, p.rows - row0);
   const uint32_t a_tile_bytes = (uint32_t)tile_rows * 128u;
-  // stage geometry from the tile height and the widest block recorded in the plan header
-  const uint32_t a_slot = (a_tile_bytes + 1023u) & ~1023u;
+  // stage = {raw A tile (SRC_TILES only), B_hi, B_lo}; sizes from the tile height and the widest plan block
+  const uint32_t a_slot = (SRC == SRC_TILES) ? ((a_tile_bytes + 1023u) & ~1023u) : 0u;
   const uint32_t b_slot = ((uint32_t)max(hdr->max_n, 16) * 128u + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 2 * a_slot + 2 * b_slot;
-  const int n_stages = max(2, min(kMbMaxStages, (int)(kMbStageBudget / stage_bytes)));
+  const uint32_t stage_bytes = a_slot + 2 * b_slot;
+  const int n_stages = max(2, min(kMbTmemStages, (int)(kMbStageBudget / stage_bytes)));
 
   if (warp == kMbProducerWarps && lane == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -135,13 +158,14 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     fence_mbar_init();
   }
   if (warp == kMbProducerWarps + 1) {
-    tmem_alloc(&s_tmem, kMbBandBlock);
+    tmem_alloc(&s_tmem, kMbTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) MB_TRACE(3, 0);
 
   // zero the accumulator: blocks of different K slices touch different column ranges, so every
   // MMA accumulates (there is no single "first" MMA per column)
@@ -161,96 +185,98 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   };
 
   if (warp < kMbProducerWarps) {
+    // =========================== A producers ====================================================
+    // thread = (frame row r = 32 * (warp % 4) + lane, bin half kh = warp / 4): it owns 16 consecutive bins
+    // of its row in every slice, splits them into tf32 hi / lo and stores both to the stage's TMEM columns
+    // (a warp can only touch the TMEM lane quarter warp % 4, which is why rows map to lanes this way).
+    const int q = warp & 3, kh = warp >> 2;
+    const int r = 32 * q + lane;
     const int64_t g_first = p.g_base + row0;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+
+    auto publish = [&](int s, const float (&v)[16]) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+        lo[i] = v[i] - hi[i];
+      }
+      const uint32_t ta = t_lane + kMbTmemA0 + 64u * (uint32_t)s + 16u * (uint32_t)kh;
+      tmem_st16(ta, hi);
+      tmem_st16(ta + 32u, lo);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_a_ready[s]);
+    };
+
     if constexpr (SRC == SRC_TILES) {
-      // ====================== in-place hi/lo split of TMA-delivered tiles ==========================
-      // The STFT kernel already wrote the rows in the swizzled operand layout, so a tile is one
-      // contiguous block: the loader warp bulk-copies it into the A_hi slot; here every 16-byte unit
-      // is split v -> (hi, lo) at the same offset of the A_hi / A_lo slots (layout preserving).
+      // the STFT kernel wrote the rows in the 128B-swizzled tile layout; the loader warp bulk-copies the
+      // (tile_rows x 32) block of this slice into the stage; reading a row's 16-byte units through the
+      // swizzle is bank-conflict free (8 consecutive rows hit 8 different 16-byte columns)
       int it = 0;
       for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         mbar_wait(&s_full[s], ph);
-        float4* a_hi = reinterpret_cast<float4*>(stage0 + (size_t)s * stage_bytes);
-        float4* a_lo = reinterpret_cast<float4*>(stage0 + (size_t)s * stage_bytes + a_slot);
-        const int units = tile_rows * 8;
-        for (int u = tid; u < units; u += kMbProducerThreads) {
-          float4 hi, lo;
-          split_tf32(a_hi[u], hi, lo);
-          a_hi[u] = hi;
-          a_lo[u] = lo;
+        if (tid == 0) MB_TRACE(1, 2 * it);
+        const unsigned char* raw = stage0 + (size_t)s * stage_bytes;
+        float v[16];
+        if (!(p.debug & 1)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t4 = *reinterpret_cast<const float4*>(raw + swz_off(r, 4 * kh + i));
+            v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+          }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_a_ready[s]);
+        mbar_wait(&s_empty[s], ph ^ 1u);          // the stage's TMEM columns are free (MMAs of its previous use retired)
+        publish(s, v);
+        if (tid == 0) MB_TRACE(1, 2 * it + 1);
       }
     } else {
-      // ====================== P-tile producers for the reference layouts ===========================
-      // thread -> row m = tid % 128 (lanes run along the contiguous time axis), 16-byte columns
-      // c16 = 4 * (tid / 128) + i.  Two register buffers alternate so that the loads of slice c+1
-      // are in flight while slice c is converted and stored.
-      const int m = tid & 127;
-      const bool ok = m < valid;
-      const int64_t g = g_first + m;
+      // reference layouts: values come straight from global memory (lanes run along the contiguous time
+      // axis); two register buffers alternate so the loads of slice c+1 fly while slice c is published
+      const bool ok = r < valid;
+      const int64_t g = g_first + r;
       const int64_t seq = g / p.frames, t = g - seq * p.frames;
       const int64_t base = seq * p.n_bins * p.frames + t;
-      const int c16_0 = 4 * (tid >> 7);
-
-      auto load_chunk = [&](int c, float4 (&v)[4]) {
-        const int k0 = c * kMbBK + 4 * c16_0;
+      auto load_chunk = [&](int c, float (&v)[16]) {
+        const int k0 = c * kMbBK + 16 * kh;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float e[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = k0 + 4 * i + j;
-            float val = 0.0f;
-            if (ok && k < p.n_bins) {
-              const int64_t idx = base + (int64_t)k * p.frames;
-              if constexpr (SRC == SRC_PUBLIC_COMPLEX) {
-                const float2 z = __ldg(reinterpret_cast<const float2*>(p.src) + idx);
-                val = power_of(z.x, z.y, p.half_power, p.power_mode);
-              } else {
-                val = ldg_stream_f1(p.src + idx);
-              }
+        for (int i = 0; i < 16; ++i) {
+          const int k = k0 + i;
+          float val = 0.0f;
+          if (ok && k < p.n_bins) {
+            const int64_t idx = base + (int64_t)k * p.frames;
+            if constexpr (SRC == SRC_PUBLIC_COMPLEX) {
+              const float2 z = __ldg(reinterpret_cast<const float2*>(p.src) + idx);
+              val = power_of(z.x, z.y, p.half_power, p.power_mode);
+            } else {
+              val = ldg_stream_f1(p.src + idx);
             }
-            e[j] = val;
           }
-          v[i] = make_float4(e[0], e[1], e[2], e[3]);
+          v[i] = val;
         }
       };
       int it = 0;
-      auto store_chunk = [&](const float4 (&v)[4]) {
+      auto publish_next = [&](const float (&v)[16]) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         mbar_wait(&s_empty[s], ph ^ 1u);
-        unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
-        unsigned char* a_lo = a_hi + a_slot;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 hi, lo;
-          split_tf32(v[i], hi, lo);
-          const uint32_t off = swz_off(m, c16_0 + i);
-          *reinterpret_cast<float4*>(a_hi + off) = hi;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_a_ready[s]);
+        publish(s, v);
         ++it;
       };
-      float4 buf_a[4], buf_b[4];
+      float buf_a[16], buf_b[16];
       int c0 = next_active(0);
       if (c0 < n_chunks) load_chunk(c0, buf_a);
       while (c0 < n_chunks) {
         const int c1 = next_active(c0 + 1);
         if (c1 < n_chunks) load_chunk(c1, buf_b);
-        store_chunk(buf_a);
+        publish_next(buf_a);
         if (c1 >= n_chunks) break;
         const int c2 = next_active(c1 + 1);
         if (c2 < n_chunks) load_chunk(c2, buf_a);
-        store_chunk(buf_b);
+        publish_next(buf_b);
         c0 = c2;
       }
     }
@@ -258,85 +284,118 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     // =========================== epilogue =======================================================
     mbar_wait(&s_accum, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int m = 32 * q + lane;
-    const bool ok = m < valid;
-    const int64_t g = g_first + m;
+    if (tid == 0) MB_TRACE(3, 2);
+    const bool ok = r < valid;
+    const int64_t g = g_first + r;
     const int64_t seq = g / p.frames, t = g - seq * p.frames;
-    const int band0 = blockIdx.y * kMbBandBlock + 64 * half;
-    float* out_base = p.out + (seq * p.n_bands + band0) * p.frames + t;
+    const int band0 = blockIdx.y * kMbBandBlock + 64 * kh;
+    float* outp = p.out + (seq * p.n_bands + band0) * p.frames + t;
+    const int n_here = min(64, p.n_bands - band0);           // bands this warp owns (<= 0: none)
+    const bool to_db = p.to_db != 0;
+    uint32_t acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float acc[16];
-      tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * half + 16 * j), acc);
+    for (int j = 0; j < 4; ++j) tmem_ld16_nowait(t_lane + (uint32_t)(64 * kh + 16 * j), acc[j]);
+    tc_wait_ld();
+    if (tid == 0) MB_TRACE(3, 1);
+    if (ok) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int b = 16 * j + i;
-        if (ok && band0 + b < p.n_bands) {
-          float v = acc[i];
-          if (p.to_db) {
-            float s2 = v * v;
-            s2 = (s2 < p.amin) ? p.amin : s2;
-            v = 10.0f * (log10f(s2) - p.log10_ref);
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (16 * j + i < n_here) {
+            float v = __uint_as_float(acc[j][i]);
+            if (to_db) {
+              float s2 = v * v;
+              s2 = (s2 < p.amin) ? p.amin : s2;
+              v = 10.0f * (log10f(s2) - p.log10_ref);
+            }
+            __stcs(outp, v);
           }
-          out_base[(int64_t)b * p.frames] = v;
+          outp += p.frames;
         }
       }
     }
   } else if (warp == kMbProducerWarps) {
     // =========================== MMA issuer =====================================================
-    if (lane == 0) {
-      int it = 0;
-      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
-        const int n = chunks[c].n;
-        const int s = it % n_stages;
-        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
-        mbar_wait(&s_full[s], ph);
-        mbar_wait(&s_a_ready[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
-        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + a_slot);
-        const uint64_t b_hi = umma_desc_sw128(st + 2 * a_slot), b_lo = umma_desc_sw128(st + 2 * a_slot + b_slot);
-        const uint32_t idesc = umma_idesc_tf32(n);
-        const uint32_t d = tmem + (uint32_t)chunks[c].band_lo;
+    // the whole warp walks the loop (converged), one elected lane issues
+    int it = 0;
+    for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
+      const int n = chunks[c].n;
+      const int s = it % n_stages;
+      const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+      mbar_wait(&s_full[s], ph);
+      mbar_wait(&s_a_ready[s], ph);
+      tc_fence_after();
+      if (lane == 0) MB_TRACE(2, 2 * it);
+      const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
+      const uint64_t b_hi = umma_desc_sw128(st + a_slot), b_lo = umma_desc_sw128(st + a_slot + b_slot);
+      const uint32_t a_hi = tmem + kMbTmemA0 + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+      const uint32_t idesc = umma_idesc_tf32(n);
+      const uint32_t d = tmem + (uint32_t)chunks[c].band_lo;
+      if (elect_one()) {
+        if (!(p.debug & 2)) {
 #pragma unroll
-        for (int ks = 0; ks < kMbBK / 8; ++ks) {        // UMMA K = 8 tf32 = 32 bytes -> +2 in the address field
-          tc_mma_tf32(d, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
-          tc_mma_tf32(d, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
-          tc_mma_tf32(d, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+          for (int ks = 0; ks < kMbBK / 8; ++ks) {      // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
+            tc_mma_tf32_ts(d, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+            tc_mma_tf32_ts(d, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
+            tc_mma_tf32_ts(d, a_hi + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+          }
         }
         tc_commit(&s_empty[s]);
       }
-      tc_commit(&s_accum);
+      __syncwarp();
+      if (lane == 0) MB_TRACE(2, 2 * it + 1);
     }
+    if (elect_one()) tc_commit(&s_accum);
+    __syncwarp();
   } else {
     // =========================== bulk-copy loader ===============================================
-    if (lane == 0) {
-      int it = 0;
-      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
-        const int n = chunks[c].n;
-        const int s = it % n_stages;
-        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
-        mbar_wait(&s_empty[s], ph ^ 1u);
-        unsigned char* st = stage0 + (size_t)s * stage_bytes;
-        const uint32_t bytes = (uint32_t)n * 128u;
+    int it = 0;
+    for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
+      const int n = chunks[c].n;
+      const int s = it % n_stages;
+      const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+      mbar_wait(&s_empty[s], ph ^ 1u);
+      if (lane == 0) MB_TRACE(0, 2 * it);
+      unsigned char* st = stage0 + (size_t)s * stage_bytes;
+      const uint32_t bytes = (uint32_t)n * 128u;
+      const unsigned char* b_src = p.plan + chunks[c].blob_off;
+      if (elect_one()) {
         if constexpr (SRC == SRC_TILES) {
-          mbar_arrive_expect_tx(&s_full[s], 2 * bytes + a_tile_bytes);
+          const uint32_t a_bytes = (p.debug & 4) ? 16u : a_tile_bytes;
+          mbar_arrive_expect_tx(&s_full[s], 2 * bytes + a_bytes);
           const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.src) +
                                        ((size_t)blockIdx.x * n_chunks + c) * a_tile_bytes;
-          bulk_g2s(st, a_src, a_tile_bytes, &s_full[s]);
+          bulk_g2s(st, a_src, a_bytes, &s_full[s]);
         } else {
           mbar_arrive_expect_tx(&s_full[s], 2 * bytes);
         }
-        bulk_g2s(st + 2 * a_slot, p.plan + chunks[c].blob_off, bytes, &s_full[s]);
-        bulk_g2s(st + 2 * a_slot + b_slot, p.plan + chunks[c].blob_off + bytes, bytes, &s_full[s]);
+        bulk_g2s(st + a_slot, b_src, bytes, &s_full[s]);
+        bulk_g2s(st + a_slot + b_slot, b_src + bytes, bytes, &s_full[s]);
       }
+      __syncwarp();
+      if (lane == 0) MB_TRACE(0, 2 * it + 1);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMbProducerWarps + 1) tmem_dealloc(tmem, kMbBandBlock);
+  if (tid == 0) MB_TRACE(3, 3);
+  if (warp == kMbProducerWarps + 1) tmem_dealloc(tmem, kMbTmemCols);
+}
+
+int dump_melbank_trace() {
+  long long h[4][80];
+  TAC_CUDA_OK(cudaDeviceSynchronize());
+  TAC_CUDA_OK(cudaMemcpyFromSymbol(h, g_mb_trace, sizeof(h)));
+  const long long t0 = h[3][0];
+  const char* names[4] = {"loader", "producer", "mma", "misc"};
+  for (int r = 0; r < 4; ++r) {
+    printf("%s:", names[r]);
+    for (int i = 0; i < (r == 3 ? 4 : 72); ++i) printf(" %lld", h[r][i] ? h[r][i] - t0 : -1);
+    printf("\n");
+  }
+  return TAC_OK;
 }
 
 template <int SRC>
@@ -344,6 +403,12 @@ static int launch_melbank(MelbankParams p, int64_t tiles, cudaStream_t stream) {
   TAC_CUDA_OK(cudaFuncSetAttribute(melbank_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMbSmemBytes));
   const int bblocks = (p.n_bands + kMbBandBlock - 1) / kMbBandBlock;
   dim3 grid((unsigned)tiles, (unsigned)bblocks);
+  static int debug_flags = -1;
+  if (debug_flags < 0) {
+    const char* e = getenv("TAC_MB_DEBUG");
+    debug_flags = e ? atoi(e) : 0;
+  }
+  p.debug = debug_flags;
   LaunchProbe probe(KIND_MELBANK, stream);
   melbank_kernel<SRC><<<grid, kMbThreads, kMbSmemBytes, stream>>>(p);
   TAC_CUDA_OK(cudaGetLastError());
@@ -466,11 +531,15 @@ extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, v
   return TAC_OK;
 }
 
+extern "C" int tac_debug_dump_melbank_trace(void) { return tac::dump_melbank_trace(); }
+
 extern "C" int tac_power_mel_f32(const float* spec, int is_complex, float power, int64_t n_seq, int64_t frames, int n_bins,
                                  const void* plan_dev, int n_bands, int to_db, float ref, float amin, float* out,
                                  void* stream) {
   using namespace tac;
   TAC_REQUIRE(n_seq >= 0 && frames >= 0 && n_bins > 0 && n_bands > 0, TAC_ERR_INVALID, "power_mel: bad shape");
+  TAC_REQUIRE(n_bins <= kMbMaxChunks * kMbBK, TAC_ERR_UNSUPPORTED, "power_mel: %d frequency bins exceed the %d supported",
+              n_bins, kMbMaxChunks * kMbBK);
   if (n_seq * frames == 0) return TAC_OK;
   TAC_REQUIRE(spec && plan_dev && out, TAC_ERR_INVALID, "power_mel: null pointer");
   TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "power_mel: plan must be 16-byte aligned");

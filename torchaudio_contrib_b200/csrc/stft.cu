@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     const float* row = p.x + seq * p.seq_stride;
     const bool bulk = p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples;
     if (bulk) {
-      if (lane == 0) {
+      if (elect_one()) {
         fence_proxy_async();
         mbar_arrive_expect_tx(bar, 2048 * sizeof(float));
         bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);

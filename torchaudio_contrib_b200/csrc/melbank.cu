@@ -110,21 +110,24 @@ __device__ long long g_mb_trace[4][80];     // TAC_MB_DEBUG & 8: clock64 stamps 
 #define MB_TRACE(role, idx) do { if ((p.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 80) g_mb_trace[role][idx] = clock64(); } while (0)
 
 // TMEM map (512 columns allocated): [0, 128) accumulator D (lane = frame, column = band);
-// [128 + 64 s, 128 + 64 s + 64): A operand of pipeline stage s, columns 0-31 = hi, 32-63 = lo of the
-// 32 bins of the slice (lane = frame, column = bin).  Feeding A from tensor memory matters here: with
-// N = 16..48 bands an MMA does little math per operand byte, and an A operand read from shared memory
-// (128 rows x 32 B per instruction, three times per k-step) made each UTCHMMA cost ~55 cycles of
+// [128 + 128 s, 128 + 128 s + 128): A operand of pipeline stage s = two 32-bin slices, each 32 columns of
+// hi followed by 32 columns of lo (lane = frame, column = bin).  Feeding A from tensor memory matters
+// here: with N = 16..48 bands an MMA does little math per operand byte, and an A operand read from shared
+// memory (128 rows x 32 B per instruction, three times per k-step) made each UTCHMMA cost ~55 cycles of
 // shared-memory bandwidth (measured); from TMEM only the small B block is read from shared memory.
+// A stage carries TWO slices (64 bins) because the per-stage handshake chain (bulk-copy latency ~1100
+// cycles, barrier wake-ups ~300) -- not the tensor pipe -- bounds the loop; fewer, larger stages halve it.
 constexpr uint32_t kMbTmemCols = 512;
 constexpr uint32_t kMbTmemA0 = 128;
-constexpr int kMbTmemStages = 6;
+constexpr int kMbTmemStages = 3;
+constexpr int kMbGroup = 2;                  // slices per stage
 
 template <int SRC>
 __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ uint64_t s_full[kMbMaxStages], s_a_ready[kMbMaxStages], s_empty[kMbMaxStages], s_accum;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) FbPlanChunk s_chunks[kMbMaxChunks];   // this band block's slice table (global reads here cost ~500 cycles per step)
+  __shared__ __align__(16) FbPlanChunk s_chunks[kMbMaxChunks + kMbGroup];   // slice table (global reads cost ~500 cycles per step)
 
   // 1024-byte aligned stage buffers (swizzle atoms must not straddle 1 KB boundaries)
   unsigned char* stage0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -132,9 +135,11 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
 
   const FbPlanHeader* hdr = reinterpret_cast<const FbPlanHeader*>(p.plan);
   const int n_chunks = hdr->n_chunks;
+  const int n_groups = (n_chunks + kMbGroup - 1) / kMbGroup;
   {
     const int4* src = reinterpret_cast<const int4*>(p.plan + sizeof(FbPlanHeader)) + (size_t)blockIdx.y * n_chunks;
-    for (int i = threadIdx.x; i < n_chunks; i += kMbThreads) reinterpret_cast<int4*>(s_chunks)[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n_groups * kMbGroup; i += kMbThreads)
+      reinterpret_cast<int4*>(s_chunks)[i] = (i < n_chunks) ? __ldg(src + i) : make_int4(0, 0, 0, 0);
   }
   const FbPlanChunk* chunks = s_chunks;
 
@@ -142,10 +147,10 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   const int64_t row0 = (int64_t)blockIdx.x * tile_rows;
   const int valid = (int)min((int64_t)tile_rows, p.rows - row0);
   const uint32_t a_tile_bytes = (uint32_t)tile_rows * 128u;
-  // stage = {raw A tile (SRC_TILES only), B_hi, B_lo}; sizes from the tile height and the widest plan block
-  const uint32_t a_slot = (SRC == SRC_TILES) ? ((a_tile_bytes + 1023u) & ~1023u) : 0u;
-  const uint32_t b_slot = ((uint32_t)max(hdr->max_n, 16) * 128u + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a_slot + 2 * b_slot;
+  // stage = {raw A tiles of the two slices (SRC_TILES only), B0 = [hi | lo], B1 = [hi | lo]}
+  const uint32_t a_slot = (SRC == SRC_TILES) ? ((kMbGroup * a_tile_bytes + 1023u) & ~1023u) : 0u;
+  const uint32_t b_slot = ((uint32_t)max(hdr->max_n, 16) * 256u + 1023u) & ~1023u;      // hi + lo of one slice
+  const uint32_t stage_bytes = a_slot + kMbGroup * b_slot;
   const int n_stages = max(2, min(kMbTmemStages, (int)(kMbStageBudget / stage_bytes)));
 
   if (warp == kMbProducerWarps && lane == 0) {
@@ -179,9 +184,11 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   __syncthreads();
   tc_fence_after();
 
-  auto next_active = [&](int c) {
-    while (c < n_chunks && chunks[c].n == 0) ++c;
-    return c;
+  // a group (stage) is active when at least one of its slices has a non-empty block
+  auto group_active = [&](int g) { return (chunks[kMbGroup * g].n | chunks[kMbGroup * g + 1].n) != 0; };
+  auto next_active = [&](int g) {
+    while (g < n_groups && !group_active(g)) ++g;
+    return g;
   };
 
   if (warp < kMbProducerWarps) {
@@ -194,16 +201,19 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     const int64_t g_first = p.g_base + row0;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
 
-    auto publish = [&](int s, const float (&v)[16]) {
-      float hi[16], lo[16];
+    auto publish = [&](int s, const float (&v)[16 * kMbGroup]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
-        lo[i] = v[i] - hi[i];
+      for (int j = 0; j < kMbGroup; ++j) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = __uint_as_float(__float_as_uint(v[16 * j + i]) & 0xFFFFE000u);
+          lo[i] = v[16 * j + i] - hi[i];
+        }
+        const uint32_t ta = t_lane + kMbTmemA0 + 128u * (uint32_t)s + 64u * (uint32_t)j + 16u * (uint32_t)kh;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
       }
-      const uint32_t ta = t_lane + kMbTmemA0 + 64u * (uint32_t)s + 16u * (uint32_t)kh;
-      tmem_st16(ta, hi);
-      tmem_st16(ta + 32u, lo);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -211,73 +221,78 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     };
 
     if constexpr (SRC == SRC_TILES) {
-      // the STFT kernel wrote the rows in the 128B-swizzled tile layout; the loader warp bulk-copies the
-      // (tile_rows x 32) block of this slice into the stage; reading a row's 16-byte units through the
+      // the STFT kernel wrote the rows in the 128B-swizzled tile layout; the loader warp bulk-copies the two
+      // (tile_rows x 32) blocks of this stage into shared memory; reading a row's 16-byte units through the
       // swizzle is bank-conflict free (8 consecutive rows hit 8 different 16-byte columns)
       int it = 0;
-      for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
+      for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         mbar_wait(&s_full[s], ph);
         if (tid == 0) MB_TRACE(1, 2 * it);
         const unsigned char* raw = stage0 + (size_t)s * stage_bytes;
-        float v[16];
+        float v[16 * kMbGroup];
         if (!(p.debug & 1)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t4 = *reinterpret_cast<const float4*>(raw + swz_off(r, 4 * kh + i));
-            v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+          for (int j = 0; j < kMbGroup; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t4 = *reinterpret_cast<const float4*>(raw + j * a_tile_bytes + swz_off(r, 4 * kh + i));
+              v[16 * j + 4 * i] = t4.x; v[16 * j + 4 * i + 1] = t4.y; v[16 * j + 4 * i + 2] = t4.z; v[16 * j + 4 * i + 3] = t4.w;
+            }
           }
         }
-        mbar_wait(&s_empty[s], ph ^ 1u);          // the stage's TMEM columns are free (MMAs of its previous use retired)
-        publish(s, v);
+        publish(s, v);       // TMEM columns of stage s are free: `full` implies the loader saw `empty`
         if (tid == 0) MB_TRACE(1, 2 * it + 1);
       }
     } else {
       // reference layouts: values come straight from global memory (lanes run along the contiguous time
-      // axis); two register buffers alternate so the loads of slice c+1 fly while slice c is published
+      // axis); two register buffers alternate so the loads of group g+1 fly while group g is published
       const bool ok = r < valid;
-      const int64_t g = g_first + r;
-      const int64_t seq = g / p.frames, t = g - seq * p.frames;
+      const int64_t gf = g_first + r;
+      const int64_t seq = gf / p.frames, t = gf - seq * p.frames;
       const int64_t base = seq * p.n_bins * p.frames + t;
-      auto load_chunk = [&](int c, float (&v)[16]) {
-        const int k0 = c * kMbBK + 16 * kh;
+      auto load_group = [&](int g, float (&v)[16 * kMbGroup]) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k = k0 + i;
-          float val = 0.0f;
-          if (ok && k < p.n_bins) {
-            const int64_t idx = base + (int64_t)k * p.frames;
-            if constexpr (SRC == SRC_PUBLIC_COMPLEX) {
-              const float2 z = __ldg(reinterpret_cast<const float2*>(p.src) + idx);
-              val = power_of(z.x, z.y, p.half_power, p.power_mode);
-            } else {
-              val = ldg_stream_f1(p.src + idx);
+        for (int j = 0; j < kMbGroup; ++j) {
+          const int k0 = (kMbGroup * g + j) * kMbBK + 16 * kh;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = k0 + i;
+            float val = 0.0f;
+            if (ok && k < p.n_bins) {
+              const int64_t idx = base + (int64_t)k * p.frames;
+              if constexpr (SRC == SRC_PUBLIC_COMPLEX) {
+                const float2 z = __ldg(reinterpret_cast<const float2*>(p.src) + idx);
+                val = power_of(z.x, z.y, p.half_power, p.power_mode);
+              } else {
+                val = ldg_stream_f1(p.src + idx);
+              }
             }
+            v[16 * j + i] = val;
           }
-          v[i] = val;
         }
       };
       int it = 0;
-      auto publish_next = [&](const float (&v)[16]) {
+      auto publish_next = [&](const float (&v)[16 * kMbGroup]) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
-        mbar_wait(&s_empty[s], ph ^ 1u);
+        mbar_wait(&s_empty[s], ph ^ 1u);          // MMAs of the stage's previous use have retired
         publish(s, v);
         ++it;
       };
-      float buf_a[16], buf_b[16];
-      int c0 = next_active(0);
-      if (c0 < n_chunks) load_chunk(c0, buf_a);
-      while (c0 < n_chunks) {
-        const int c1 = next_active(c0 + 1);
-        if (c1 < n_chunks) load_chunk(c1, buf_b);
+      float buf_a[16 * kMbGroup], buf_b[16 * kMbGroup];
+      int g0 = next_active(0);
+      if (g0 < n_groups) load_group(g0, buf_a);
+      while (g0 < n_groups) {
+        const int g1 = next_active(g0 + 1);
+        if (g1 < n_groups) load_group(g1, buf_b);
         publish_next(buf_a);
-        if (c1 >= n_chunks) break;
-        const int c2 = next_active(c1 + 1);
-        if (c2 < n_chunks) load_chunk(c2, buf_a);
+        if (g1 >= n_groups) break;
+        const int g2 = next_active(g1 + 1);
+        if (g2 < n_groups) load_group(g2, buf_a);
         publish_next(buf_b);
-        c0 = c2;
+        g0 = g2;
       }
     }
 
@@ -286,8 +301,8 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     tc_fence_after();
     if (tid == 0) MB_TRACE(3, 2);
     const bool ok = r < valid;
-    const int64_t g = g_first + r;
-    const int64_t seq = g / p.frames, t = g - seq * p.frames;
+    const int64_t gf = g_first + r;
+    const int64_t seq = gf / p.frames, t = gf - seq * p.frames;
     const int band0 = blockIdx.y * kMbBandBlock + 64 * kh;
     float* outp = p.out + (seq * p.n_bands + band0) * p.frames + t;
     const int n_here = min(64, p.n_bands - band0);           // bands this warp owns (<= 0: none)
@@ -319,26 +334,31 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     // =========================== MMA issuer =====================================================
     // the whole warp walks the loop (converged), one elected lane issues
     int it = 0;
-    for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
-      const int n = chunks[c].n;
+    for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
       const int s = it % n_stages;
       const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
-      mbar_wait(&s_full[s], ph);
+      if constexpr (SRC != SRC_TILES) mbar_wait(&s_full[s], ph);      // tiles: a_ready already implies full
       mbar_wait(&s_a_ready[s], ph);
       tc_fence_after();
       if (lane == 0) MB_TRACE(2, 2 * it);
-      const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
-      const uint64_t b_hi = umma_desc_sw128(st + a_slot), b_lo = umma_desc_sw128(st + a_slot + b_slot);
-      const uint32_t a_hi = tmem + kMbTmemA0 + 64u * (uint32_t)s, a_lo = a_hi + 32u;
-      const uint32_t idesc = umma_idesc_tf32(n);
-      const uint32_t d = tmem + (uint32_t)chunks[c].band_lo;
+      const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes) + a_slot;
       if (elect_one()) {
         if (!(p.debug & 2)) {
 #pragma unroll
-          for (int ks = 0; ks < kMbBK / 8; ++ks) {      // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
-            tc_mma_tf32_ts(d, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
-            tc_mma_tf32_ts(d, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
-            tc_mma_tf32_ts(d, a_hi + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+          for (int j = 0; j < kMbGroup; ++j) {
+            const int n = chunks[kMbGroup * g + j].n;
+            if (n == 0) continue;
+            const uint64_t b_hi = umma_desc_sw128(st + j * b_slot);
+            const uint64_t b_lo = umma_desc_sw128(st + j * b_slot + (uint32_t)n * 128u);
+            const uint32_t a_hi = tmem + kMbTmemA0 + 128u * (uint32_t)s + 64u * (uint32_t)j, a_lo = a_hi + 32u;
+            const uint32_t idesc = umma_idesc_tf32(n);
+            const uint32_t d = tmem + (uint32_t)chunks[kMbGroup * g + j].band_lo;
+#pragma unroll
+            for (int ks = 0; ks < kMbBK / 8; ++ks) {    // UMMA K = 8: 8 TMEM columns of A, 32 bytes of each B row
+              tc_mma_tf32_ts(d, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+              tc_mma_tf32_ts(d, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
+              tc_mma_tf32_ts(d, a_hi + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+            }
           }
         }
         tc_commit(&s_empty[s]);
@@ -351,27 +371,26 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   } else {
     // =========================== bulk-copy loader ===============================================
     int it = 0;
-    for (int c = next_active(0); c < n_chunks; c = next_active(c + 1), ++it) {
-      const int n = chunks[c].n;
+    for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
       const int s = it % n_stages;
       const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
       mbar_wait(&s_empty[s], ph ^ 1u);
       if (lane == 0) MB_TRACE(0, 2 * it);
       unsigned char* st = stage0 + (size_t)s * stage_bytes;
-      const uint32_t bytes = (uint32_t)n * 128u;
-      const unsigned char* b_src = p.plan + chunks[c].blob_off;
+      const int c0 = kMbGroup * g;
+      const int slices = min(kMbGroup, n_chunks - c0);
+      const uint32_t b0 = (uint32_t)chunks[c0].n * 256u, b1 = (uint32_t)chunks[c0 + 1].n * 256u;   // hi + lo images
       if (elect_one()) {
+        uint32_t a_bytes = 0;
+        if constexpr (SRC == SRC_TILES) a_bytes = (p.debug & 4) ? 16u : (uint32_t)slices * a_tile_bytes;
+        mbar_arrive_expect_tx(&s_full[s], a_bytes + b0 + b1);
         if constexpr (SRC == SRC_TILES) {
-          const uint32_t a_bytes = (p.debug & 4) ? 16u : a_tile_bytes;
-          mbar_arrive_expect_tx(&s_full[s], 2 * bytes + a_bytes);
           const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.src) +
-                                       ((size_t)blockIdx.x * n_chunks + c) * a_tile_bytes;
+                                       ((size_t)blockIdx.x * n_chunks + c0) * a_tile_bytes;
           bulk_g2s(st, a_src, a_bytes, &s_full[s]);
-        } else {
-          mbar_arrive_expect_tx(&s_full[s], 2 * bytes);
         }
-        bulk_g2s(st + a_slot, b_src, bytes, &s_full[s]);
-        bulk_g2s(st + a_slot + b_slot, b_src + bytes, bytes, &s_full[s]);
+        if (b0) bulk_g2s(st + a_slot, p.plan + chunks[c0].blob_off, b0, &s_full[s]);
+        if (b1) bulk_g2s(st + a_slot + b_slot, p.plan + chunks[c0 + 1].blob_off, b1, &s_full[s]);
       }
       __syncwarp();
       if (lane == 0) MB_TRACE(0, 2 * it + 1);

@@ -28,7 +28,7 @@ static int64_t slice_rows(int kpad) {
   }
   if (override_rows > 0) return override_rows;
   const int64_t wave = (int64_t)sm_count() * 16;
-  const int64_t budget = (int64_t)48 << 20;                  // bytes of power rows per slice
+  const int64_t budget = (int64_t)96 << 20;                  // bytes of power tiles per slice (L2 is 126 MB)
   int64_t waves = budget / (wave * kpad * 4);
   if (waves < 1) waves = 1;
   return waves * wave;

@@ -29,6 +29,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("TAC_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout: one JSON line only
 
 WORKLOADS = {
     # name: (batch, channels, samples, sample_rate, to_db)

@@ -180,9 +180,12 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     for (int j = 0; j < 4; ++j) tmem_zero16(t0 + 16 * j);
     tc_wait_st();
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  if (warp <= kMbProducerWarps) {
+    // producers + MMA warp only (named barrier 1): the loader warp is already streaming the first stages
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"((kMbProducerWarps + 1) * 32) : "memory");
+    tc_fence_after();
+  }
 
   // a group (stage) is active when at least one of its slices has a non-empty block
   auto group_active = [&](int g) { return (chunks[kMbGroup * g].n | chunks[kMbGroup * g + 1].n) != 0; };

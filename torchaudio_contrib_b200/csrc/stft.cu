@@ -68,7 +68,8 @@ __device__ __forceinline__ void emit_bin(const StftParams& p, int64_t seq, int64
 // ---------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 16;
 constexpr int kFastThreads = kFastWarps * 32;
-constexpr int kSlabComplex = 32 * 33;                        // transposition slab, row stride 33
+constexpr int kSlabStride = 34;                              // complex per slab row: 272 B keeps 16-byte alignment, conflict free
+constexpr int kSlabComplex = 32 * kSlabStride;               // transposition slab
 constexpr size_t kFastSmemBytes = 3 * 1024 * sizeof(float2)  // window pairs, tw1, tw2
                                   + kFastWarps * sizeof(uint64_t) + kFastWarps * kSlabComplex * sizeof(float2);
 
@@ -89,22 +90,26 @@ __device__ __forceinline__ float fast_power(float re, float im, float half_power
 template <int OUT_MODE, int PMODE>
 __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* s_win = reinterpret_cast<float2*>(smem_raw);      // [1024]   (w[2n], w[2n+1]) * 0.5 * scale
-  float2* s_tw1 = s_win + 1024;                             // [n1][k2] W_1024^(n1 k2)
-  float2* s_tw2 = s_tw1 + 1024;                             // [k1][l]  W_2048^(32 k1 + l)
+  // tables are stored pair-interleaved, [j / 2][lane][j % 2], so that one LDS.128 fetches the entries of two
+  // consecutive register indices of a lane (conflict free: consecutive lanes are 16 bytes apart)
+  float2* s_win = reinterpret_cast<float2*>(smem_raw);      // (w[2n], w[2n+1]) * 0.5 * scale, n = lane + 32 r -> [r/2][lane][r%2]
+  float2* s_tw1 = s_win + 1024;                             // W_1024^(n1 k2), k2 = lane                   -> [n1/2][lane][n1%2]
+  float2* s_tw2 = s_tw1 + 1024;                             // W_2048^(32 k1 + lane)                      -> [k1/2][lane][k1%2]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + 1024);
   float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < 1024; i += kFastThreads) {
+    const int j = i >> 5, l = i & 31;                       // register index, lane
+    const int slot = ((j >> 1) * 32 + l) * 2 + (j & 1);
     const float g = 0.5f * p.scale;
-    s_win[i] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
+    s_win[slot] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
     float sn, cs;
-    sincospif(-2.0f * (float)((i & 31) * (i >> 5)) / 1024.0f, &sn, &cs);
-    s_tw1[i] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)(j * l) / 1024.0f, &sn, &cs);
+    s_tw1[slot] = make_float2(cs, sn);
     sincospif(-2.0f * (float)i / 2048.0f, &sn, &cs);
-    s_tw2[i] = make_float2(cs, sn);
+    s_tw2[slot] = make_float2(cs, sn);
   }
   uint64_t* bar = s_bar + warp;
   if (lane == 0) {
@@ -157,10 +162,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     // ---- load: lane = n1, register r <-> z[n], n = n1 + 32 r, windowed ------------------------------
     float2 v[32];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const float2 xs = slab[lane + 32 * r];
-      const float2 w = s_win[lane + 32 * r];
-      v[r] = make_float2(xs.x * w.x, xs.y * w.y);
+    for (int r = 0; r < 32; r += 2) {
+      const float2 x0 = slab[lane + 32 * r], x1 = slab[lane + 32 * r + 32];
+      const float4 w = reinterpret_cast<const float4*>(s_win)[(r >> 1) * 32 + lane];
+      v[r] = make_float2(x0.x * w.x, x0.y * w.y);
+      v[r + 1] = make_float2(x1.x * w.z, x1.y * w.w);
     }
     __syncwarp();                                  // samples consumed; slab becomes the transpose buffer
 
@@ -171,13 +177,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       if (pass == 1) break;
       // transpose through the slab: row k2 gets this lane's k2-th output, then lane k2 reads its row
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) slab[k2 * 33 + lane] = v[bit_reverse<32>(k2)];
+      for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = v[bit_reverse<32>(k2)];
       __syncwarp();
 #pragma unroll
-      for (int n1 = 0; n1 < 32; ++n1) {
-        const float2 a = slab[lane * 33 + n1];
-        const float2 w = s_tw1[n1 * 32 + lane];    // W_1024^(n1 * k2), k2 = lane
+      for (int n1 = 0; n1 < 32; n1 += 2) {
+        const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
+        const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];   // W_1024^(n1 * k2), k2 = lane
         v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+        v[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
       }
       __syncwarp();                                // slab free again: prefetch the next frame
       const int64_t g_next = g + step;
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].y, partner);
       if (lane == 0) q = v[bit_reverse<32>((32 - k1) & 31)];
       const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
-      const float2 w = s_tw2[k1 * 32 + lane];      // (c, d), W = c + i d
+      const float2 w = s_tw2[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];      // (c, d), W = c + i d
       const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
       const float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
       if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {

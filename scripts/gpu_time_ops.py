@@ -1,0 +1,34 @@
+"""Event-timed throughput of the non-headline entry points (frames/s) on (64,1,160000)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torchaudio_contrib_b200 as tac
+
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+x = torch.randn(64, 1, 160000, device="cuda")
+with torch.no_grad():
+    for fft in (256, 512, 1024, 2048, 4096):
+        hop = fft // 4
+        frames = 64 * (1 + 160000 // hop)
+        st = tac.STFT(fft, hop).cuda()
+        sp = tac.Spectrogram(fft, hop, power=2.0).cuda()
+        mel = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=fft, hop_length=hop).cuda()
+        t1, t2, t3 = timeit(lambda: st(x)), timeit(lambda: sp(x)), timeit(lambda: mel(x))
+        print("fft %4d hop %4d frames %7d | stft %.3f ms %.2e f/s | spectrogram %.3f ms %.2e f/s | mel %.3f ms %.2e f/s"
+              % (fft, hop, frames, t1, frames / t1 * 1e3, t2, frames / t2 * 1e3, t3, frames / t3 * 1e3))
+    st = tac.STFT(2048, 512).cuda()
+    z = st(x)
+    cn = tac.ComplexNorm(2.0)
+    fb = tac.ApplyFilterbank(tac.MelFilterbank(1025, 128, sample_rate=16000).get_filterbank()).cuda()
+    p = cn(z)
+    print("complex_norm %.3f ms  apply_filterbank(public) %.3f ms  amplitude_to_db %.3f ms"
+          % (timeit(lambda: cn(z)), timeit(lambda: fb(p)), timeit(lambda: tac.amplitude_to_db(p))))
+    chain = torch.nn.Sequential(st, cn, fb)
+    print("unfused chain (plain nn.Sequential) %.3f ms" % timeit(lambda: chain(x)))

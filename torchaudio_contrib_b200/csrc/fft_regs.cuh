@@ -80,4 +80,65 @@ __device__ __forceinline__ void dif_fft(float2 (&v)[N]) {
   DifStage<N, 0, N>::run(v);
 }
 
+// ---------------------------------------------------------------------------------------------
+// FMA-form decimation-in-time variant (Linzer-Feig): same contract as dif_fft -- natural-order input in
+// v[0..N), X[k] left in v[bit_reverse<N>(k)] -- but every butterfly with a non-trivial twiddle costs six
+// FMAs instead of four add/sub plus a four-instruction complex multiply:
+//      w b = c (b_r + t b_i) + i c (b_i - t b_r),  t = s / c        (|c| >= |s|, else the cotangent form)
+//      X = u + c p,  Y = u - c p
+// 32 points: 388 fp32 instructions instead of 456.  The DIT network runs on the virtually bit-reversed
+// array A[i] = v[bit_reverse(i)] (a compile-time relabelling), which is what leaves X[k] in v[bit_reverse(k)].
+// ---------------------------------------------------------------------------------------------
+template <int J, int M>
+__device__ __forceinline__ void dit_butterfly(float2& u, float2& b) {
+  static_assert(M <= 64 && 64 % M == 0 && J >= 0 && 2 * J < M, "twiddle out of range");
+  float pr, pi, g;                                 // w b = g * (pr + i pi)
+  if constexpr (J == 0) {
+    const float ur = u.x, ui = u.y;
+    u = make_float2(ur + b.x, ui + b.y);
+    b = make_float2(ur - b.x, ui - b.y);
+    return;
+  } else if constexpr (4 * J == M) {               // w = -i
+    const float ur = u.x, ui = u.y, br = b.x, bi = b.y;
+    u = make_float2(ur + bi, ui - br);
+    b = make_float2(ur - bi, ui + br);
+    return;
+  } else {
+    constexpr double c = (double)cos64(J * (64 / M)), sn = (double)sin64(J * (64 / M));
+    if constexpr ((c >= 0 ? c : -c) >= (sn >= 0 ? sn : -sn)) {
+      constexpr float t = (float)(sn / c);
+      pr = fmaf(t, b.y, b.x);
+      pi = fmaf(-t, b.x, b.y);
+      g = (float)c;
+    } else {
+      constexpr float ct = (float)(c / sn);
+      pr = fmaf(ct, b.x, b.y);
+      pi = fmaf(ct, b.y, -b.x);
+      g = (float)sn;
+    }
+    const float ur = u.x, ui = u.y;
+    u = make_float2(fmaf(g, pr, ur), fmaf(g, pi, ui));
+    b = make_float2(fmaf(-g, pr, ur), fmaf(-g, pi, ui));
+  }
+}
+
+template <int N, int M, int K, int J>
+__device__ __forceinline__ void dit_stage_walk(float2 (&v)[N]) {
+  dit_butterfly<J, M>(v[bit_reverse<N>(K + J)], v[bit_reverse<N>(K + J + M / 2)]);
+  if constexpr (J + 1 < M / 2) dit_stage_walk<N, M, K, J + 1>(v);
+  else if constexpr (K + M < N) dit_stage_walk<N, M, K + M, 0>(v);
+}
+
+template <int N, int M>
+__device__ __forceinline__ void dit_stages(float2 (&v)[N]) {
+  dit_stage_walk<N, M, 0, 0>(v);
+  if constexpr (2 * M <= N) dit_stages<N, 2 * M>(v);
+}
+
+template <int N>
+__device__ __forceinline__ void dit_fft_fma(float2 (&v)[N]) {
+  static_assert(N >= 2 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two in [2, 64]");
+  dit_stages<N, 2>(v);
+}
+
 }  // namespace tac

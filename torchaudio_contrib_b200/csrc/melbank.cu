@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   }
   const FbPlanChunk* chunks = s_chunks;
 
+  // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the stage barriers simply keep counting
+  // across tiles, so the loader streams the next tile's first stages while this tile's epilogue stores drain
   const int tile_rows = p.rows_per_tile;
-  const int64_t row0 = (int64_t)blockIdx.x * tile_rows;
-  const int valid = (int)min((int64_t)tile_rows, p.rows - row0);
+  const int64_t n_tiles = (p.rows + tile_rows - 1) / tile_rows;
   const uint32_t a_tile_bytes = (uint32_t)tile_rows * 128u;
   // stage = {raw A tiles of the two slices (SRC_TILES only), B0 = [hi | lo], B1 = [hi | lo]}
   const uint32_t a_slot = (SRC == SRC_TILES) ? ((kMbGroup * a_tile_bytes + 1023u) & ~1023u) : 0u;
@@ -172,20 +173,14 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   const uint32_t tmem = s_tmem;
   if (tid == 0) MB_TRACE(3, 0);
 
-  // zero the accumulator: blocks of different K slices touch different column ranges, so every
-  // MMA accumulates (there is no single "first" MMA per column)
-  if (warp < kMbProducerWarps) {
-    const uint32_t t0 = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tmem_zero16(t0 + 16 * j);
-    tc_wait_st();
-  }
-  if (warp <= kMbProducerWarps) {
-    // producers + MMA warp only (named barrier 1): the loader warp is already streaming the first stages
+  // Per tile the accumulator is zeroed first (blocks of different K slices touch different column ranges, so
+  // every MMA accumulates -- there is no single "first" MMA per column); producers and the MMA warp meet on
+  // named barrier 1 for that, the loader warp never waits for it.
+  auto accumulator_ready = [&]() {
     tc_fence_before();
     asm volatile("bar.sync 1, %0;" ::"n"((kMbProducerWarps + 1) * 32) : "memory");
     tc_fence_after();
-  }
+  };
 
   // a group (stage) is active when at least one of its slices has a non-empty block
   auto group_active = [&](int g) { return (chunks[kMbGroup * g].n | chunks[kMbGroup * g + 1].n) != 0; };
@@ -201,8 +196,20 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     // (a warp can only touch the TMEM lane quarter warp % 4, which is why rows map to lanes this way).
     const int q = warp & 3, kh = warp >> 2;
     const int r = 32 * q + lane;
-    const int64_t g_first = p.g_base + row0;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    int it = 0;
+    uint32_t tile_parity = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tile_parity ^= 1u) {
+    const int64_t row0 = tile * tile_rows;
+    const int valid = (int)min((int64_t)tile_rows, p.rows - row0);
+    const int64_t g_first = p.g_base + row0;
+    {
+      const uint32_t t0 = t_lane + (uint32_t)(64 * kh);       // the region this warp read in its last epilogue
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_zero16(t0 + 16 * j);
+      tc_wait_st();
+    }
+    accumulator_ready();
 
     auto publish = [&](int s, const float (&v)[16 * kMbGroup]) {
 #pragma unroll
@@ -227,7 +234,6 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
       // the STFT kernel wrote the rows in the 128B-swizzled tile layout; the loader warp bulk-copies the two
       // (tile_rows x 32) blocks of this stage into shared memory; reading a row's 16-byte units through the
       // swizzle is bank-conflict free (8 consecutive rows hit 8 different 16-byte columns)
-      int it = 0;
       for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
@@ -276,7 +282,6 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
           }
         }
       };
-      int it = 0;
       auto publish_next = [&](const float (&v)[16 * kMbGroup]) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     }
 
     // =========================== epilogue =======================================================
-    mbar_wait(&s_accum, 0);
+    mbar_wait(&s_accum, tile_parity);
     tc_fence_after();
     if (tid == 0) MB_TRACE(3, 2);
     const bool ok = r < valid;
@@ -333,10 +338,13 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
         }
       }
     }
+    }   // tile loop
   } else if (warp == kMbProducerWarps) {
     // =========================== MMA issuer =====================================================
     // the whole warp walks the loop (converged), one elected lane issues
     int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    accumulator_ready();
     for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
       const int s = it % n_stages;
       const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
@@ -371,9 +379,11 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
     }
     if (elect_one()) tc_commit(&s_accum);
     __syncwarp();
+    }   // tile loop
   } else {
     // =========================== bulk-copy loader ===============================================
     int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int g = next_active(0); g < n_groups; g = next_active(g + 1), ++it) {
       const int s = it % n_stages;
       const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
@@ -385,12 +395,24 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
       const uint32_t b0 = (uint32_t)chunks[c0].n * 256u, b1 = (uint32_t)chunks[c0 + 1].n * 256u;   // hi + lo images
       if (elect_one()) {
         uint32_t a_bytes = 0;
-        if constexpr (SRC == SRC_TILES) a_bytes = (p.debug & 4) ? 16u : (uint32_t)slices * a_tile_bytes;
+        if constexpr (SRC == SRC_TILES) a_bytes = (p.debug & 4) ? 0u : (uint32_t)slices * a_tile_bytes;
         mbar_arrive_expect_tx(&s_full[s], a_bytes + b0 + b1);
         if constexpr (SRC == SRC_TILES) {
-          const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.src) +
-                                       ((size_t)blockIdx.x * n_chunks + c0) * a_tile_bytes;
-          bulk_g2s(st, a_src, a_bytes, &s_full[s]);
+          // rows [r_lo, r_lo + tile_rows) of the STFT kernel's 128-row power tiles: one contiguous piece per
+          // slice, two when the range straddles a 128-row tile (both 8-row aligned, so atoms stay whole)
+          const int64_t r_lo = tile * tile_rows;
+          const int64_t t0 = r_lo >> 7;
+          const uint32_t in0 = (uint32_t)(r_lo & 127);
+          const uint32_t n0 = min((uint32_t)tile_rows, 128u - in0);
+          const unsigned char* base = reinterpret_cast<const unsigned char*>(p.src);
+          for (int j = 0; j < slices && !(p.debug & 4); ++j) {
+            const unsigned char* src0 = base + (((size_t)t0 * n_chunks + (c0 + j)) * 128 + in0) * 128;
+            bulk_g2s(st + j * a_tile_bytes, src0, n0 * 128u, &s_full[s]);
+            if (n0 < (uint32_t)tile_rows) {
+              const unsigned char* src1 = base + (((size_t)(t0 + 1) * n_chunks + (c0 + j)) * 128) * 128;
+              bulk_g2s(st + j * a_tile_bytes + n0 * 128u, src1, ((uint32_t)tile_rows - n0) * 128u, &s_full[s]);
+            }
+          }
         }
         if (b0) bulk_g2s(st + a_slot, p.plan + chunks[c0].blob_off, b0, &s_full[s]);
         if (b1) bulk_g2s(st + a_slot + b_slot, p.plan + chunks[c0 + 1].blob_off, b1, &s_full[s]);
@@ -398,6 +420,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
       __syncwarp();
       if (lane == 0) MB_TRACE(0, 2 * it + 1);
     }
+    }   // tile loop
   }
 
   tc_fence_before();
@@ -424,7 +447,8 @@ template <int SRC>
 static int launch_melbank(MelbankParams p, int64_t tiles, cudaStream_t stream) {
   TAC_CUDA_OK(cudaFuncSetAttribute(melbank_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMbSmemBytes));
   const int bblocks = (p.n_bands + kMbBandBlock - 1) / kMbBandBlock;
-  dim3 grid((unsigned)tiles, (unsigned)bblocks);
+  const int64_t ctas = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM walks its tiles
+  dim3 grid((unsigned)ctas, (unsigned)bblocks);
   static int debug_flags = -1;
   if (debug_flags < 0) {
     const char* e = getenv("TAC_MB_DEBUG");
@@ -443,7 +467,7 @@ int launch_melbank_tiles(const float* tiles_ws, int64_t n_rows, int tile_rows, i
                          cudaStream_t stream) {
   if (n_rows <= 0) return TAC_OK;
   TAC_REQUIRE((reinterpret_cast<uintptr_t>(tiles_ws) & 127) == 0 && tile_rows >= 8 && tile_rows <= kMbRows && (tile_rows & 7) == 0,
-              TAC_ERR_INVALID, "melbank: power tiles must be 128-byte aligned, tile height a multiple of 8 in [8, 128]");
+              TAC_ERR_INVALID, "melbank: power tiles must be 128-byte aligned, row range a multiple of 8 in [8, 128]");
   TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melbank: plan must be 16-byte aligned");
   MelbankParams p;
   memset(&p, 0, sizeof(p));

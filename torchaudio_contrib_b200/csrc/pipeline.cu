@@ -41,7 +41,7 @@ static int run_melspec(StftParams sp, float power, const void* plan_dev, int n_b
   const int64_t row_bytes = (int64_t)sp.kpad * 4;
   int64_t rows = slice_rows(sp.kpad);
   if (rows > total) rows = total;
-  if ((rows + 128) * row_bytes > workspace_bytes) rows = workspace_bytes / row_bytes - 128;   // tiles are padded to full height
+  if (power_tile_bytes(rows, sp.kpad) > workspace_bytes) rows = (workspace_bytes / (row_bytes * 128) - 1) * 128;   // whole tiles + slack
   TAC_REQUIRE(rows >= 1 && workspace, TAC_ERR_WORKSPACE, "melspec: workspace of %lld bytes cannot hold one row of %lld bytes",
               (long long)workspace_bytes, (long long)row_bytes);
   sp.out = workspace;
@@ -51,11 +51,10 @@ static int run_melspec(StftParams sp, float power, const void* plan_dev, int n_b
   for (int64_t g0 = 0; g0 < total; g0 += rows) {
     sp.g0 = g0;
     sp.g1 = (g0 + rows < total) ? g0 + rows : total;
-    sp.tile_rows = balanced_tile_rows(sp.g1 - sp.g0);
     int rc = launch_stft(sp, stream);
     if (rc != TAC_OK) return rc;
-    rc = launch_melbank_tiles(workspace, sp.g1 - sp.g0, sp.tile_rows, g0, sp.frames, sp.bins, plan_dev, n_bands, to_db, ref,
-                              amin, out, stream);
+    rc = launch_melbank_tiles(workspace, sp.g1 - sp.g0, balanced_tile_rows(sp.g1 - sp.g0), g0, sp.frames, sp.bins, plan_dev,
+                              n_bands, to_db, ref, amin, out, stream);
     if (rc != TAC_OK) return rc;
   }
   return TAC_OK;
@@ -71,7 +70,7 @@ extern "C" int64_t tac_melspec_workspace_bytes(int64_t n_seq, int64_t n_samples,
   int64_t rows = slice_rows(kpad);
   if (rows > total) rows = total;
   if (rows < 1) rows = 1;
-  return (rows + 128) * kpad * 4;                            // + one tile of padding rows
+  return power_tile_bytes(rows, kpad);
 }
 
 extern "C" int tac_melspec_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,

@@ -55,7 +55,7 @@ __device__ __forceinline__ float spectral_power(float re, float im, float power,
 __device__ __forceinline__ void emit_bin(const StftParams& p, int64_t seq, int64_t t, int64_t row, int k,
                                          float re, float im) {
   if (p.out_mode == OUT_POWER_ROWS) {
-    p.out[power_tile_index(row, k, p.tile_rows, p.kpad)] = spectral_power(re, im, p.power, p.power_mode);
+    p.out[power_tile_index(row, k, p.kpad)] = spectral_power(re, im, p.power, p.power_mode);
   } else if (p.out_mode == OUT_POWER_PUBLIC) {
     p.out[(seq * p.bins + k) * p.frames + t] = spectral_power(re, im, p.power, p.power_mode);
   } else {
@@ -124,11 +124,23 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   const float half_power = 0.5f * p.power;
   uint32_t parity = 0;
 
+  // (sequence, frame-in-sequence) of this warp's frames advance incrementally: a 64-bit division per frame
+  // costs ~100 instructions in the hot loop (it did, twice per frame, in the first version)
+  const uint32_t frames_u = (uint32_t)p.frames;
+  const uint32_t step_seq = (uint32_t)(step / p.frames), step_t = (uint32_t)(step % p.frames);
+  auto advance = [&](uint32_t& seq, uint32_t& t) {
+    seq += step_seq;
+    t += step_t;
+    if (t >= frames_u) {
+      t -= frames_u;
+      ++seq;
+    }
+  };
+
   // a frame can use the bulk copy when it lies inside the sequence and everything is 16B aligned
-  auto stage_frame = [&](int64_t g) -> bool {    // returns true when a bulk copy is in flight
-    const int64_t seq = g / p.frames;
-    const int64_t start = (g - seq * p.frames) * p.hop - p.pad;
-    const float* row = p.x + seq * p.seq_stride;
+  auto stage_frame = [&](uint32_t seq, uint32_t t) -> bool {    // returns true when a bulk copy is in flight
+    const int64_t start = (int64_t)t * p.hop - p.pad;
+    const float* row = p.x + (int64_t)seq * p.seq_stride;
     const bool bulk = p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples;
     if (bulk) {
       if (elect_one()) {
@@ -147,8 +159,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   };
 
   int64_t g = p.g0 + (int64_t)blockIdx.x * kFastWarps + warp;
+  uint32_t seq = (uint32_t)(g / p.frames), t = (uint32_t)(g % p.frames);      // once per warp
   bool in_flight = false;
-  if (g < p.g1) in_flight = stage_frame(g);
+  if (g < p.g1) in_flight = stage_frame(seq, t);
 
 #pragma unroll 1
   for (; g < p.g1; g += step) {
@@ -170,41 +183,39 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     }
     __syncwarp();                                  // samples consumed; slab becomes the transpose buffer
 
-    // ---- two 32-point passes sharing one copy of the butterfly code ----------------------------------
-#pragma unroll 1
-    for (int pass = 0;; ++pass) {
-      dif_fft<32>(v);
-      if (pass == 1) break;
-      // transpose through the slab: row k2 gets this lane's k2-th output, then lane k2 reads its row
+    // ---- pass 1: 32-point FFT over r for fixed n1 = lane, transpose through the slab, twiddle ------------
+    dit_fft_fma<32>(v);
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = v[bit_reverse<32>(k2)];
-      __syncwarp();
+    for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = v[bit_reverse<32>(k2)];
+    __syncwarp();
 #pragma unroll
-      for (int n1 = 0; n1 < 32; n1 += 2) {
-        const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
-        const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];   // W_1024^(n1 * k2), k2 = lane
-        v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
-        v[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
-      }
-      __syncwarp();                                // slab free again: prefetch the next frame
-      const int64_t g_next = g + step;
-      in_flight = (g_next < p.g1) ? stage_frame(g_next) : false;
+    for (int n1 = 0; n1 < 32; n1 += 2) {
+      const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
+      const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];   // W_1024^(n1 * k2), k2 = lane
+      v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+      v[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
     }
+    __syncwarp();                                  // slab free again: prefetch the next frame
+    {
+      uint32_t seq_next = seq, t_next = t;
+      advance(seq_next, t_next);
+      in_flight = (g + step < p.g1) ? stage_frame(seq_next, t_next) : false;
+    }
+    // ---- pass 2: 32-point FFT over n1 for fixed k2 = lane ---------------------------------------------
+    dit_fft_fma<32>(v);
     // now v[bit_reverse(k1)] = Z[32 k1 + lane] / 2
 
     // ---- real-FFT untangling: bin k = 32 k1 + lane pairs with 1024 - k ------------------------------
-    const int64_t seq = g / p.frames, t = g - seq * p.frames;
+    // destination of bin `lane` of this frame; bins 32 k1 + lane follow at a fixed stride
     float* dst;
-    int64_t dst_stride;                            // floats between consecutive k1 (bins 32 apart)
+    int64_t dst_stride = 0;                        // floats between consecutive k1 (public layouts only)
     if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-      const int64_t row = g - p.g0;               // power tiles: one 128-byte swizzled row segment per slice
-      dst = p.out + power_tile_index(row, lane, p.tile_rows, p.kpad);
-      dst_stride = 32 * p.tile_rows;
+      dst = p.out + power_tile_index(g - p.g0, lane, p.kpad);      // + k1 * 4096 floats: immediate offsets below
     } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
-      dst = p.out + (seq * p.bins + lane) * p.frames + t;
+      dst = p.out + ((int64_t)seq * p.bins + lane) * p.frames + t;
       dst_stride = 32 * p.frames;
     } else {
-      dst = p.out + 2 * ((seq * p.bins + lane) * p.frames + t);
+      dst = p.out + 2 * (((int64_t)seq * p.bins + lane) * p.frames + t);
       dst_stride = 64 * p.frames;
     }
     const int partner = (32 - lane) & 31;
@@ -219,25 +230,29 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       const float2 w = s_tw2[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];      // (c, d), W = c + i d
       const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
       const float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
-      if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
+      if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+        dst[k1 * 4096] = fast_power<PMODE>(xr, xi, half_power);
+      } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
         *reinterpret_cast<float2*>(dst) = make_float2(xr, xi);
+        dst += dst_stride;
       } else {
         *dst = fast_power<PMODE>(xr, xi, half_power);
+        dst += dst_stride;
       }
-      dst += dst_stride;
     }
     // Nyquist bin (and zero fill of the row padding in frame-major mode); dst now points at bin 1024 + lane
     {
       const float2 z0 = v[0];
       const float nyq = 2.0f * (z0.x - z0.y);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-        if (1024 + lane < p.kpad) *dst = (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f;
+        dst[32 * 4096] = (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f;   // slice 32: Nyquist + zero fill
       } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
         if (lane == 0) *dst = fast_power<PMODE>(nyq, 0.0f, half_power);
       } else {
         if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(nyq, 0.0f);
       }
     }
+    advance(seq, t);
   }
 }
 
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
       if (!p.onesided && k > 0 && k < C) emit_bin(p, seq, t, out_row, n_fft - k, xr, -xi);
     }
     if (p.out_mode == OUT_POWER_ROWS)
-      for (int k = C + 1 + tid; k < p.kpad; k += kGenThreads) p.out[power_tile_index(out_row, k, p.tile_rows, p.kpad)] = 0.0f;
+      for (int k = C + 1 + tid; k < p.kpad; k += kGenThreads) p.out[power_tile_index(out_row, k, p.kpad)] = 0.0f;
     __syncthreads();
   }
 }
@@ -383,11 +398,12 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.onesided = onesided ? 1 : 0;
   p.bins = onesided ? n_fft / 2 + 1 : n_fft;
   p.frames = tac_stft_num_frames(n_samples, n_fft, hop, center);
+  TAC_REQUIRE(n_seq * p.frames < ((int64_t)1 << 31) && p.frames < ((int64_t)1 << 31), TAC_ERR_UNSUPPORTED,
+              "stft: %lld frames in one call exceed the 2^31 the kernels index; split the batch", (long long)(n_seq * p.frames));
   p.scale = normalized ? (float)(1.0 / sqrt((double)n_fft)) : 1.0f;
   p.g0 = 0;
   p.g1 = n_seq * p.frames;
   p.kpad = kpad_for_bins(p.bins);
-  p.tile_rows = 128;
   p.bulk_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (seq_stride & 3) == 0 && (hop & 3) == 0 && (pad & 3) == 0) ? 1 : 0;
   p.power = 1.0f;
   p.power_mode = 1;

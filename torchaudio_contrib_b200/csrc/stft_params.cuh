@@ -21,7 +21,6 @@ struct StftParams {
   int64_t g0, g1;          // flattened frame range [g0, g1) handled by this launch (g = seq * frames + t)
   int n_fft, hop, pad, pad_mode;
   int onesided, bins, kpad;
-  int tile_rows;           // OUT_POWER_ROWS: frames per tile (multiple of 8, <= 128)
   int bulk_ok;             // interior frames may use the 1-D bulk copy (16 B alignment holds)
   int out_mode;
   int power_mode;          // 2: |X|^2, 1: |X|, 0: |X|^power
@@ -29,16 +28,22 @@ struct StftParams {
   float scale;             // n_fft^-0.5 when normalized, else 1
 };
 
-// Power tiles (OUT_POWER_ROWS): frames are grouped in tiles of `tile_rows`; for each tile and each
-// 32-bin slice the (tile_rows x 32) block is stored contiguously in the 128B-swizzled K-major layout
-// the tcgen05 A operand wants, so the filterbank kernel fetches it with one bulk copy:
-//   float index = ((row / tile_rows) * (kpad / 32) + bin / 32) * tile_rows * 32
-//                 + (ri / 8) * 256 + (ri % 8) * 32 + (((kk / 4) ^ (ri % 8)) * 4) + kk % 4,   ri = row % tile_rows, kk = bin % 32
-__host__ __device__ inline int64_t power_tile_index(int64_t row, int bin, int tile_rows, int kpad) {
-  const int64_t tile = row / tile_rows;
-  const int ri = (int)(row - tile * tile_rows), kk = bin & 31;
-  return (tile * (kpad >> 5) + (bin >> 5)) * (int64_t)tile_rows * 32 + (ri >> 3) * 256 + (ri & 7) * 32 +
-         ((((kk >> 2) ^ (ri & 7)) << 2) | (kk & 3));
+// Power tiles (OUT_POWER_ROWS): frames are grouped in tiles of 128; for each tile and each 32-bin slice the
+// (128 x 32) fp32 block is stored contiguously (16 KB) in the 128B-swizzled K-major layout the tcgen05 A
+// operand wants (8-row x 128-byte atoms, 16-byte columns XOR-ed with the row index), so the filterbank kernel
+// fetches any 8-row-aligned range of a block with one bulk copy, and the STFT kernel addresses the 33 slices of
+// a frame as base + slice * 16 KB (an immediate offset: no address arithmetic in its store loop):
+//   float index = ((row / 128) * (kpad / 32) + bin / 32) * 4096 + (ri / 8) * 256 + (ri % 8) * 32
+//                 + (((kk / 4) ^ (ri % 8)) * 4) + kk % 4,        ri = row % 128, kk = bin % 32
+constexpr int kPowerTileRows = 128;
+__host__ __device__ inline int64_t power_tile_index(int64_t row, int bin, int kpad) {
+  const int64_t tile = row >> 7;
+  const int ri = (int)(row & 127), kk = bin & 31;
+  return (tile * (kpad >> 5) + (bin >> 5)) * 4096 + (ri >> 3) * 256 + (ri & 7) * 32 + ((((kk >> 2) ^ (ri & 7)) << 2) | (kk & 3));
+}
+// bytes of workspace for `rows` frames (whole tiles, plus one tile of slack for 8-row-aligned over-reads)
+__host__ __device__ inline int64_t power_tile_bytes(int64_t rows, int kpad) {
+  return ((rows + kPowerTileRows - 1) / kPowerTileRows + 1) * (int64_t)kPowerTileRows * kpad * 4;
 }
 
 int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,

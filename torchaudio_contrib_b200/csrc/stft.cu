@@ -27,24 +27,6 @@ namespace tac {
 // ---------------------------------------------------------------------------------------------
 // shared pieces
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int64_t s, int64_t n, int pad_mode) {
-  if (s >= 0 && s < n) return __ldg(row + s);
-  switch (pad_mode) {
-    case TAC_PAD_REFLECT:
-      s = (s < 0) ? -s : 2 * (n - 1) - s;
-      break;
-    case TAC_PAD_REPLICATE:
-      s = (s < 0) ? 0 : n - 1;
-      break;
-    case TAC_PAD_CIRCULAR:
-      s = (s < 0) ? s + n : s - n;
-      break;
-    default:
-      return 0.0f;
-  }
-  return (s >= 0 && s < n) ? __ldg(row + s) : 0.0f;
-}
-
 __device__ __forceinline__ float spectral_power(float re, float im, float power, int mode) {
   const float s = fmaf(re, re, im * im);
   if (mode == 2) return s;
@@ -338,6 +320,7 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
 int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
+  if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024)) return launch_stft_warp(p, stream);
   if (p.n_fft == 2048 && p.onesided) {
     const int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());

@@ -1,0 +1,245 @@
+// K1b: the warp-level register FFT of stft.cu generalised to n_fft = 256 / 512 / 1024.
+//
+// A frame of n_fft real samples is a complex FFT of C = n_fft / 2 points; C = R1 x R2 with both factors at most
+// 32, so a warp handles F = 1024 / C frames at once and every lane still owns exactly 32 complex values:
+//
+//     n_fft   C    R1 x R2   F (frames per warp batch)   pass-1 FFTs per lane   pass-2 FFTs per lane
+//     1024   512   16 x 32   2                           2 x 16-point           1 x 32-point
+//      512   256   16 x 16   4                           2 x 16-point           2 x 16-point
+//      256   128    8 x 16   8                           4 x  8-point           2 x 16-point
+//
+// Per frame: n = n1 + R2 n2, pass 1 transforms over n2 (R1 points) for each n1, the result goes through the
+// warp's shared-memory slab laid out by pass-2 work item (frame, k2) with an odd row stride (conflict free),
+// pass 2 applies W_C^(n1 k2) and transforms over n1 (R2 points): Z[R1 k1 + k2].  The real-FFT untangling
+// pairs (k1, k2) with (R2-1-k1, R1-k2) inside the frame's group of R1 lanes by one shuffle.
+// Frames are staged like in stft2048_kernel: one bulk async copy per interior frame into the slab, a gather
+// for frames touching the padding.  n_fft = 2048 keeps its own kernel (stft.cu); 4096+ and the option
+// surface that these do not cover (two-sided output) use stft_generic_kernel.
+#include "fft_regs.cuh"
+#include "stft_params.cuh"
+#include "tac_common.cuh"
+
+namespace tac {
+
+constexpr int kMwWarps = 16;
+constexpr int kMwThreads = kMwWarps * 32;
+constexpr int kMwSlabFloats = 2 * 64 * 17 + 32;          // >= 2048 samples and >= rows x stride complex for every size
+
+template <int LOG2N>
+struct WarpFftShape {
+  static constexpr int N = 1 << LOG2N, C = N / 2;
+  static constexpr int R1 = (LOG2N == 10) ? 16 : (LOG2N == 9 ? 16 : 8);
+  static constexpr int R2 = C / R1;
+  static constexpr int F = 1024 / C;
+  static constexpr int A1 = F * R2 / 32, A2 = F * R1 / 32;
+  static constexpr int S = R2 + 1;                       // slab row stride (complex), odd
+  static_assert(A1 * R1 == 32 && A2 * R2 == 32 && F * R1 * S * 2 <= kMwSlabFloats && F * N <= kMwSlabFloats, "shape");
+};
+
+template <int PMODE>
+__device__ __forceinline__ float mw_power(float re, float im, float half_power) {
+  const float s = fmaf(re, re, im * im);
+  if constexpr (PMODE == 2) return s;
+  if constexpr (PMODE == 1) return sqrtf(s);
+  return s > 0.0f ? exp2f(half_power * __log2f(s)) : (half_power == 0.0f ? 1.0f : 0.0f);
+}
+
+template <int LOG2N, int OUT_MODE, int PMODE>
+__global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftParams p) {
+  using Sh = WarpFftShape<LOG2N>;
+  constexpr int N = Sh::N, C = Sh::C, R1 = Sh::R1, R2 = Sh::R2, F = Sh::F, A1 = Sh::A1, A2 = Sh::A2, S = Sh::S;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_win = reinterpret_cast<float2*>(smem_raw);        // [C]        (w[2n], w[2n+1]) * 0.5 * scale
+  float2* s_tw1 = s_win + C;                                  // [R2][R1]   W_C^(n1 k2)
+  float2* s_tw2 = s_tw1 + C;                                  // [R2][R1]   W_N^(R1 k1 + k2)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + C);
+  float* s_slab = reinterpret_cast<float*>(s_bar + kMwWarps);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C; i += kMwThreads) {
+    const float g = 0.5f * p.scale;
+    s_win[i] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
+    const int a = i / R1, b = i % R1;                         // (n1, k2) resp. (k1, k2)
+    float sn, cs;
+    sincospif(-2.0f * (float)(a * b) / (float)C, &sn, &cs);
+    s_tw1[i] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)(R1 * a + b) / (float)N, &sn, &cs);
+    s_tw2[i] = make_float2(cs, sn);
+  }
+  uint64_t* bar = s_bar + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  float* slab_f = s_slab + warp * kMwSlabFloats;
+  float2* slab = reinterpret_cast<float2*>(slab_f);
+  const float half_power = 0.5f * p.power;
+  const uint32_t frames_u = (uint32_t)p.frames;
+  const int64_t n_batches = (p.g1 - p.g0 + F - 1) / F;
+  uint32_t parity = 0;
+
+  for (int64_t batch = (int64_t)blockIdx.x * kMwWarps + warp; batch < n_batches; batch += (int64_t)gridDim.x * kMwWarps) {
+    const uint32_t gb = (uint32_t)(p.g0 + batch * F);         // first frame of the batch (flattened index)
+    // ---- stage the F frames: bulk copy where possible, gather otherwise ---------------------------------
+    __syncwarp();                                             // previous batch is done with the slab
+    uint32_t bulk_bytes = 0;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const uint32_t g = gb + f;
+      const uint32_t seq = g / frames_u, t = g - seq * frames_u;
+      const int64_t start = (int64_t)t * p.hop - p.pad;
+      const bool live = (int64_t)g < p.g1;
+      const bool bulk = live && p.bulk_ok && start >= 0 && start + N <= p.n_samples;
+      if (bulk) bulk_bytes += N * 4;
+    }
+    if (elect_one()) {
+      fence_proxy_async();
+      if (bulk_bytes) mbar_arrive_expect_tx(bar, bulk_bytes);
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const uint32_t g = gb + f;
+      const uint32_t seq = g / frames_u, t = g - seq * frames_u;
+      const int64_t start = (int64_t)t * p.hop - p.pad;
+      const bool live = (int64_t)g < p.g1;
+      const float* row = p.x + (int64_t)seq * p.seq_stride;
+      const bool bulk = live && p.bulk_ok && start >= 0 && start + N <= p.n_samples;
+      if (bulk) {
+        if (elect_one()) bulk_g2s(slab_f + f * N, row + start, N * 4, bar);
+      } else {
+        for (int j = lane; j < N; j += 32)
+          slab_f[f * N + j] = live ? fetch_padded(row, start + j, p.n_samples, p.pad_mode) : 0.0f;
+      }
+    }
+    if (bulk_bytes) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    }
+    __syncwarp();
+
+    // ---- pass 1: item i1 = a * 32 + lane = (frame f1, n1); R1-point FFT over n2 -------------------------
+    float2 v[32];
+#pragma unroll
+    for (int a = 0; a < A1; ++a) {
+      const int i1 = a * 32 + lane, f1 = i1 / R2, n1 = i1 % R2;
+#pragma unroll
+      for (int n2 = 0; n2 < R1; ++n2) {
+        const float2 xs = slab[f1 * C + n1 + R2 * n2];
+        const float2 w = s_win[n1 + R2 * n2];
+        v[a * R1 + n2] = make_float2(xs.x * w.x, xs.y * w.y);
+      }
+    }
+    __syncwarp();                                             // samples consumed: the slab becomes the transpose buffer
+#pragma unroll
+    for (int a = 0; a < A1; ++a) {
+      float2 w[R1];
+#pragma unroll
+      for (int i = 0; i < R1; ++i) w[i] = v[a * R1 + i];
+      dit_fft_fma<R1>(w);
+      const int i1 = a * 32 + lane, f1 = i1 / R2, n1 = i1 % R2;
+#pragma unroll
+      for (int k2 = 0; k2 < R1; ++k2) slab[(f1 * R1 + k2) * S + n1] = w[bit_reverse<R1>(k2)];
+    }
+    __syncwarp();
+
+    // ---- pass 2: item i2 = b * 32 + lane = (frame f2, k2); twiddle, R2-point FFT over n1, untangle -------
+    const int kk2 = lane % R1;                                // k2 of this lane's items (R1 divides 32)
+    const int partner = (lane & ~(R1 - 1)) | ((R1 - kk2) & (R1 - 1));
+#pragma unroll
+    for (int b = 0; b < A2; ++b) {
+      const int i2 = b * 32 + lane, f2 = i2 / R1;
+      float2 u[R2];
+#pragma unroll
+      for (int n1 = 0; n1 < R2; ++n1) {
+        const float2 a = slab[i2 * S + n1];
+        const float2 w = s_tw1[n1 * R1 + kk2];
+        u[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+      }
+      dit_fft_fma<R2>(u);                                     // u[bit_reverse(k1)] = Z[R1 k1 + k2] / 2
+
+      const uint32_t g = gb + f2;
+      const bool live = (int64_t)g < p.g1;
+      const uint32_t seq = g / frames_u, t = g - seq * frames_u;
+      const int64_t row = (int64_t)g - p.g0;
+      auto emit = [&](int k, float re, float im) {
+        if (!live) return;
+        if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+          p.out[power_tile_index(row, k, p.kpad)] = mw_power<PMODE>(re, im, half_power);
+        } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
+          p.out[((int64_t)seq * p.bins + k) * p.frames + t] = mw_power<PMODE>(re, im, half_power);
+        } else {
+          reinterpret_cast<float2*>(p.out)[((int64_t)seq * p.bins + k) * p.frames + t] = make_float2(re, im);
+        }
+      };
+#pragma unroll
+      for (int k1 = 0; k1 < R2; ++k1) {
+        const float2 z = u[bit_reverse<R2>(k1)];
+        float2 q;
+        q.x = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].x, partner);
+        q.y = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].y, partner);
+        if (kk2 == 0) q = u[bit_reverse<R2>((R2 - k1) % R2)];
+        const float a = z.x + q.x, bb = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+        const float2 w = s_tw2[k1 * R1 + kk2];
+        emit(R1 * k1 + kk2, fmaf(w.x, gs, fmaf(-w.y, h, a)), fmaf(w.x, h, fmaf(w.y, gs, bb)));
+      }
+      // Nyquist bin C (owned by the k2 = 0 lane) and, for power tiles, the zero fill of its 32-bin slice
+      const float2 z0 = u[0];
+      const float nyq = 2.0f * (z0.x - z0.y);
+      if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32 / R1; ++j) {
+            const int kq = kk2 + R1 * j;
+            p.out[power_tile_index(row, C + kq, p.kpad)] = (kq == 0) ? mw_power<PMODE>(nyq, 0.0f, half_power) : 0.0f;
+          }
+        }
+      } else {
+        if (kk2 == 0) emit(C, nyq, 0.0f);
+      }
+    }
+  }
+}
+
+template <int LOG2N>
+static size_t warp_kernel_smem() {
+  return 3 * (size_t)WarpFftShape<LOG2N>::C * sizeof(float2) + kMwWarps * sizeof(uint64_t) + (size_t)kMwWarps * kMwSlabFloats * sizeof(float);
+}
+
+template <int LOG2N>
+static int launch_warp_kernel(const StftParams& p, cudaStream_t stream) {
+  using Kernel = void (*)(const StftParams);
+  Kernel k = nullptr;
+  if (p.out_mode == OUT_COMPLEX_PUBLIC) k = stft_warp_kernel<LOG2N, OUT_COMPLEX_PUBLIC, 1>;
+  else if (p.out_mode == OUT_POWER_PUBLIC)
+    k = p.power_mode == 2 ? stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 2>
+                          : (p.power_mode == 1 ? stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 1> : stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 0>);
+  else
+    k = p.power_mode == 2 ? stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 2>
+                          : (p.power_mode == 1 ? stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 1> : stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 0>);
+  const size_t smem = warp_kernel_smem<LOG2N>();
+  TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t batches = (p.g1 - p.g0 + WarpFftShape<LOG2N>::F - 1) / WarpFftShape<LOG2N>::F;
+  const int64_t want = (batches + kMwWarps - 1) / kMwWarps;
+  const int grid = (int)(want < sm_count() ? want : sm_count());
+  LaunchProbe probe(KIND_STFT, stream);
+  k<<<grid, kMwThreads, smem, stream>>>(p);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+// n_fft = 256 / 512 / 1024, one-sided output: returns TAC_ERR_UNSUPPORTED for anything else (caller falls
+// through to the generic kernel)
+int launch_stft_warp(const StftParams& p, cudaStream_t stream) {
+  if (!p.onesided) return TAC_ERR_UNSUPPORTED;
+  switch (p.n_fft) {
+    case 256: return launch_warp_kernel<8>(p, stream);
+    case 512: return launch_warp_kernel<9>(p, stream);
+    case 1024: return launch_warp_kernel<10>(p, stream);
+    default: return TAC_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tac

@@ -46,6 +46,21 @@ __host__ __device__ inline int64_t power_tile_bytes(int64_t rows, int kpad) {
   return ((rows + kPowerTileRows - 1) / kPowerTileRows + 1) * (int64_t)kPowerTileRows * kpad * 4;
 }
 
+#ifdef __CUDACC__
+// x[s] under torch.stft's centre padding (torch.nn.functional.pad modes), 0 <= pad < n guaranteed by the host
+__device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int64_t s, int64_t n, int pad_mode) {
+  if (s >= 0 && s < n) return __ldg(row + s);
+  switch (pad_mode) {
+    case 0: s = (s < 0) ? -s : 2 * (n - 1) - s; break;          // TAC_PAD_REFLECT
+    case 2: s = (s < 0) ? 0 : n - 1; break;                     // TAC_PAD_REPLICATE
+    case 3: s = (s < 0) ? s + n : s - n; break;                 // TAC_PAD_CIRCULAR
+    default: return 0.0f;                                       // TAC_PAD_CONSTANT
+  }
+  return (s >= 0 && s < n) ? __ldg(row + s) : 0.0f;
+}
+#endif
+
+int launch_stft_warp(const StftParams& p, cudaStream_t stream);   // stft_multi.cu: n_fft = 256 / 512 / 1024
 int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                      const float* window, int n_fft, int hop, int center, int pad_mode, int normalized, int onesided);
 int launch_stft(const StftParams& p, cudaStream_t stream);

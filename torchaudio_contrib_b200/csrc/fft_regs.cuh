@@ -23,6 +23,19 @@ __host__ __device__ constexpr float quarter_cos64(int q) {
 __host__ __device__ constexpr float cos64(int q) { return q <= 16 ? quarter_cos64(q) : -quarter_cos64(32 - q); }
 __host__ __device__ constexpr float sin64(int q) { return q <= 16 ? quarter_cos64(16 - q) : quarter_cos64(q - 16); }
 
+// compile-time loop: f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, N-1>{})
+template <int I>
+struct IntC {
+  static constexpr int value = I;
+};
+template <int N, int I = 0, class Fn>
+__device__ __forceinline__ void static_for(Fn&& f) {
+  if constexpr (I < N) {
+    f(IntC<I>{});
+    static_for<N, I + 1>(f);
+  }
+}
+
 template <int N>
 __host__ __device__ constexpr int bit_reverse(int k) {
   int r = 0;

@@ -16,6 +16,8 @@
 //
 // The tables are produced by the host side of the package from the reference formula
 // (torchaudio_contrib_b200/_mulaw_tables.py) and passed in as device pointers.
+#include <stdlib.h>
+
 #include "tac_common.cuh"
 
 namespace tac {
@@ -27,7 +29,7 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(kMuLawThreads)
 mulaw_encode_kernel(const float* __restrict__ x, int64_t n, long long* __restrict__ out,
                     const float* __restrict__ thr, int n_thr, int idx_min, float x_limit,
-                    float mu, float half_mu_over_log2) {
+                    float mu, float half_mu_over_log2, int variant) {
   extern __shared__ float s_thr[];
   const float* table = thr;
   if (kSmemTable) {
@@ -63,8 +65,13 @@ mulaw_encode_kernel(const float* __restrict__ x, int64_t n, long long* __restric
       hi.x = encode_one(v.z);
       hi.y = encode_one(v.w);
       longlong2* o = reinterpret_cast<longlong2*>(out) + 2 * i;
-      __stcs(o, lo);
-      __stcs(o + 1, hi);
+      if (variant & 1) {
+        o[0] = lo;
+        o[1] = hi;
+      } else {
+        __stcs(o, lo);
+        __stcs(o + 1, hi);
+      }
     }
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
       out[i] = encode_one(x[i]);
@@ -129,9 +136,9 @@ mulaw_decode_kernel(const CodeT* __restrict__ codes, int64_t n, float* __restric
   }
 }
 
-static int streaming_grid(int64_t n_vec) {
+static int streaming_grid(int64_t n_vec, int ctas_per_sm = 8) {
   const int64_t want = (n_vec + kMuLawThreads - 1) / kMuLawThreads;
-  const int64_t cap = (int64_t)sm_count() * 8;          // 8 x 256 threads resident per SM
+  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -145,15 +152,21 @@ extern "C" int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantiz
   TAC_REQUIRE(x && out && thresholds_dev && n_thresholds >= 1, TAC_ERR_INVALID, "mulaw_encode: null pointer / empty table");
   const float mu = (float)(n_quantize - 1);
   const float half_mu_over_log2 = (float)(0.5 * (double)mu / log2(1.0 + (double)mu));
-  const int grid = streaming_grid((n + 3) / 4);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("TAC_MULAW_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  int grid = streaming_grid((n + 3) / 4);
+  if (variant >> 4) grid = (grid > sm_count() * (variant >> 4)) ? sm_count() * (variant >> 4) : grid;
   LaunchProbe probe(KIND_MULAW, as_stream(stream));
   if (n_thresholds <= kMuLawSmemTableMax) {
     const size_t smem = (size_t)n_thresholds * sizeof(float);
     mulaw_encode_kernel<true><<<grid, kMuLawThreads, smem, as_stream(stream)>>>(
-        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2, variant);
   } else {
     mulaw_encode_kernel<false><<<grid, kMuLawThreads, 0, as_stream(stream)>>>(
-        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2, variant);
   }
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;

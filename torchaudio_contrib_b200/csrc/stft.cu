@@ -51,7 +51,7 @@ __device__ __forceinline__ void emit_bin(const StftParams& p, int64_t seq, int64
 constexpr int kFastWarps = 16;
 constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kSlabStride = 34;                              // complex per slab row: 272 B keeps 16-byte alignment, conflict free
-constexpr int kSlabComplex = 32 * kSlabStride;               // transposition slab
+constexpr int kSlabComplex = 32 * kSlabStride + 2;           // transposition slab (+2: 16 slabs hold a 1025 x 17 float2 output tile)
 constexpr size_t kFastSmemBytes = 3 * 1024 * sizeof(float2)  // window pairs, tw1, tw2
                                   + kFastWarps * sizeof(uint64_t) + kFastWarps * kSlabComplex * sizeof(float2);
 
@@ -63,6 +63,61 @@ __device__ __forceinline__ float fast_power(float re, float im, float half_power
   if constexpr (PMODE == 2) return s;
   if constexpr (PMODE == 1) return sqrtf(s);
   return s > 0.0f ? exp2f(half_power * __log2f(s)) : (half_power == 0.0f ? 1.0f : 0.0f);
+}
+
+// Front half of a frame's FFT, shared by both n_fft = 2048 kernels.  In: the 2048 samples in `slab`.
+// Out: v[n1] = pass-2 input of lane k2 = lane (pass-1 result transposed through the slab and multiplied by
+// W_1024^(n1 k2)); the slab is free again on return.
+__device__ __forceinline__ void fft2048_front(float2 (&v)[32], float2* slab, const float2* s_win, const float2* s_tw1, int lane) {
+#pragma unroll
+  for (int r = 0; r < 32; r += 2) {                // lane = n1, register r <-> z[n], n = n1 + 32 r, windowed
+    const float2 x0 = slab[lane + 32 * r], x1 = slab[lane + 32 * r + 32];
+    const float4 w = reinterpret_cast<const float4*>(s_win)[(r >> 1) * 32 + lane];
+    v[r] = make_float2(x0.x * w.x, x0.y * w.y);
+    v[r + 1] = make_float2(x1.x * w.z, x1.y * w.w);
+  }
+  __syncwarp();                                    // samples consumed; slab becomes the transpose buffer
+  dit_fft_fma<32>(v);                              // pass 1: over r for fixed n1 = lane
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = v[bit_reverse<32>(k2)];
+  __syncwarp();
+#pragma unroll
+  for (int n1 = 0; n1 < 32; n1 += 2) {
+    const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
+    const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];   // W_1024^(n1 * k2), k2 = lane
+    v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+    v[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
+  }
+  __syncwarp();
+}
+
+// Real-FFT untangling of bin k = 32 K1 + lane from v[bit_reverse(k1)] = Z[32 k1 + lane] / 2: pairs with bin
+// 1024 - k, held by lane (32 - lane) % 32 in register 31 - K1 (lane 0 pairs with itself, register (32 - K1) % 32).
+template <int K1>
+__device__ __forceinline__ float2 fft2048_untangle(const float2 (&v)[32], const float2* s_tw2, int lane, int partner) {
+  const float2 z = v[bit_reverse<32>(K1)];
+  float2 q;
+  q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - K1)].x, partner);
+  q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - K1)].y, partner);
+  if (lane == 0) q = v[bit_reverse<32>((32 - K1) & 31)];
+  const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+  const float2 w = s_tw2[((K1 >> 1) * 32 + lane) * 2 + (K1 & 1)];        // (c, d), W = c + i d
+  return make_float2(fmaf(w.x, gs, fmaf(-w.y, h, a)), fmaf(w.x, h, fmaf(w.y, gs, b)));
+}
+
+// table set-up shared by both kernels: pair-interleaved [j / 2][lane][j % 2] so one LDS.128 serves two registers
+__device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_win, float2* s_tw1, float2* s_tw2, int tid, int nthreads) {
+  for (int i = tid; i < 1024; i += nthreads) {
+    const int j = i >> 5, l = i & 31;                       // register index, lane
+    const int slot = ((j >> 1) * 32 + l) * 2 + (j & 1);
+    const float g = 0.5f * p.scale;
+    s_win[slot] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
+    float sn, cs;
+    sincospif(-2.0f * (float)(j * l) / 1024.0f, &sn, &cs);
+    s_tw1[slot] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)i / 2048.0f, &sn, &cs);
+    s_tw2[slot] = make_float2(cs, sn);
+  }
 }
 
 // The kernel is specialised on the output mode and the exponent: the frame loop is ~2k fully
@@ -82,17 +137,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < 1024; i += kFastThreads) {
-    const int j = i >> 5, l = i & 31;                       // register index, lane
-    const int slot = ((j >> 1) * 32 + l) * 2 + (j & 1);
-    const float g = 0.5f * p.scale;
-    s_win[slot] = make_float2(p.window[2 * i] * g, p.window[2 * i + 1] * g);
-    float sn, cs;
-    sincospif(-2.0f * (float)(j * l) / 1024.0f, &sn, &cs);
-    s_tw1[slot] = make_float2(cs, sn);
-    sincospif(-2.0f * (float)i / 2048.0f, &sn, &cs);
-    s_tw2[slot] = make_float2(cs, sn);
-  }
+  fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
   uint64_t* bar = s_bar + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -154,30 +199,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       __syncwarp();
     }
 
-    // ---- load: lane = n1, register r <-> z[n], n = n1 + 32 r, windowed ------------------------------
     float2 v[32];
-#pragma unroll
-    for (int r = 0; r < 32; r += 2) {
-      const float2 x0 = slab[lane + 32 * r], x1 = slab[lane + 32 * r + 32];
-      const float4 w = reinterpret_cast<const float4*>(s_win)[(r >> 1) * 32 + lane];
-      v[r] = make_float2(x0.x * w.x, x0.y * w.y);
-      v[r + 1] = make_float2(x1.x * w.z, x1.y * w.w);
-    }
-    __syncwarp();                                  // samples consumed; slab becomes the transpose buffer
-
-    // ---- pass 1: 32-point FFT over r for fixed n1 = lane, transpose through the slab, twiddle ------------
-    dit_fft_fma<32>(v);
-#pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = v[bit_reverse<32>(k2)];
-    __syncwarp();
-#pragma unroll
-    for (int n1 = 0; n1 < 32; n1 += 2) {
-      const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
-      const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];   // W_1024^(n1 * k2), k2 = lane
-      v[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
-      v[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
-    }
-    __syncwarp();                                  // slab free again: prefetch the next frame
+    fft2048_front(v, slab, s_win, s_tw1, lane);    // slab free again afterwards: prefetch the next frame
     {
       uint32_t seq_next = seq, t_next = t;
       advance(seq_next, t_next);
@@ -201,27 +224,20 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       dst_stride = 64 * p.frames;
     }
     const int partner = (32 - lane) & 31;
-#pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-      const float2 z = v[bit_reverse<32>(k1)];
-      float2 q;
-      q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].x, partner);
-      q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].y, partner);
-      if (lane == 0) q = v[bit_reverse<32>((32 - k1) & 31)];
-      const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
-      const float2 w = s_tw2[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];      // (c, d), W = c + i d
-      const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
-      const float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
+    auto emit = [&](auto k1c) {
+      constexpr int k1 = decltype(k1c)::value;
+      const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-        dst[k1 * 4096] = fast_power<PMODE>(xr, xi, half_power);
+        dst[k1 * 4096] = fast_power<PMODE>(x.x, x.y, half_power);
       } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
-        *reinterpret_cast<float2*>(dst) = make_float2(xr, xi);
+        *reinterpret_cast<float2*>(dst) = x;
         dst += dst_stride;
       } else {
-        *dst = fast_power<PMODE>(xr, xi, half_power);
+        *dst = fast_power<PMODE>(x.x, x.y, half_power);
         dst += dst_stride;
       }
-    }
+    };
+    static_for<32>(emit);
     // Nyquist bin (and zero fill of the row padding in frame-major mode); dst now points at bin 1024 + lane
     {
       const float2 z0 = v[0];
@@ -235,6 +251,100 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       }
     }
     advance(seq, t);
+  }
+}
+
+// n_fft = 2048 with the reference's public output layouts, (n_seq, 1025, frames[, 2]) with time innermost.
+// A frame's bins are 4 * frames bytes apart there, so per-frame stores would scatter 4-byte writes over 1025
+// rows.  Instead the CTA works on tiles of 16 consecutive frames of one sequence (warp w = frame t0 + w), the
+// 16 warps drop their spectra into a shared [bin][16] tile that re-uses the 16 slabs, and all 512 threads write
+// the tile out as 64-byte (power) / 128-byte (complex) row segments.  Costs three CTA barriers per tile and the
+// load/compute overlap of the power-tile kernel; buys 4-8x fewer store transactions.
+template <int OUT_MODE, int PMODE>
+__global__ void __launch_bounds__(kFastThreads, 1) stft2048_public_kernel(const StftParams p) {
+  static_assert(OUT_MODE == OUT_COMPLEX_PUBLIC || OUT_MODE == OUT_POWER_PUBLIC, "public layouts only");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_win = reinterpret_cast<float2*>(smem_raw);
+  float2* s_tw1 = s_win + 1024;
+  float2* s_tw2 = s_tw1 + 1024;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + 1024);
+  float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
+  constexpr int kRow = 17;                                  // staged tile row stride (elements): odd -> conflict free
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
+  uint64_t* bar = s_bar + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  float2* slab = s_slab + warp * kSlabComplex;
+  float* slab_f = reinterpret_cast<float*>(slab);
+  const float half_power = 0.5f * p.power;
+  const uint32_t frames_u = (uint32_t)p.frames;
+  const uint32_t tiles_per_seq = (frames_u + kFastWarps - 1) / kFastWarps;
+  const int64_t n_tiles = p.n_seq * (int64_t)tiles_per_seq;
+  const int partner = (32 - lane) & 31;
+  uint32_t parity = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t seq = (uint32_t)(tile / tiles_per_seq);
+    const uint32_t t0 = (uint32_t)(tile - (int64_t)seq * tiles_per_seq) * kFastWarps;
+    const uint32_t t = t0 + warp;
+    const bool active = t < frames_u;                       // warp-uniform
+    float2 v[32];
+    if (active) {
+      const int64_t start = (int64_t)t * p.hop - p.pad;
+      const float* row = p.x + (int64_t)seq * p.seq_stride;
+      if (p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples) {
+        if (elect_one()) {
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar, 2048 * sizeof(float));
+          bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+      } else {
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) slab_f[lane + 32 * i] = fetch_padded(row, start + lane + 32 * i, p.n_samples, p.pad_mode);
+        __syncwarp();
+      }
+      fft2048_front(v, slab, s_win, s_tw1, lane);
+      dit_fft_fma<32>(v);
+    }
+    __syncthreads();                                        // every slab is free: together they hold the output tile
+
+    if (active) {
+      auto stash = [&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
+        const int idx = (32 * k1 + lane) * kRow + warp;
+        if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) s_slab[idx] = x;
+        else reinterpret_cast<float*>(s_slab)[idx] = fast_power<PMODE>(x.x, x.y, half_power);
+      };
+      static_for<32>(stash);
+      if (lane == 0) {
+        const float nyq = 2.0f * (v[0].x - v[0].y);
+        if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) s_slab[1024 * kRow + warp] = make_float2(nyq, 0.0f);
+        else reinterpret_cast<float*>(s_slab)[1024 * kRow + warp] = fast_power<PMODE>(nyq, 0.0f, half_power);
+      }
+    }
+    __syncthreads();
+
+    // write-out: 16 threads per bin row, rows of this tile are `n_valid` consecutive frames
+    const uint32_t n_valid = min((uint32_t)kFastWarps, frames_u - t0);
+    const int f = tid & 15;
+    const int64_t out_base = ((int64_t)seq * 1025) * p.frames + t0 + f;
+    if (f < (int)n_valid) {
+      for (int bin = tid >> 4; bin < 1025; bin += kFastThreads / 16) {
+        const int64_t o = out_base + (int64_t)bin * p.frames;
+        if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) __stcs(reinterpret_cast<float2*>(p.out) + o, s_slab[bin * kRow + f]);
+        else __stcs(p.out + o, reinterpret_cast<const float*>(s_slab)[bin * kRow + f]);
+      }
+    }
+    __syncthreads();                                        // tile consumed: slabs may be refilled
   }
 }
 
@@ -322,11 +432,15 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
   if (n_frames <= 0) return TAC_OK;
   if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024)) return launch_stft_warp(p, stream);
   if (p.n_fft == 2048 && p.onesided) {
-    const int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
+    const bool whole = p.g0 == 0 && p.g1 == p.n_seq * p.frames;       // the tiled public kernel walks whole sequences
+    int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
+    if (whole && p.out_mode != OUT_POWER_ROWS) want = p.n_seq * ((p.frames + kFastWarps - 1) / kFastWarps);
     const int grid = (int)(want < sm_count() ? want : sm_count());
     using Kernel = void (*)(const StftParams);
     Kernel k = nullptr;
-    if (p.out_mode == OUT_COMPLEX_PUBLIC) k = stft2048_kernel<OUT_COMPLEX_PUBLIC, 1>;
+    if (p.out_mode == OUT_COMPLEX_PUBLIC) k = whole ? stft2048_public_kernel<OUT_COMPLEX_PUBLIC, 1> : stft2048_kernel<OUT_COMPLEX_PUBLIC, 1>;
+    else if (p.out_mode == OUT_POWER_PUBLIC && whole)
+      k = p.power_mode == 2 ? stft2048_public_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_public_kernel<OUT_POWER_PUBLIC, 1> : stft2048_public_kernel<OUT_POWER_PUBLIC, 0>);
     else if (p.out_mode == OUT_POWER_PUBLIC)
       k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_PUBLIC, 1> : stft2048_kernel<OUT_POWER_PUBLIC, 0>);
     else

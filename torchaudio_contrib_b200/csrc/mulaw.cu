@@ -29,7 +29,7 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(kMuLawThreads)
 mulaw_encode_kernel(const float* __restrict__ x, int64_t n, long long* __restrict__ out,
                     const float* __restrict__ thr, int n_thr, int idx_min, float x_limit,
-                    float mu, float half_mu_over_log2, int variant) {
+                    float mu, float half_mu_over_log2) {
   extern __shared__ float s_thr[];
   const float* table = thr;
   if (kSmemTable) {
@@ -65,13 +65,8 @@ mulaw_encode_kernel(const float* __restrict__ x, int64_t n, long long* __restric
       hi.x = encode_one(v.z);
       hi.y = encode_one(v.w);
       longlong2* o = reinterpret_cast<longlong2*>(out) + 2 * i;
-      if (variant & 1) {
-        o[0] = lo;
-        o[1] = hi;
-      } else {
-        __stcs(o, lo);
-        __stcs(o + 1, hi);
-      }
+      __stcs(o, lo);
+      __stcs(o + 1, hi);
     }
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kMuLawThreads + threadIdx.x; i < n; i += stride)
       out[i] = encode_one(x[i]);
@@ -152,21 +147,17 @@ extern "C" int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantiz
   TAC_REQUIRE(x && out && thresholds_dev && n_thresholds >= 1, TAC_ERR_INVALID, "mulaw_encode: null pointer / empty table");
   const float mu = (float)(n_quantize - 1);
   const float half_mu_over_log2 = (float)(0.5 * (double)mu / log2(1.0 + (double)mu));
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("TAC_MULAW_VARIANT");
-    variant = e ? atoi(e) : 0;
-  }
-  int grid = streaming_grid((n + 3) / 4);
-  if (variant >> 4) grid = (grid > sm_count() * (variant >> 4)) ? sm_count() * (variant >> 4) : grid;
+  // 6 CTAs (1536 threads) per SM: measured 92.8 % of the HBM copy peak, against 74.6 % at full occupancy
+  // (8 CTAs) and 78 % at 4 -- profiles/r01_notes.md
+  const int grid = streaming_grid((n + 3) / 4, 6);
   LaunchProbe probe(KIND_MULAW, as_stream(stream));
   if (n_thresholds <= kMuLawSmemTableMax) {
     const size_t smem = (size_t)n_thresholds * sizeof(float);
     mulaw_encode_kernel<true><<<grid, kMuLawThreads, smem, as_stream(stream)>>>(
-        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2, variant);
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
   } else {
     mulaw_encode_kernel<false><<<grid, kMuLawThreads, 0, as_stream(stream)>>>(
-        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2, variant);
+        x, n, reinterpret_cast<long long*>(out), thresholds_dev, n_thresholds, idx_min, x_limit, mu, half_mu_over_log2);
   }
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
@@ -182,7 +173,7 @@ static int launch_decode(const CodeT* codes, int64_t n, int n_quantize, const fl
               n_quantize, kMuLawSmemTableMax);
   const float mu = (float)(n_quantize - 1);
   const float log1p_mu = (float)log1p((double)mu);
-  const int grid = streaming_grid((n + 3) / 4);
+  const int grid = streaming_grid((n + 3) / 4, 6);
   LaunchProbe probe(KIND_MULAW, as_stream(stream));
   mulaw_decode_kernel<CodeT><<<grid, kMuLawThreads, (size_t)n_quantize * sizeof(float), as_stream(stream)>>>(
       codes, n, out, lut_dev, n_quantize, mu, log1p_mu);

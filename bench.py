@@ -311,10 +311,40 @@ def run_ours(args, rank, world, local):
         e2e_s = time.perf_counter() - t0
         barrier()
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # optional output all-gather (BASELINE config 4): every rank ends up with the (world*batch, C, M, frames)
+    # tensor.  One NCCL all_gather_into_tensor per step, issued on a side stream so it overlaps the next step.
+    gather_ms = 0.0
+    if world > 1:
+        import torch.distributed as dist
+        full = torch.empty((world * batch, channels, N_MELS, frames), dtype=torch.float32, device=dev)
+        comm = torch.cuda.Stream(device=dev)
+        outs = [torch.empty((batch, channels, N_MELS, frames), dtype=torch.float32, device=dev) for _ in range(2)]
+        with torch.no_grad():
+            def step(i):
+                y = model(inputs[i % n_sets])
+                buf = outs[i % 2]
+                buf.copy_(y)
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(comm):
+                    comm.wait_event(done)
+                    dist.all_gather_into_tensor(full, buf)
+            for i in range(3):
+                step(i)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for i in range(args.steps):
+                step(i)
+            torch.cuda.current_stream(dev).wait_stream(comm)
+            g1.record()
+            barrier()
+        gather_ms = g0.elapsed_time(g1)
+
+    t = torch.tensor([ms, e2e_s * 1e3, gather_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -350,6 +380,12 @@ def run_ours(args, rank, world, local):
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
+        if world > 1:
+            line["with_allgather"] = {
+                "value": world * args.steps * frames_per_step / (gather_ms * 1e-3), "unit": "frames/s",
+                "ms_per_step": gather_ms / args.steps,
+                "what": "same steps + one NCCL all_gather_into_tensor of the (batch,C,128,frames) output per step on a side stream",
+                "bytes_received_per_rank_per_step": (world - 1) * out_bytes}
         traffic_file = os.path.join(ROOT, "profiles", "r01_stft2048_dram_bytes.json")
         if os.path.exists(traffic_file):
             with open(traffic_file) as fh:

@@ -210,6 +210,21 @@ def test_stft_2048_fast_path(tac, oc, fft):
     assert rel_err(sp, oc.spectrogram(x, fft, 512, power=2.0)) < REL
 
 
+@pytest.mark.parametrize("fft,hop", [(2048, 512), (2048, 500), (512, 128), (256, 64), (1024, 256)])
+@pytest.mark.parametrize("pad_mode", ["reflect", "replicate", "constant"])
+def test_stft_edge_frames_rect_window(tac, oc, fft, hop, pad_mode):
+    """Edge frames are bulk-copied and their padding is rebuilt inside shared memory; a rectangular window keeps
+    every padded sample visible (a Hann window hides sample 0 of frame 0), short rows make most frames edge frames."""
+    torch.manual_seed(31)
+    for T in (fft + 4, 3 * fft, 5 * fft + 8):
+        x = torch.randn(3, T)
+        win = torch.ones(fft)
+        got = tac.stft(dev(x), fft, hop, window=dev(win), pad_mode=pad_mode).cpu()
+        want = oc.stft(x, fft, hop, window=win, pad_mode=pad_mode)
+        assert got.shape == want.shape
+        assert rel_err(got, want) < REL, (T, pad_mode)
+
+
 def test_spectrogram_db_vs_f64(tac):
     """tests/test_layers.py:55-83 with librosa replaced by the float64 restatement (atol 1e-2)."""
     from oracle import f64_chain

@@ -18,6 +18,8 @@
 //
 // Output modes (OUT_*): the public layouts of the reference, and the frame-major power rows that
 // feed the filterbank kernel (melbank.cu) inside the Melspectrogram pipeline.
+#include <stdlib.h>
+
 #include "fft_regs.cuh"
 #include "stft_params.cuh"
 #include "tac_common.cuh"
@@ -124,6 +126,9 @@ __device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_wi
 // unrolled instructions and has to stay resident in the instruction caches while 16 warps run
 // through it at different phases (a first version that branched on these at run time was 12k
 // instructions and spent most of its time stalled on instruction fetch).
+__device__ long long g_k1_trace[64];      // TAC_K1_TRACE: clock64 stamps of CTA 0 / warp 0
+#define K1_TRACE(i) do { if (p.debug && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_k1_trace[i] = clock64(); } while (0)
+
 template <int OUT_MODE, int PMODE>
 __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  K1_TRACE(0);
 
   fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
   uint64_t* bar = s_bar + warp;
@@ -144,6 +150,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     fence_mbar_init();
   }
   __syncthreads();
+  K1_TRACE(1);
+  int trace_i = 2;
 
   float2* slab = s_slab + warp * kSlabComplex;
   float* slab_f = reinterpret_cast<float*>(slab);
@@ -165,47 +173,55 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   };
 
   // a frame can use the bulk copy when it lies inside the sequence and everything is 16B aligned
-  auto stage_frame = [&](uint32_t seq, uint32_t t) -> bool {    // returns true when a bulk copy is in flight
+  // Interior frames: the bulk copy is issued in the middle of the previous frame (slab just freed) and lands
+  // while that frame finishes.  Frames that touch the padding are gathered instead, and that is deferred to the
+  // end of the previous frame, when all 64 data registers are free and 32 loads per lane can be in flight.
+  FrameSpan span_cur, span_next;                                // which part of the slab the bulk copy fills
+  span_cur.lo = 0; span_cur.hi = 2048; span_cur.bulk = false;
+  span_next = span_cur;
+  auto stage_bulk = [&](uint32_t seq, uint32_t t, FrameSpan& span) -> bool {   // true: bulk copy in flight; false: needs the gather
     const int64_t start = (int64_t)t * p.hop - p.pad;
-    const float* row = p.x + (int64_t)seq * p.seq_stride;
-    const bool bulk = p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples;
-    if (bulk) {
-      if (elect_one()) {
-        fence_proxy_async();
-        mbar_arrive_expect_tx(bar, 2048 * sizeof(float));
-        bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);
-      }
-    } else {
-#pragma unroll 4
-      for (int i = 0; i < 64; ++i) {
-        const int j = lane + 32 * i;
-        slab_f[j] = fetch_padded(row, start + j, p.n_samples, p.pad_mode);
-      }
+    span = frame_span<2048>(p, start);
+    if (span.bulk && elect_one()) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)(span.hi - span.lo) * sizeof(float);
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(slab_f + span.lo, p.x + (int64_t)seq * p.seq_stride + (start + span.lo), bytes, bar);
     }
-    return bulk;
+    return span.bulk;
+  };
+  auto stage_gather = [&](uint32_t seq, uint32_t t) {
+    const int64_t start = (int64_t)t * p.hop - p.pad;
+    gather_padded<64, 32>(slab_f, p.x + (int64_t)seq * p.seq_stride, (int)start, (int)p.n_samples, p.pad_mode, lane);
   };
 
   int64_t g = p.g0 + (int64_t)blockIdx.x * kFastWarps + warp;
   uint32_t seq = (uint32_t)(g / p.frames), t = (uint32_t)(g % p.frames);      // once per warp
   bool in_flight = false;
-  if (g < p.g1) in_flight = stage_frame(seq, t);
+  if (g < p.g1) {
+    in_flight = stage_bulk(seq, t, span_cur);
+    if (!in_flight) stage_gather(seq, t);
+  }
 
 #pragma unroll 1
   for (; g < p.g1; g += step) {
     if (in_flight) {
       mbar_wait(bar, parity);
       parity ^= 1u;
+      fill_padding<2048>(slab_f, span_cur, p.pad_mode, lane, p.x + (int64_t)seq * p.seq_stride, (int64_t)t * p.hop - p.pad);
     } else {
       __syncwarp();
     }
 
+    K1_TRACE(trace_i); ++trace_i;                  // sample data arrived
+    if (p.debug && blockIdx.x == 0 && lane == 0 && g_k1_trace[40 + warp] == 0) g_k1_trace[40 + warp] = clock64();
     float2 v[32];
     fft2048_front(v, slab, s_win, s_tw1, lane);    // slab free again afterwards: prefetch the next frame
-    {
-      uint32_t seq_next = seq, t_next = t;
-      advance(seq_next, t_next);
-      in_flight = (g + step < p.g1) ? stage_frame(seq_next, t_next) : false;
-    }
+    K1_TRACE(trace_i); ++trace_i;                  // front half done
+    uint32_t seq_next = seq, t_next = t;
+    advance(seq_next, t_next);
+    const bool has_next = g + step < p.g1;
+    in_flight = has_next ? stage_bulk(seq_next, t_next, span_next) : false;
     // ---- pass 2: 32-point FFT over n1 for fixed k2 = lane ---------------------------------------------
     dit_fft_fma<32>(v);
     // now v[bit_reverse(k1)] = Z[32 k1 + lane] / 2
@@ -250,7 +266,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
         if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(nyq, 0.0f);
       }
     }
-    advance(seq, t);
+    K1_TRACE(trace_i); ++trace_i;                  // frame done
+    if (has_next && !in_flight) stage_gather(seq_next, t_next);
+    seq = seq_next;
+    t = t_next;
+    span_cur = span_next;
   }
 }
 
@@ -298,17 +318,19 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_public_kernel(const 
     if (active) {
       const int64_t start = (int64_t)t * p.hop - p.pad;
       const float* row = p.x + (int64_t)seq * p.seq_stride;
-      if (p.bulk_ok && start >= 0 && start + 2048 <= p.n_samples) {
+      const FrameSpan span = frame_span<2048>(p, start);
+      if (span.bulk) {
         if (elect_one()) {
           fence_proxy_async();
-          mbar_arrive_expect_tx(bar, 2048 * sizeof(float));
-          bulk_g2s(slab, row + start, 2048 * sizeof(float), bar);
+          const uint32_t bytes = (uint32_t)(span.hi - span.lo) * sizeof(float);
+          mbar_arrive_expect_tx(bar, bytes);
+          bulk_g2s(slab_f + span.lo, row + (start + span.lo), bytes, bar);
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
+        fill_padding<2048>(slab_f, span, p.pad_mode, lane, row, start);
       } else {
-#pragma unroll 4
-        for (int i = 0; i < 64; ++i) slab_f[lane + 32 * i] = fetch_padded(row, start + lane + 32 * i, p.n_samples, p.pad_mode);
+        gather_padded<64, 32>(slab_f, row, (int)start, (int)p.n_samples, p.pad_mode, lane);
         __syncwarp();
       }
       fft2048_front(v, slab, s_win, s_tw1, lane);
@@ -427,6 +449,18 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
   }
 }
 
+int dump_k1_trace() {
+  long long h[64];
+  TAC_CUDA_OK(cudaDeviceSynchronize());
+  TAC_CUDA_OK(cudaMemcpyFromSymbol(h, g_k1_trace, sizeof(h)));
+  printf("k1 trace (cycles since kernel entry of CTA 0):");
+  for (int i = 0; i < 40; ++i) printf(" %lld", h[i] ? h[i] - h[0] : -1);
+  printf("\nfirst data arrival per warp of CTA 0:");
+  for (int i = 40; i < 56; ++i) printf(" %lld", h[i] ? h[i] - h[0] : -1);
+  printf("\n");
+  return TAC_OK;
+}
+
 int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
@@ -481,6 +515,8 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   if (center && pad_mode == TAC_PAD_CIRCULAR)
     TAC_REQUIRE(pad <= n_samples, TAC_ERR_INVALID, "stft: circular padding %d wraps more than once (time %lld)", pad,
                 (long long)n_samples);
+  TAC_REQUIRE(n_samples + 2 * (int64_t)n_fft < ((int64_t)1 << 31), TAC_ERR_UNSUPPORTED,
+              "stft: sequences of %lld samples exceed the 2^31 the kernels index", (long long)n_samples);
   TAC_REQUIRE(n_samples + 2 * pad >= n_fft, TAC_ERR_INVALID, "stft: input of %lld samples is shorter than n_fft=%d",
               (long long)n_samples, n_fft);
   p.x = x;
@@ -506,10 +542,15 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.power_mode = 1;
   p.out_mode = OUT_COMPLEX_PUBLIC;
   p.out = nullptr;
+  static int debug = -1;
+  if (debug < 0) debug = getenv("TAC_K1_TRACE") ? 1 : 0;
+  p.debug = debug;
   return TAC_OK;
 }
 
 }  // namespace tac
+
+extern "C" int tac_debug_dump_k1_trace(void) { return tac::dump_k1_trace(); }
 
 extern "C" int64_t tac_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center) {
   if (hop <= 0 || n_fft <= 0) return 0;

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
       const uint32_t seq = g / frames_u, t = g - seq * frames_u;
       const int64_t start = (int64_t)t * p.hop - p.pad;
       const bool live = (int64_t)g < p.g1;
-      const bool bulk = live && p.bulk_ok && start >= 0 && start + N <= p.n_samples;
-      if (bulk) bulk_bytes += N * 4;
+      const FrameSpan span = frame_span<N>(p, start);
+      if (live && span.bulk) bulk_bytes += (uint32_t)(span.hi - span.lo) * 4;
     }
     if (elect_one()) {
       fence_proxy_async();
@@ -106,17 +106,25 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
       const int64_t start = (int64_t)t * p.hop - p.pad;
       const bool live = (int64_t)g < p.g1;
       const float* row = p.x + (int64_t)seq * p.seq_stride;
-      const bool bulk = live && p.bulk_ok && start >= 0 && start + N <= p.n_samples;
-      if (bulk) {
-        if (elect_one()) bulk_g2s(slab_f + f * N, row + start, N * 4, bar);
+      const FrameSpan span = frame_span<N>(p, start);
+      if (live && span.bulk) {
+        if (elect_one()) bulk_g2s(slab_f + f * N + span.lo, row + (start + span.lo), (uint32_t)(span.hi - span.lo) * 4, bar);
       } else {
-        for (int j = lane; j < N; j += 32)
-          slab_f[f * N + j] = live ? fetch_padded(row, start + j, p.n_samples, p.pad_mode) : 0.0f;
+        gather_padded<N / 32>(slab_f + f * N, row, (int)start, (int)p.n_samples, p.pad_mode, lane, live);
       }
     }
     if (bulk_bytes) {
       mbar_wait(bar, parity);
       parity ^= 1u;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {                            // frames that stick out of their row: fill from the slab
+        const uint32_t g = gb + f;
+        const uint32_t seq = g / frames_u, t = g - seq * frames_u;
+        const int64_t start = (int64_t)t * p.hop - p.pad;
+        const FrameSpan span = frame_span<N>(p, start);
+        if ((int64_t)g < p.g1 && span.bulk)
+          fill_padding<N>(slab_f + f * N, span, p.pad_mode, lane, p.x + (int64_t)seq * p.seq_stride, start);
+      }
     }
     __syncwarp();
 

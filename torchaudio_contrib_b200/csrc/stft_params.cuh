@@ -26,6 +26,7 @@ struct StftParams {
   int power_mode;          // 2: |X|^2, 1: |X|, 0: |X|^power
   float power;
   float scale;             // n_fft^-0.5 when normalized, else 1
+  int debug;               // TAC_K1_TRACE: clock stamps of CTA 0 / warp 0 (timing experiments only)
 };
 
 // Power tiles (OUT_POWER_ROWS): frames are grouped in tiles of 128; for each tile and each 32-bin slice the
@@ -57,6 +58,86 @@ __device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int
     default: return 0.0f;                                       // TAC_PAD_CONSTANT
   }
   return (s >= 0 && s < n) ? __ldg(row + s) : 0.0f;
+}
+
+// Gather of 32 * COUNT consecutive padded samples (lane-strided) into shared memory, in explicit batches of
+// BATCH loads so that BATCH global loads are in flight per lane (a
+// load-store-load-store sequence costs a full memory latency per sample: measured 16 us per edge frame).
+// 32-bit index arithmetic: the host guarantees n_samples + n_fft < 2^31.
+__device__ __forceinline__ int padded_index(int s, int n, int pad_mode) {
+  int r = s;
+  if (pad_mode == 0) r = (s < 0) ? -s : ((s >= n) ? 2 * (n - 1) - s : s);          // reflect
+  else if (pad_mode == 3) r = (s < 0) ? s + n : ((s >= n) ? s - n : s);              // circular
+  return r < 0 ? 0 : (r >= n ? n - 1 : r);                                           // replicate / safety clamp
+}
+template <int COUNT, int BATCH = 8>
+__device__ __forceinline__ void gather_padded(float* dst, const float* __restrict__ row, int start, int n, int pad_mode, int lane,
+                                              bool live = true) {
+  static_assert(COUNT % BATCH == 0, "whole batches");
+#pragma unroll 1
+  for (int base = 0; base < COUNT; base += BATCH) {
+    float tmp[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int s = start + lane + 32 * (base + u);
+      const bool inside = (s >= 0) & (s < n);
+      const float v = live ? __ldg(row + padded_index(s, n, pad_mode)) : 0.0f;
+      tmp[u] = (pad_mode == 1 && !inside) ? 0.0f : v;
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) dst[lane + 32 * (base + u)] = tmp[u];
+  }
+}
+
+// ---- frame staging shared by the warp-level kernels ------------------------------------------------------
+// A frame is samples [start, start + N) of its row, start = t * hop - pad.  With 16-byte alignment
+// (p.bulk_ok, and n_samples % 4 == 0 for frames that cross the end) the part that lies inside the row is
+// fetched with ONE bulk async copy into its place in the slab; whatever sticks out on the left / right is
+// then produced from the slab itself: reflection = mirror inside the slab, replicate = edge value, constant =
+// zeros.  (Per-sample gathers with index arithmetic made an edge frame ~8x as expensive as an interior one and
+// the warps owning the first two frames of a sequence set the kernel's makespan.)  Circular padding and frames
+// wider than the row use the gather.
+struct FrameSpan {
+  int lo, hi;        // slab indices [lo, hi) filled by the bulk copy (0 / N for interior frames)
+  bool bulk;
+};
+template <int N>
+__device__ __forceinline__ FrameSpan frame_span(const StftParams& p, int64_t start) {
+  FrameSpan f;
+  const int64_t lo = start < 0 ? -start : 0;
+  const int64_t hi = (start + N > p.n_samples) ? p.n_samples - start : N;
+  f.lo = (int)lo;
+  f.hi = (int)hi;
+  const bool interior = lo == 0 && hi == N;
+  f.bulk = p.bulk_ok && hi > lo && (interior || (p.pad_mode != 3 && (p.n_samples & 3) == 0 && !(lo > 0 && hi < N)));
+  return f;
+}
+// after the bulk copy has landed: fill slab[0, lo) and slab[hi, N) (warp-cooperative, then __syncwarp).
+// `row` / `start` locate the frame in its row: a reflected sample whose source lies outside the part of the
+// frame that was copied (only when the padding is as long as the valid part, e.g. sample 0 of frame 0) is
+// read from global memory.
+template <int N>
+__device__ __forceinline__ void fill_padding(float* slab_f, const FrameSpan f, int pad_mode, int lane,
+                                             const float* __restrict__ row, int64_t start) {
+  if (f.lo == 0 && f.hi == N) return;
+  if (pad_mode == 0) {                                   // reflect: x[-k] = x[k], x[n-1+k] = x[n-1-k]
+    for (int j = lane; j < f.lo; j += 32) {
+      const int src = 2 * f.lo - j;
+      slab_f[j] = (src < f.hi) ? slab_f[src] : __ldg(row + (start + src));
+    }
+    for (int j = f.hi + lane; j < N; j += 32) {
+      const int src = 2 * (f.hi - 1) - j;
+      slab_f[j] = (src >= f.lo) ? slab_f[src] : __ldg(row + (start + src));
+    }
+  } else if (pad_mode == 2) {                            // replicate
+    const float a = slab_f[f.lo], b = slab_f[f.hi - 1];
+    for (int j = lane; j < f.lo; j += 32) slab_f[j] = a;
+    for (int j = f.hi + lane; j < N; j += 32) slab_f[j] = b;
+  } else {                                               // constant
+    for (int j = lane; j < f.lo; j += 32) slab_f[j] = 0.0f;
+    for (int j = f.hi + lane; j < N; j += 32) slab_f[j] = 0.0f;
+  }
+  __syncwarp();
 }
 #endif
 

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   // Interior frames: the bulk copy is issued in the middle of the previous frame (slab just freed) and lands
   // while that frame finishes.  Frames that touch the padding are gathered instead, and that is deferred to the
   // end of the previous frame, when all 64 data registers are free and 32 loads per lane can be in flight.
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   FrameSpan span_cur, span_next;                                // which part of the slab the bulk copy fills
   span_cur.lo = 0; span_cur.hi = 2048; span_cur.bulk = false;
   span_next = span_cur;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       fence_proxy_async();
       const uint32_t bytes = (uint32_t)(span.hi - span.lo) * sizeof(float);
       mbar_arrive_expect_tx(bar, bytes);
-      bulk_g2s(slab_f + span.lo, p.x + (int64_t)seq * p.seq_stride + (start + span.lo), bytes, bar);
+      bulk_g2s_hint(slab_f + span.lo, p.x + (int64_t)seq * p.seq_stride + (start + span.lo), bytes, bar, pol_stream);
     }
     return span.bulk;
   };
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       constexpr int k1 = decltype(k1c)::value;
       const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-        dst[k1 * 4096] = fast_power<PMODE>(x.x, x.y, half_power);
+        st_global_hint(dst + k1 * 4096, fast_power<PMODE>(x.x, x.y, half_power), pol_keep);
       } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
         *reinterpret_cast<float2*>(dst) = x;
         dst += dst_stride;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       const float2 z0 = v[0];
       const float nyq = 2.0f * (z0.x - z0.y);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-        dst[32 * 4096] = (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f;   // slice 32: Nyquist + zero fill
+        st_global_hint(dst + 32 * 4096, (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f, pol_keep);   // slice 32: Nyquist + zero fill
       } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
         if (lane == 0) *dst = fast_power<PMODE>(nyq, 0.0f, half_power);
       } else {

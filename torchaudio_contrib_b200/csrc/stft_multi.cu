@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
     // ---- stage the F frames: bulk copy where possible, gather otherwise ---------------------------------
     __syncwarp();                                             // previous batch is done with the slab
     uint32_t bulk_bytes = 0;
+    bool any_edge = false;                                    // some bulk-copied frame sticks out of its row
 #pragma unroll
     for (int f = 0; f < F; ++f) {
       const uint32_t g = gb + f;
@@ -93,7 +94,10 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
       const int64_t start = (int64_t)t * p.hop - p.pad;
       const bool live = (int64_t)g < p.g1;
       const FrameSpan span = frame_span<N>(p, start);
-      if (live && span.bulk) bulk_bytes += (uint32_t)(span.hi - span.lo) * 4;
+      if (live && span.bulk) {
+        bulk_bytes += (uint32_t)(span.hi - span.lo) * 4;
+        any_edge |= (span.hi - span.lo) != N;
+      }
     }
     if (elect_one()) {
       fence_proxy_async();
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
       mbar_wait(bar, parity);
       parity ^= 1u;
 #pragma unroll
-      for (int f = 0; f < F; ++f) {                            // frames that stick out of their row: fill from the slab
+      for (int f = 0; f < F && any_edge; ++f) {                // frames that stick out of their row: fill from the slab
         const uint32_t g = gb + f;
         const uint32_t seq = g / frames_u, t = g - seq * frames_u;
         const int64_t start = (int64_t)t * p.hop - p.pad;

@@ -3,8 +3,7 @@ set -x
 mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep gpurun_out/launches*.csv
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6 > gpurun_out/t_gpu_all.log; cat gpurun_out/t_gpu_all.log
 python bench.py --steps 1000 --warmup 5 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; cut -c1-1200 gpurun_out/bench_cfg2.json
-TAC_MELSPEC_SLICE_ROWS=20032 python bench.py --steps 500 --warmup 5 --cpu-seconds 0.2 > gpurun_out/bench_cfg2_oneslice.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/bench_cfg2_oneslice.json')); print('oneslice', d['value'], d['ms_per_step'], d['kernel_ms_per_step'])"
+python scripts/gpu_time_ops.py > gpurun_out/time_ops.txt 2>&1; cat gpurun_out/time_ops.txt
 python bench.py --steps 20 --warmup 3 --workload cfg3 --cpu-seconds 4 > gpurun_out/bench_cfg3.json 2>/dev/null; cut -c1-400 gpurun_out/bench_cfg3.json
 python bench.py --workload mulaw --steps 20 > gpurun_out/bench_mulaw.json 2>/dev/null; cut -c1-1500 gpurun_out/bench_mulaw.json
 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/bench_reference.json 2>/dev/null; cut -c1-300 gpurun_out/bench_reference.json

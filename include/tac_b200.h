@@ -75,6 +75,12 @@ int64_t tac_fbplan_bytes(int n_bins, int n_bands);                 /* upper boun
 int tac_fbplan_build_host(const float* fb_host, int n_bins, int n_bands,
                           void* plan_host, int64_t plan_capacity, int64_t* plan_bytes_used);
 
+/* Non-zero when the plan also carries the matrix as a "band plan": every row has at most two
+ * non-zeros, in adjacent columns, and they chain from band to band (any triangular filterbank,
+ * e.g. create_mel_filter functional.py:131-169, n_bins = 1025).  The opaque handle is what
+ * tac_melspec_banded_f32 takes; 0 means only the tensor-core path applies. */
+int64_t tac_fbplan_band_handle(const void* plan_host);
+
 /* spec: (n_seq, n_bins, frames) real, or (n_seq, n_bins, frames, 2) complex when is_complex.
  * Computes |.|^power first when is_complex (a2), contracts over bins with the plan (a3) and,
  * when to_db, applies amplitude_to_db(ref, amin) in the epilogue (a5).
@@ -94,6 +100,19 @@ int tac_melspec_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t se
                     int normalized, float power,
                     const void* plan_dev, int n_bands, int to_db, float ref, float amin,
                     void* workspace, int64_t workspace_bytes, float* out, void* stream);
+
+/* Same chain in ONE kernel for n_fft = 2048 and a plan with a band plan: each warp takes a
+ * frame from its bulk-copied samples to its n_bands outputs; the spectrum never leaves the SM
+ * and HBM sees the input once and the output once (SURVEY 2a "K3").  Replaces torch.stft
+ * (functional.py:99-107), torch.norm/.pow (:126-128), the transpose-matmul-transpose (:183-184)
+ * and the dB chain (:291-296).  out: (n_seq, n_bands, frames) contiguous, or when frame_major
+ * (n_seq, frames, n_bands) -- the memory order behind the reference's transposed view. */
+int tac_melspec_banded_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                           const float* window, int n_fft, int hop, int center, int pad_mode,
+                           int normalized, float power,
+                           const void* plan_dev, int64_t band_handle, int n_bands,
+                           int to_db, float ref, float amin,
+                           float* out, int frame_major, void* stream);
 
 /* ---- a7: mu_law_encoding (functional.py:317-335) ----------------------------------------
  * The quantiser is evaluated as a table of decision levels: thresholds[j] is the smallest

@@ -343,3 +343,101 @@ def test_melspectrogram_stretch_shapes(tac):
     model = torch.nn.Sequential(tac.STFT(512, hop_length=256), tac.ComplexNorm(power=2.0), tac.ApplyFilterbank(fb)).cuda()
     y = model(x)
     assert y.shape == (4, 128, (100000 + 512 - 512 + 256) // 256)
+
+
+# ------------------------------------------------------------------------------------------ one-kernel mel path
+def _mel_chain(tac, sr=16000, num_mels=128, to_db=False, **stft_kw):
+    mods = list(tac.Melspectrogram(num_mels=num_mels, sample_rate=sr, fft_length=2048, **stft_kw))
+    if to_db:
+        mods.append(tac.AmplitudeToDb())
+    return tac.Sequential(*mods).cuda()
+
+
+def test_fused_mel_is_taken_and_matches_two_kernel_path(tac, oc, monkeypatch):
+    """fft 2048 + triangular matrix -> ONE launch (csrc/stft.cu OUT_MEL_FUSED); TAC_MELSPEC_FUSED=0 -> the
+    stft + tensor-core filterbank pair.  Both must agree with the oracle."""
+    torch.manual_seed(41)
+    x = torch.randn(5, 1, 40000)
+    m = _mel_chain(tac, hop_length=512)
+    lib = tac._cabi.lib()
+    m(dev(x))                                                   # plan built, tables uploaded
+    n0 = lib.tac_launch_count()
+    fused = m(dev(x)).cpu()
+    assert lib.tac_launch_count() - n0 == 1
+    monkeypatch.setenv("TAC_MELSPEC_FUSED", "0")
+    n0 = lib.tac_launch_count()
+    pair = m(dev(x)).cpu()
+    assert lib.tac_launch_count() - n0 == 2
+    want = oc.melspectrogram(x, 128, 16000, fft_length=2048, hop_length=512)
+    assert pure_rel_err(fused, want) < REL
+    assert pure_rel_err(pair, want) < REL
+
+
+def test_fused_mel_reference_layout(tac, oc):
+    """layout='reference': the memory order behind the reference's `.transpose(-2, -1)` view
+    (functional.py:183-184; SURVEY H6 measured strides (..., 1, num_bands))."""
+    torch.manual_seed(43)
+    x = torch.randn(3, 2, 30000)
+    fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+    got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512, layout="reference")
+    want = oc.melspectrogram(x, 128, 16000, fft_length=2048, hop_length=512)
+    assert got.shape == want.shape == (3, 2, 128, 59)
+    assert got.stride()[-2:] == (1, 128) == want.stride()[-2:]
+    assert pure_rel_err(got.cpu(), want) < REL
+    same = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512)
+    assert same.is_contiguous() and torch.equal(same, got.contiguous())
+
+
+@pytest.mark.parametrize("power", [1.0, 2.0, 0.7])
+def test_fused_mel_other_exponents(tac, oc, power):
+    torch.manual_seed(47)
+    x = torch.randn(2, 1, 20000)
+    fb = tac.MelFilterbank(num_freqs=1025, num_mels=64, sample_rate=22050).get_filterbank()
+    got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 300, power=power).cpu()
+    want = oc.apply_filterbank(oc.spectrogram(x, 2048, 300, power=power), fb)
+    assert got.shape == want.shape
+    assert pure_rel_err(got, want) < REL
+
+
+@pytest.mark.parametrize("pad_mode", ["reflect", "replicate", "constant", "circular"])
+def test_fused_mel_edge_frames_and_options(tac, oc, pad_mode):
+    """short rows (most frames touch the padding), rectangular window, normalized, win_length, htk, min_freq"""
+    torch.manual_seed(53)
+    win = torch.ones(2048)
+    fb = tac.functional.create_mel_filter(1025, 96, 200.0, 7000.0, True)
+    for T in (2052, 6144, 10248, 4099):                         # 4099: odd length -> per-sample gather path
+        x = torch.randn(3, T)
+        got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512, window=dev(win), pad_mode=pad_mode,
+                                            normalized=True, to_db=True, ref=2.0, amin=1e-6).cpu()
+        spec = oc.spectrogram(x, 2048, 512, window=win, pad_mode=pad_mode, normalized=True, power=2.0)
+        want = oc.amplitude_to_db(oc.apply_filterbank(spec, fb), ref=2.0, amin=1e-6)
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() < 1e-3, (T, pad_mode)
+    x = torch.randn(2, 9000)
+    got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512, win_length=1200, center=False).cpu()
+    want = oc.apply_filterbank(oc.spectrogram(x, 2048, 512, win_length=1200, center=False, power=2.0), fb)
+    assert got.shape == want.shape and pure_rel_err(got, want) < REL
+
+
+def test_fused_mel_full_size_cfg3_properties(tac):
+    """BASELINE config 3 shape per channel pair, reduced batch (16 of 256): dB output finite, deterministic,
+    batch-independent, +20*log10(2)*2 dB when the input doubles (the reference squares the power again)."""
+    torch.manual_seed(59)
+    x = torch.randn(16, 2, 480000, device="cuda")
+    m = _mel_chain(tac, sr=48000, to_db=True, hop_length=512)
+    y = m(x)
+    assert y.shape == (16, 2, 128, 938) and torch.isfinite(y).all()
+    assert torch.equal(m(x), y)
+    assert torch.equal(m(x[3:5]), y[3:5])
+    y2 = m(2.0 * x)
+    assert (y2 - y - 40.0 * np.log10(2.0)).abs().max().item() < 1e-3
+
+
+def test_host_pipeline_mel_fused_and_pair(tac, monkeypatch):
+    g = golden("mel_16k_2048_512.npz")
+    fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+    hp = tac.HostPipeline(2048, 512, power=2.0, filterbank=fb)
+    assert pure_rel_err(hp(g["x"]), g["out"]) < REL
+    monkeypatch.setenv("TAC_MELSPEC_FUSED", "0")
+    hp2 = tac.HostPipeline(2048, 512, power=2.0, filterbank=fb)
+    assert pure_rel_err(hp2(g["x"]), g["out"]) < REL

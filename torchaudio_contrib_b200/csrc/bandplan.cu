@@ -1,0 +1,124 @@
+// Host-side construction of the band plan (bandplan.cuh) from a (n_bins, n_bands) row-major matrix.
+#include "bandplan.cuh"
+
+#include <string.h>
+
+#include <vector>
+
+#include "tac_common.cuh"
+
+namespace tac {
+
+int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char* dst, int64_t capacity) {
+  if (n_bins != kBandBins || n_bands < 1 || n_bands > 4096) return 0;
+  if (capacity < band_plan_capacity(n_bands)) return 0;
+
+  // ---- every bin -> (band b, w0 into b, w1 into b + 1) -------------------------------------------------
+  std::vector<int> band(n_bins, 0);
+  std::vector<float> w0(n_bins, 0.0f), w1(n_bins, 0.0f);
+  int prev = 0;
+  for (int k = 0; k < n_bins; ++k) {
+    const float* row = fb + (size_t)k * n_bands;
+    int first = -1, last = -1, nnz = 0;
+    for (int b = 0; b < n_bands; ++b)
+      if (row[b] != 0.0f) {              // NaN != 0 too: it has to reach the output, as in the reference's matmul
+        if (first < 0) first = b;
+        last = b;
+        ++nnz;
+      }
+    if (nnz > 2 || (nnz == 2 && last != first + 1)) return 0;
+    if (nnz == 0) {
+      band[k] = prev;
+    } else if (nnz == 2) {
+      band[k] = first;
+      w0[k] = row[first];
+      w1[k] = row[first + 1];
+    } else if (first == prev + 1) {      // continue the running segment: the single weight is its upper band
+      band[k] = prev;
+      w1[k] = row[first];
+    } else {
+      band[k] = first;
+      w0[k] = row[first];
+    }
+    prev = band[k];
+  }
+
+  // ---- per lane: segment mask and the floats it stores --------------------------------------------------
+  // lane l walks bins 32 l .. 32 l + 31 (lane 31: .. 1024).  Bit i: the band steps after local bin i (bit 31:
+  // between bins 1023 and 1024, lane 31 only): u goes to column i of the lane's stash row, then u = v, v = 0.
+  std::vector<std::vector<uint16_t>> lists(n_bands);
+  auto record = [&](int b, int pos, bool used) {
+    if (used && b >= 0 && b < n_bands) lists[b].push_back((uint16_t)pos);
+  };
+  uint32_t mask[32], end_pos[32];
+  int n_stored = 0;
+  for (int l = 0; l < 32; ++l) {
+    mask[l] = 0;
+    end_pos[l] = (l == 31) ? (uint32_t)kStashEnd31 : (uint32_t)(l * kStashStride + 31);
+    const int k_begin = 32 * l, k_end = (l == 31) ? n_bins : 32 * l + 32;     // exclusive
+    bool u_used = false, v_used = false;
+    for (int k = k_begin; k < k_end; ++k) {
+      u_used |= (w0[k] != 0.0f);
+      v_used |= (w1[k] != 0.0f);
+      if (k + 1 == k_end) {
+        record(band[k], (int)end_pos[l], u_used);
+        record(band[k] + 1, (int)end_pos[l] + 1, v_used);
+        n_stored += 2;
+      } else if (band[k + 1] != band[k]) {
+        if (band[k + 1] != band[k] + 1 && v_used) return 0;     // v would be orphaned: not a chain
+        mask[l] |= 1u << (k - k_begin);
+        record(band[k], l * kStashStride + (k - k_begin), u_used);
+        ++n_stored;
+        u_used = (band[k + 1] == band[k] + 1) ? v_used : false;  // u = v carries the upper band's sum on
+        v_used = false;
+      }
+    }
+  }
+  int cmax = 1;
+  for (int b = 0; b < n_bands; ++b)
+    if ((int)lists[b].size() > cmax) cmax = (int)lists[b].size();
+  if (cmax > kBandMaxComb) return 0;
+  const int pad = (n_bands + 31) / 32 * 32;
+
+  BandPlanHeader hdr;
+  memset(&hdr, 0, sizeof(hdr));
+  hdr.magic = kBandPlanMagic;
+  hdr.n_bins = n_bins;
+  hdr.n_bands = n_bands;
+  hdr.n_stored = n_stored;
+  hdr.cmax = cmax;
+  hdr.n_bands_pad = pad;
+  hdr.zero_idx = kStashZero;
+  memcpy(dst, &hdr, sizeof(hdr));
+
+  float* w = reinterpret_cast<float*>(dst + kBandOffW);
+  for (int j = 0; j < 16; ++j)
+    for (int l = 0; l < 32; ++l) {
+      const int k = 32 * l + 2 * j;
+      float* q = w + ((size_t)j * 32 + l) * 4;
+      q[0] = w0[k];
+      q[1] = w1[k];
+      q[2] = w0[k + 1];
+      q[3] = w1[k + 1];
+    }
+  uint32_t* meta = reinterpret_cast<uint32_t*>(dst + kBandOffMeta);
+  for (int l = 0; l < 32; ++l) {
+    meta[4 * l] = mask[l];
+    meta[4 * l + 1] = end_pos[l];
+    float e0 = 0.0f, e1 = 0.0f;
+    if (l == 31) {
+      e0 = w0[n_bins - 1];
+      e1 = w1[n_bins - 1];
+    }
+    memcpy(&meta[4 * l + 2], &e0, 4);
+    memcpy(&meta[4 * l + 3], &e1, 4);
+  }
+  uint16_t* comb = reinterpret_cast<uint16_t*>(dst + kBandOffComb);
+  for (int c = 0; c < cmax; ++c)
+    for (int b = 0; b < pad; ++b)
+      comb[(size_t)c * pad + b] = (b < n_bands && c < (int)lists[b].size()) ? lists[b][c] : (uint16_t)kStashZero;
+  const int64_t used = kBandOffComb + (int64_t)cmax * pad * 2;
+  return (used + 15) & ~(int64_t)15;
+}
+
+}  // namespace tac

@@ -1,0 +1,54 @@
+// Band plan: the form of a filterbank matrix consumed by the fused STFT + filterbank kernel (stft.cu,
+// OUT_MEL_FUSED).  Applies to matrices whose every row (frequency bin) has at most two non-zeros, in
+// adjacent columns -- every triangular filterbank (create_mel_filter, functional.py:131-169) is of that
+// form: bin k feeds band b_k with weight w0[k] and band b_k + 1 with weight w1[k].
+//
+// The kernel has one warp per frame; after the FFT the warp transposes the 1025 power values through a
+// shared-memory stash so that lane l owns the 32 CONSECUTIVE bins 32 l .. 32 l + 31 (lane 31 also bin 1024).
+// The lane walks its bins keeping two running sums (u: band b, v: band b + 1).  Where b steps to b + 1 (bit i
+// of the lane's segment mask: after local bin i) it stores u into its own, already consumed, stash row at
+// column i and carries on with u = v, v = 0; at the end of its run it stores u and v at `end_pos`, `end_pos + 1`.
+// A second step with lane = band sums the few stored floats that belong to a band (list `comb`, fixed order,
+// so the result is deterministic).  The plan exists only when consecutive segments inside a lane's run step
+// from band b to band b + 1 (or the value that would be orphaned is identically zero) -- true for chains of
+// overlapping triangles.
+//
+// Blob layout (all offsets from the start of the band plan, which is 128-byte aligned inside the
+// filterbank plan blob):
+//   BandPlanHeader                                  32 B
+//   w     [16][32] float4   (w0[i], w1[i], w0[i+1], w1[i+1]) of bins 32 l + i, i = 2 j     8192 B
+//   meta  [32]     uint4    (segment mask, end_pos, w0 / w1 of bin 1024 as float bits [lane 31 only])   512 B
+//   comb  [cmax][n_bands_pad] uint16   float index into the stash, padded with zero_idx
+#pragma once
+
+#include <stdint.h>
+
+namespace tac {
+
+constexpr uint32_t kBandPlanMagic = 0x7ac0ba2du;
+constexpr int kBandBins = 1025;                    // n_fft = 2048
+constexpr int kStashStride = 33;                   // stash row stride (floats): odd -> conflict-free both ways
+constexpr int kStashNyquist = 32 * kStashStride;   // where bin 1024 sits
+constexpr int kStashEnd31 = kStashNyquist + 1;     // end-of-run pair of lane 31 (its row's last columns are taken)
+constexpr int kStashZero = 1060;                   // a float that is always 0 (padding entries of `comb`)
+constexpr int kStashFloats = 1064;                 // per warp
+constexpr int kBandMaxComb = 16;
+
+struct BandPlanHeader {
+  uint32_t magic;
+  int32_t n_bins, n_bands, n_stored, cmax, n_bands_pad, zero_idx, reserved;
+};
+constexpr int kBandOffW = 32;
+constexpr int kBandOffMeta = kBandOffW + 16 * 32 * 16;
+constexpr int kBandOffComb = kBandOffMeta + 32 * 16;
+
+static inline int64_t band_plan_capacity(int n_bands) {
+  const int64_t pad = ((int64_t)n_bands + 31) / 32 * 32;
+  return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 128;
+}
+
+// Returns the bytes written at `dst` (multiple of 16), or 0 when the matrix is not of the two-adjacent-bands
+// form (or needs more slots / list entries than the kernel holds).  Host code (bandplan.cu).
+int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char* dst, int64_t capacity);
+
+}  // namespace tac

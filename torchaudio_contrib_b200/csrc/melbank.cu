@@ -21,6 +21,7 @@
 // stages, mbarrier full/ready/empty handshakes, tcgen05.commit releases a stage when its MMAs retired.
 #include <stdlib.h>
 
+#include "bandplan.cuh"
 #include "tac_common.cuh"
 
 namespace tac {
@@ -44,7 +45,8 @@ struct FbPlanHeader {
   uint32_t magic;
   int32_t n_bins, n_bands, n_chunks, n_bblocks;
   int32_t max_n;      // widest block (bands) over all K slices
-  int32_t reserved[2];
+  int32_t band_off;   // byte offset of the band plan (bandplan.cuh) inside this blob, 0: the matrix has no such form
+  int32_t band_cmax;  // its list length (entries per band)
 };
 struct FbPlanChunk {
   int32_t band_lo;    // first band of the block, relative to the band block, multiple of 16
@@ -510,7 +512,8 @@ extern "C" int64_t tac_fbplan_bytes(int n_bins, int n_bands) {
   if (n_bins <= 0 || n_bands <= 0) return 0;
   const int64_t n_chunks = (n_bins + kMbBK - 1) / kMbBK;
   const int64_t n_bblocks = (n_bands + kMbBandBlock - 1) / kMbBandBlock;
-  return 128 + (int64_t)sizeof(FbPlanHeader) + n_chunks * n_bblocks * ((int64_t)sizeof(FbPlanChunk) + 2 * kMbTileBytes);
+  return 128 + (int64_t)sizeof(FbPlanHeader) + n_chunks * n_bblocks * ((int64_t)sizeof(FbPlanChunk) + 2 * kMbTileBytes) +
+         band_plan_capacity(n_bands);
 }
 
 extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, void* plan_host, int64_t capacity,
@@ -576,8 +579,24 @@ extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, v
       off += 2 * (int64_t)n * 128;
     }
   }
+  // the same matrix as a band plan for the fused STFT + filterbank kernel, when it has that form
+  off = (off + 127) & ~(int64_t)127;
+  const int64_t band_bytes = build_band_plan(fb, n_bins, n_bands, base + off, capacity - off);
+  if (band_bytes > 0) {
+    hdr->band_off = (int32_t)off;
+    hdr->band_cmax = reinterpret_cast<const BandPlanHeader*>(base + off)->cmax;
+    off += band_bytes;
+  }
   *used = off;
   return TAC_OK;
+}
+
+extern "C" int64_t tac_fbplan_band_handle(const void* plan_host) {
+  using namespace tac;
+  if (!plan_host) return 0;
+  const FbPlanHeader* hdr = static_cast<const FbPlanHeader*>(plan_host);
+  if (hdr->magic != kPlanMagic || hdr->band_off <= 0) return 0;
+  return (int64_t)hdr->band_off | ((int64_t)hdr->band_cmax << 48);
 }
 
 extern "C" int tac_debug_dump_melbank_trace(void) { return tac::dump_melbank_trace(); }

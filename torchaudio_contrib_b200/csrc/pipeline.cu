@@ -7,6 +7,8 @@
 //                       two streams, so copies in both directions overlap compute.
 #include <stdlib.h>
 
+#include <math.h>
+
 #include "stft_params.cuh"
 #include "tac_common.cuh"
 
@@ -60,7 +62,59 @@ static int run_melspec(StftParams sp, float power, const void* plan_dev, int n_b
   return TAC_OK;
 }
 
+// TAC_MELSPEC_FUSED=0 keeps the host pipeline on the two-kernel path (A/B timing)
+static bool fused_enabled() {
+  const char* e = getenv("TAC_MELSPEC_FUSED");       // read per pipeline creation, not cached
+  return !(e && atoi(e) == 0);
+}
+
+// Fused path: STFT + |.|^p + two-band filterbank [+ dB] in ONE kernel, the spectrum never leaves the SM
+// (stft.cu, OUT_MEL_FUSED).  n_fft = 2048 and a plan that carries a band plan (tac_fbplan_band_handle != 0).
+static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, int64_t band_handle, int n_bands, int to_db,
+                              float ref, float amin, float* out, int frame_major, cudaStream_t stream) {
+  TAC_REQUIRE(sp.n_fft == 2048, TAC_ERR_UNSUPPORTED, "melspec_banded: the fused kernel exists for n_fft = 2048 only (got %d)", sp.n_fft);
+  const int64_t off = band_handle & (((int64_t)1 << 48) - 1);
+  const int cmax = (int)(band_handle >> 48);
+  TAC_REQUIRE(off > 0 && (off & 15) == 0 && cmax >= 1 && cmax <= 16, TAC_ERR_INVALID, "melspec_banded: bad band handle");
+  TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melspec_banded: plan must be 16-byte aligned");
+  if (sp.n_seq * sp.frames == 0) return TAC_OK;
+  sp.out = out;
+  sp.out_mode = OUT_MEL_FUSED;
+  sp.power = power;
+  sp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  sp.band_plan = static_cast<const unsigned char*>(plan_dev) + off;
+  sp.band_cmax = cmax;
+  sp.n_bands = n_bands;
+  sp.n_bands_pad = (n_bands + 31) / 32 * 32;
+  sp.to_db = to_db ? 1 : 0;
+  sp.amin = amin;
+  sp.log10_ref = log10f(ref);
+  if (frame_major) {                     // (n_seq, frames, n_bands): the memory order of the reference's transposed view
+    sp.out_seq_stride = sp.frames * n_bands;
+    sp.out_t_stride = n_bands;
+    sp.out_band_stride = 1;
+  } else {                               // (n_seq, n_bands, frames) contiguous
+    sp.out_seq_stride = (int64_t)n_bands * sp.frames;
+    sp.out_t_stride = 1;
+    sp.out_band_stride = sp.frames;
+  }
+  return launch_stft(sp, stream);
+}
+
 }  // namespace tac
+
+extern "C" int tac_melspec_banded_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
+                                      int n_fft, int hop, int center, int pad_mode, int normalized, float power,
+                                      const void* plan_dev, int64_t band_handle, int n_bands, int to_db, float ref, float amin,
+                                      float* out, int frame_major, void* stream) {
+  using namespace tac;
+  StftParams sp;
+  const int rc = fill_stft_params(sp, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(plan_dev && n_bands > 0, TAC_ERR_INVALID, "melspec_banded: missing filterbank plan");
+  TAC_REQUIRE(out || sp.g1 == 0, TAC_ERR_INVALID, "melspec_banded: null output pointer");
+  return run_melspec_banded(sp, power, plan_dev, band_handle, n_bands, to_db, ref, amin, out, frame_major, as_stream(stream));
+}
 
 extern "C" int64_t tac_melspec_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
   using namespace tac;
@@ -99,6 +153,7 @@ struct tac_pipeline {
   int device;
   float* d_window;
   void* d_plan;
+  int64_t band_handle;                  // non-zero: the one-kernel path applies (n_fft = 2048, two-band matrix)
   cudaStream_t stream[kHostSlots];
   float* d_x[kHostSlots];
   float* d_out[kHostSlots];
@@ -154,6 +209,7 @@ extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* 
     if (rc == TAC_OK) {
       cudaError_t e = cudaMalloc(&p->d_plan, (size_t)used);
       if (e == cudaSuccess) e = cudaMemcpy(p->d_plan, host, (size_t)used, cudaMemcpyHostToDevice);
+      if (cfg->n_fft == 2048 && fused_enabled()) p->band_handle = tac_fbplan_band_handle(host);
       if (e != cudaSuccess) rc = fail(TAC_ERR_CUDA, "pipeline_create: plan upload failed: %s", cudaGetErrorString(e));
     }
     free(host);
@@ -194,7 +250,7 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   if (per > n_seq) per = n_seq;
   const int64_t x_bytes = per * n_samples * 4;
   const int64_t o_bytes = per * out_rows * frames * 4;
-  const int64_t ws_bytes = c.n_bands > 0 ? tac_melspec_workspace_bytes(per, n_samples, c.n_fft, c.hop, c.center) : 0;
+  const int64_t ws_bytes = (c.n_bands > 0 && !p->band_handle) ? tac_melspec_workspace_bytes(per, n_samples, c.n_fft, c.hop, c.center) : 0;
   int rc = pipeline_reserve(p, x_bytes, o_bytes, ws_bytes);
   if (rc != TAC_OK) return rc;
   int slot = 0;
@@ -206,7 +262,9 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
     rc = fill_stft_params(sp, p->d_x[slot], ns, n_samples, n_samples, p->d_window, c.n_fft, c.hop, c.center, c.pad_mode,
                           c.normalized, 1);
     if (rc != TAC_OK) return rc;
-    if (c.n_bands > 0) {
+    if (c.n_bands > 0 && p->band_handle) {
+      rc = run_melspec_banded(sp, c.power, p->d_plan, p->band_handle, c.n_bands, c.to_db, c.ref, c.amin, p->d_out[slot], 0, st);
+    } else if (c.n_bands > 0) {
       rc = run_melspec(sp, c.power, p->d_plan, c.n_bands, c.to_db, c.ref, c.amin, p->d_ws[slot], p->cap_ws, p->d_out[slot], st);
     } else {
       sp.out = p->d_out[slot];

@@ -20,6 +20,7 @@
 // feed the filterbank kernel (melbank.cu) inside the Melspectrogram pipeline.
 #include <stdlib.h>
 
+#include "bandplan.cuh"
 #include "fft_regs.cuh"
 #include "stft_params.cuh"
 #include "tac_common.cuh"
@@ -56,6 +57,9 @@ constexpr int kSlabStride = 34;                              // complex per slab
 constexpr int kSlabComplex = 32 * kSlabStride + 2;           // transposition slab (+2: 16 slabs hold a 1025 x 17 float2 output tile)
 constexpr size_t kFastSmemBytes = 3 * 1024 * sizeof(float2)  // window pairs, tw1, tw2
                                   + kFastWarps * sizeof(uint64_t) + kFastWarps * kSlabComplex * sizeof(float2);
+// OUT_MEL_FUSED: plus one power-spectrum stash per warp (bandplan.cuh) -- 232 320 of the 232 448 bytes a CTA may have
+constexpr size_t kFusedSmemBytes = kFastSmemBytes + kFastWarps * kStashFloats * sizeof(float);
+static_assert(kFusedSmemBytes <= 227 * 1024, "fused STFT + filterbank kernel exceeds the shared memory of one CTA");
 
 // |X|^p with the exponent resolved at compile time (PMODE 2: p = 2, 1: p = 1, 0: runtime p through
 // the hardware lg2 / ex2 units -- ~1e-6 relative, far inside the parity budget)
@@ -122,6 +126,60 @@ __device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_wi
   }
 }
 
+// OUT_MEL_FUSED: the frame's power spectrum (in this warp's stash) times a two-band filterbank (bandplan.cuh),
+// optional dB epilogue (amplitude_to_db, functional.py:291-296), result to global memory.
+// Replaces apply_filterbank's transpose + matmul + transpose (functional.py:183-184) for such matrices.
+__device__ __forceinline__ void band_contract(const StftParams& p, float* stash, int lane, uint32_t seq, uint32_t t) {
+  __syncwarp();                                    // the stash holds the whole frame
+  float pw[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) pw[i] = stash[lane * kStashStride + i];     // lane <- bins 32 lane + i
+  const float p_last = (lane == 31) ? stash[kStashNyquist] : 0.0f;
+  __syncwarp();                                    // stash consumed: it now takes the partial sums
+  const uint4 meta = __ldg(reinterpret_cast<const uint4*>(p.band_plan + kBandOffMeta) + lane);
+  const float4* wtab = reinterpret_cast<const float4*>(p.band_plan + kBandOffW) + lane;
+  const uint32_t mask = meta.x;
+  float* row = stash + lane * kStashStride;        // this lane's own (consumed) row takes what it stores
+  float u = 0.0f, v = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float4 w = __ldg(wtab + j * 32);
+    u = fmaf(pw[2 * j], w.x, u);
+    v = fmaf(pw[2 * j], w.y, v);
+    if (mask & (1u << (2 * j))) {                  // band b -> b + 1
+      row[2 * j] = u;
+      u = v;
+      v = 0.0f;
+    }
+    u = fmaf(pw[2 * j + 1], w.z, u);
+    v = fmaf(pw[2 * j + 1], w.w, v);
+    if (mask & (1u << (2 * j + 1))) {
+      row[2 * j + 1] = u;
+      u = v;
+      v = 0.0f;
+    }
+  }
+  u = fmaf(p_last, __uint_as_float(meta.z), u);    // bin 1024 (weights are zero except on lane 31)
+  v = fmaf(p_last, __uint_as_float(meta.w), v);
+  stash[meta.y] = u;
+  stash[meta.y + 1] = v;
+  __syncwarp();
+  // lane = band: add up the band's slots in list order
+  const uint16_t* comb = reinterpret_cast<const uint16_t*>(p.band_plan + kBandOffComb);
+  float* dst = p.out + (int64_t)seq * p.out_seq_stride + (int64_t)t * p.out_t_stride;
+  for (int m = lane; m < p.n_bands; m += 32) {
+    float acc = 0.0f;
+    for (int c = 0; c < p.band_cmax; ++c) acc += stash[__ldg(comb + c * p.n_bands_pad + m)];
+    if (p.to_db) {
+      float s2 = acc * acc;
+      s2 = (s2 < p.amin) ? p.amin : s2;
+      acc = 10.0f * (log10f(s2) - p.log10_ref);
+    }
+    __stcs(dst + (int64_t)m * p.out_band_stride, acc);
+  }
+  __syncwarp();                                    // slots consumed before the next frame's spectrum lands
+}
+
 // The kernel is specialised on the output mode and the exponent: the frame loop is ~2k fully
 // unrolled instructions and has to stay resident in the instruction caches while 16 warps run
 // through it at different phases (a first version that branched on these at run time was 12k
@@ -158,6 +216,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   const int64_t step = (int64_t)gridDim.x * kFastWarps;
   const float half_power = 0.5f * p.power;
   uint32_t parity = 0;
+  // OUT_MEL_FUSED: this warp's power-spectrum stash, row k1 = bins 32 k1 .. 32 k1 + 31, stride 33
+  float* stash = reinterpret_cast<float*>(s_slab + kFastWarps * kSlabComplex) + warp * kStashFloats;
+  if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+    if (lane == 0) stash[kStashZero] = 0.0f;
+    __syncwarp();
+  }
 
   // (sequence, frame-in-sequence) of this warp's frames advance incrementally: a 64-bit division per frame
   // costs ~100 instructions in the hot loop (it did, twice per frame, in the first version)
@@ -233,6 +297,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     int64_t dst_stride = 0;                        // floats between consecutive k1 (public layouts only)
     if constexpr (OUT_MODE == OUT_POWER_ROWS) {
       dst = p.out + power_tile_index(g - p.g0, lane, p.kpad);      // + k1 * 4096 floats: immediate offsets below
+    } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+      dst = stash + lane;                                          // + k1 * 33 floats
     } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
       dst = p.out + ((int64_t)seq * p.bins + lane) * p.frames + t;
       dst_stride = 32 * p.frames;
@@ -246,6 +312,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
         st_global_hint(dst + k1 * 4096, fast_power<PMODE>(x.x, x.y, half_power), pol_keep);
+      } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+        dst[k1 * kStashStride] = fast_power<PMODE>(x.x, x.y, half_power);
       } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
         *reinterpret_cast<float2*>(dst) = x;
         dst += dst_stride;
@@ -261,12 +329,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       const float nyq = 2.0f * (z0.x - z0.y);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
         st_global_hint(dst + 32 * 4096, (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f, pol_keep);   // slice 32: Nyquist + zero fill
+      } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+        if (lane == 0) stash[kStashNyquist] = fast_power<PMODE>(nyq, 0.0f, half_power);
       } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
         if (lane == 0) *dst = fast_power<PMODE>(nyq, 0.0f, half_power);
       } else {
         if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(nyq, 0.0f);
       }
     }
+    if constexpr (OUT_MODE == OUT_MEL_FUSED) band_contract(p, stash, lane, seq, t);
     K1_TRACE(trace_i); ++trace_i;                  // frame done
     if (has_next && !in_flight) stage_gather(seq_next, t_next);
     seq = seq_next;
@@ -506,11 +577,14 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
       k = p.power_mode == 2 ? stft2048_public_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_public_kernel<OUT_POWER_PUBLIC, 1> : stft2048_public_kernel<OUT_POWER_PUBLIC, 0>);
     else if (p.out_mode == OUT_POWER_PUBLIC)
       k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_PUBLIC, 1> : stft2048_kernel<OUT_POWER_PUBLIC, 0>);
+    else if (p.out_mode == OUT_MEL_FUSED)
+      k = p.power_mode == 2 ? stft2048_kernel<OUT_MEL_FUSED, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_MEL_FUSED, 1> : stft2048_kernel<OUT_MEL_FUSED, 0>);
     else
       k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_ROWS, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_ROWS, 1> : stft2048_kernel<OUT_POWER_ROWS, 0>);
-    TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes));
+    const size_t smem = p.out_mode == OUT_MEL_FUSED ? kFusedSmemBytes : kFastSmemBytes;
+    TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchProbe probe(KIND_STFT, stream);
-    k<<<grid, kFastThreads, kFastSmemBytes, stream>>>(p);
+    k<<<grid, kFastThreads, smem, stream>>>(p);
   } else {
     const size_t smem = generic_smem_bytes(p.n_fft);
     if (smem > 48 * 1024)
@@ -574,6 +648,11 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   static int debug = -1;
   if (debug < 0) debug = getenv("TAC_K1_TRACE") ? 1 : 0;
   p.debug = debug;
+  p.band_plan = nullptr;
+  p.band_cmax = p.n_bands = p.n_bands_pad = p.to_db = 0;
+  p.amin = 0.0f;
+  p.log10_ref = 0.0f;
+  p.out_seq_stride = p.out_t_stride = p.out_band_stride = 0;
   return TAC_OK;
 }
 

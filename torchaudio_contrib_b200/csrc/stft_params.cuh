@@ -9,7 +9,8 @@ namespace tac {
 enum StftOutMode {
   OUT_COMPLEX_PUBLIC = 0,   // (n_seq, bins, frames, 2)   -- reference layout of `stft`
   OUT_POWER_PUBLIC = 1,     // (n_seq, bins, frames)      -- reference layout of `Spectrogram`
-  OUT_POWER_ROWS = 2        // |X|^p in "power tiles": the swizzled tensor-core operand layout (below)
+  OUT_POWER_ROWS = 2,       // |X|^p in "power tiles": the swizzled tensor-core operand layout (below)
+  OUT_MEL_FUSED = 3         // |X|^p contracted with a two-band filterbank inside the kernel (bandplan.cuh) [+ dB]
 };
 
 struct StftParams {
@@ -27,6 +28,12 @@ struct StftParams {
   float power;
   float scale;             // n_fft^-0.5 when normalized, else 1
   int debug;               // TAC_K1_TRACE: clock stamps of CTA 0 / warp 0 (timing experiments only)
+  // OUT_MEL_FUSED only: the band plan and where band m of frame (seq, t) goes:
+  //   out[seq * out_seq_stride + t * out_t_stride + m * out_band_stride]
+  const unsigned char* band_plan;
+  int band_cmax, n_bands, n_bands_pad, to_db;
+  float amin, log10_ref;
+  int64_t out_seq_stride, out_t_stride, out_band_stride;
 };
 
 // Power tiles (OUT_POWER_ROWS): frames are grouped in tiles of 128; for each tile and each 32-bin slice the

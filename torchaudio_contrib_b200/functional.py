@@ -8,6 +8,7 @@ kernels are forward-only; an input that requires grad raises instead of silently
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -16,6 +17,7 @@ from . import _cabi, _mulaw_tables
 __all__ = [
     "stft", "complex_norm", "create_mel_filter", "apply_filterbank", "amplitude_to_db",
     "mu_law_encoding", "mu_law_decoding", "spectrogram", "melspectrogram", "FilterbankPlan",
+    "PreparedMelspectrogram",
 ]
 
 
@@ -195,6 +197,8 @@ class FilterbankPlan(object):
         used = ctypes.c_int64(0)
         _cabi.check(lib.tac_fbplan_build_host(_cabi.ptr(fb), self.num_freqs, self.num_bands, _cabi.ptr(host), cap,
                                               ctypes.byref(used)))
+        # non-zero: the matrix is a chain of two-band rows and the one-kernel path applies (n_fft = 2048)
+        self.band_handle = int(lib.tac_fbplan_band_handle(_cabi.ptr(host)))
         self.blob = host[:used.value].to(device)
         self.device = self.blob.device
         self.key = FilterbankPlan.key_of(filterbank)
@@ -278,11 +282,19 @@ def _workspace(device, nbytes):
 
 def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_length=None, window=None,
                    center=True, pad_mode='reflect', normalized=False, power=2.0,
-                   to_db=False, ref=1.0, amin=1e-7, _cache=None):
+                   to_db=False, ref=1.0, amin=1e-7, layout="contiguous", _cache=None):
     """`Melspectrogram(...)(x)` (layers.py:307-347), optionally with `AmplitudeToDb` appended
-    (layers.py:350-381), as two back-to-back kernels: stft + |.|^power into frame-major rows that
-    stay in L2, then the tensor-core filterbank with the dB clamp in its epilogue.
-    `(*, channel, time) -> (*, channel, num_bands, frames)`."""
+    (layers.py:350-381).  `(*, channel, time) -> (*, channel, num_bands, frames)`.
+
+    `fft_length == 2048` and a filterbank whose rows have at most two adjacent non-zeros (every
+    triangular filterbank): ONE kernel, a warp per frame from its samples to its `num_bands` outputs,
+    the spectrum never leaves the SM (csrc/stft.cu OUT_MEL_FUSED; `TAC_MELSPEC_FUSED=0` disables).
+    Otherwise two back-to-back kernels: stft + |.|^power into frame-major power tiles that stay in
+    L2, then the tensor-core filterbank with the dB clamp in its epilogue.
+
+    `layout="reference"` (one-kernel path only) returns the reference's memory order -- a transposed
+    view of a `(*, frames, num_bands)` buffer, exactly the strides of `apply_filterbank`'s
+    `matmul(...).transpose(-2, -1)` (functional.py:183-184); the default is a contiguous tensor."""
     _forward_only(waveforms, "melspectrogram")
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
@@ -291,16 +303,83 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     if plan.num_freqs != fft_length // 2 + 1:
         raise RuntimeError("melspectrogram: filterbank has %d rows, stft yields %d bins"
                            % (plan.num_freqs, fft_length // 2 + 1))
+    if layout not in ("contiguous", "reference"):
+        raise ValueError("melspectrogram: layout must be 'contiguous' or 'reference', got %r" % (layout,))
     lib = _cabi.lib()
+    frames = max(frames, 0)
+    if plan.band_handle and int(fft_length) == 2048 and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0":
+        frame_major = layout == "reference"
+        shape = (flat.size(0), frames, plan.num_bands) if frame_major else (flat.size(0), plan.num_bands, frames)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.tac_melspec_banded_f32(
+                *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
+                float(power), _cabi.ptr(plan.blob), plan.band_handle, plan.num_bands, int(bool(to_db)), float(ref),
+                float(amin), _cabi.ptr(out), int(frame_major), _cabi.stream_ptr(x.device)))
+        if frame_major:
+            return out.reshape(lead + out.shape[1:]).transpose(-2, -1)
+        return out.reshape(lead + out.shape[1:])
     ws_bytes = int(lib.tac_melspec_workspace_bytes(flat.size(0), flat.size(1), int(fft_length), hop, int(bool(center))))
     ws = _workspace(x.device, ws_bytes)
-    out = torch.empty((flat.size(0), plan.num_bands, max(frames, 0)), dtype=torch.float32, device=x.device)
+    out = torch.empty((flat.size(0), plan.num_bands, frames), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _cabi.check(lib.tac_melspec_f32(
             *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
             float(power), _cabi.ptr(plan.blob), plan.num_bands, int(bool(to_db)), float(ref), float(amin),
             _cabi.ptr(ws), ws.numel(), _cabi.ptr(out), _cabi.stream_ptr(x.device)))
     return out.reshape(lead + out.shape[1:])
+
+
+class PreparedMelspectrogram(object):
+    """The `melspectrogram` call with everything shape-independent resolved once (window on the device,
+    filterbank plan, argument marshalling): `prepared(x, out)` is then a single C-ABI call into a
+    caller-owned output -- what a serving loop or a CUDA-graph capture wants.  `x`: contiguous float32
+    CUDA tensor `(*, channel, time)` of the shape given at construction; `out`: contiguous
+    `(*, channel, num_bands, frames)` (`empty_output()` allocates one)."""
+
+    def __init__(self, shape, device, filterbank, fft_length, hop_length=None, win_length=None, window=None,
+                 center=True, pad_mode='reflect', normalized=False, power=2.0, to_db=False, ref=1.0, amin=1e-7):
+        self.device = torch.device(device)
+        self.shape = tuple(int(d) for d in shape)
+        self.n_samples = self.shape[-1]
+        self.n_seq = 1
+        for d in self.shape[:-1]:
+            self.n_seq *= d
+        lib = _cabi.lib()
+        self.hop = fft_length // 4 if hop_length is None else int(hop_length)
+        self.frames = max(int(lib.tac_stft_num_frames(self.n_samples, int(fft_length), self.hop, int(bool(center)))), 0)
+        self.window = _frame_window(window, win_length, fft_length, self.device)
+        self.plan = _plan_for(filterbank, self.device, None)
+        if self.plan.num_freqs != fft_length // 2 + 1:
+            raise RuntimeError("melspectrogram: filterbank has %d rows, stft yields %d bins"
+                               % (self.plan.num_freqs, fft_length // 2 + 1))
+        if pad_mode not in _cabi.PAD_MODES:
+            raise NotImplementedError("stft: pad_mode=%r" % (pad_mode,))
+        self.out_shape = self.shape[:-1] + (self.plan.num_bands, self.frames)
+        self.fused = bool(self.plan.band_handle) and int(fft_length) == 2048 and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0"
+        head = [self.n_seq, self.n_samples, self.n_samples, _cabi.ptr(self.window), int(fft_length), self.hop,
+                int(bool(center)), _cabi.PAD_MODES[pad_mode], int(bool(normalized)), float(power), _cabi.ptr(self.plan.blob)]
+        tail = [self.plan.num_bands, int(bool(to_db)), float(ref), float(amin)]
+        if self.fused:
+            self._fn, self._head, self._tail = lib.tac_melspec_banded_f32, head + [self.plan.band_handle] + tail, [0]
+            self._ws = None
+        else:
+            nbytes = int(lib.tac_melspec_workspace_bytes(self.n_seq, self.n_samples, int(fft_length), self.hop, int(bool(center))))
+            self._ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            self._fn, self._head, self._tail = lib.tac_melspec_f32, head + tail + [_cabi.ptr(self._ws), self._ws.numel()], []
+
+    def empty_output(self):
+        return torch.empty(self.out_shape, dtype=torch.float32, device=self.device)
+
+    def __call__(self, x, out):
+        if (tuple(x.shape) != self.shape or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device
+                or tuple(out.shape) != self.out_shape or out.dtype != torch.float32 or not out.is_contiguous()
+                or out.device != self.device):
+            raise RuntimeError("PreparedMelspectrogram: expected contiguous float32 x %s and out %s on %s"
+                               % (self.shape, self.out_shape, self.device))
+        _cabi.check(self._fn(_cabi.ptr(x), *self._head, _cabi.ptr(out), *self._tail,
+                             ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

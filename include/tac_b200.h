@@ -66,6 +66,13 @@ int tac_complex_norm_f32(const float* z, int64_t n, float power, float* out, voi
 int tac_amplitude_to_db_f32(const float* x, int64_t n, float ref, float amin, float* out,
                             void* stream);
 
+/* ---- N4: db_to_amplitude (functional.py:299-314): sqrt(10^(x/10 + log10(ref))) -------------- */
+int tac_db_to_amplitude_f32(const float* x, int64_t n, float ref, float* out, void* stream);
+
+/* ---- N4: angle / magphase (functional.py:187-201): z (n, 2) -> phase (n) = atan2(im, re) and,
+ * when mag != NULL, mag (n) = |z|^power in the same pass. */
+int tac_magphase_f32(const float* z, int64_t n, float power, float* mag, float* phase, void* stream);
+
 /* ---- a3: apply_filterbank (functional.py:172-184) on tcgen05 tensor cores ---------------
  * The (n_bins, n_bands) row-major matrix is first turned into a "plan": per 32-bin K slice
  * the range of non-zero bands, plus the tf32 hi/lo split of that block laid out as the

@@ -41,6 +41,11 @@ def kernel_model(blob, handle, power_rows, n_bands):
     w = bp[OFF_W:OFF_W + 8192].view(np.float32).reshape(16, 32, 4)
     meta = bp[OFF_META:OFF_META + 512].view(np.uint32).reshape(32, 4)
     comb = bp[OFF_COMB:OFF_COMB + cmax * pad * 2].view(np.uint16).reshape(cmax, pad)
+    fast_off = int(hdr[7])
+    assert (fast_off != 0) == (n_bands <= 128 and cmax <= 4)
+    if fast_off:
+        assert fast_off == (OFF_COMB + cmax * pad * 2 + 15) // 16 * 16          # where pipeline.cu expects it
+        fast = bp[fast_off:fast_off + 2048].view(np.uint32).reshape(32, 4, 4)
     out = np.zeros((power_rows.shape[0], n_bands), dtype=np.float32)
     for f, p in enumerate(power_rows.astype(np.float32)):
         stash = np.full(FLOATS, np.nan, dtype=np.float32)
@@ -72,6 +77,14 @@ def kernel_model(blob, handle, power_rows, n_bands):
             for c in range(cmax):
                 acc = np.float32(acc + stash[comb[c, m]])
             out[f, m] = acc
+            if fast_off:                                       # the per-lane 4 x 4 form must give the same sum
+                e = fast[m % 32, m // 32]
+                assert (e % 4 == 0).all()
+                a, b, c, d = (stash[i // 4] for i in e)
+                assert np.float32(np.float32(np.float32(a + b) + c) + d) == acc
+        if fast_off:
+            for m in range(n_bands, 128):
+                assert (fast[m % 32, m // 32] == ZERO * 4).all()
     return out
 
 

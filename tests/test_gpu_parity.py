@@ -441,3 +441,15 @@ def test_host_pipeline_mel_fused_and_pair(tac, monkeypatch):
     monkeypatch.setenv("TAC_MELSPEC_FUSED", "0")
     hp2 = tac.HostPipeline(2048, 512, power=2.0, filterbank=fb)
     assert pure_rel_err(hp2(g["x"]), g["out"]) < REL
+
+
+@pytest.mark.parametrize("num_mels,sr", [(40, 16000), (80, 44100), (24, 8000)])
+def test_fused_mel_few_wide_bands(tac, oc, num_mels, sr):
+    """few, wide triangles: a band collects partial sums of more than four lanes -> the general list walk of
+    band_contract instead of its 4 x 4 fast form"""
+    torch.manual_seed(61)
+    x = torch.randn(2, 1, 30000)
+    m = _mel_chain(tac, sr=sr, num_mels=num_mels, hop_length=512)
+    got = m(dev(x)).cpu()
+    want = oc.melspectrogram(x, num_mels, sr, fft_length=2048, hop_length=512)
+    assert got.shape == want.shape and pure_rel_err(got, want) < REL

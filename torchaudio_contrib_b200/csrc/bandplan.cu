@@ -117,8 +117,23 @@ int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char*
   for (int c = 0; c < cmax; ++c)
     for (int b = 0; b < pad; ++b)
       comb[(size_t)c * pad + b] = (b < n_bands && c < (int)lists[b].size()) ? lists[b][c] : (uint16_t)kStashZero;
-  const int64_t used = kBandOffComb + (int64_t)cmax * pad * 2;
-  return (used + 15) & ~(int64_t)15;
+  int64_t used = kBandOffComb + (int64_t)cmax * pad * 2;
+  used = (used + 15) & ~(int64_t)15;
+  // fast form: lane l sums bands l, l + 32, l + 64, l + 96, four entries each, as byte offsets into the stash
+  if (n_bands <= 128 && cmax <= 4) {
+    uint32_t* fastp = reinterpret_cast<uint32_t*>(dst + used);
+    for (int l = 0; l < 32; ++l)
+      for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < 4; ++c) {
+          const int b = l + 32 * j;
+          const int idx = (b < n_bands && c < (int)lists[b].size()) ? lists[b][c] : kStashZero;
+          fastp[(l * 4 + j) * 4 + c] = (uint32_t)idx * 4u;
+        }
+    hdr.reserved = (int32_t)used;
+    memcpy(dst, &hdr, sizeof(hdr));
+    used += 32 * 16 * 4;
+  }
+  return used;
 }
 
 }  // namespace tac

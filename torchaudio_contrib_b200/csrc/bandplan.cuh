@@ -19,6 +19,8 @@
 //   w     [16][32] float4   (w0[i], w1[i], w0[i+1], w1[i+1]) of bins 32 l + i, i = 2 j     8192 B
 //   meta  [32]     uint4    (segment mask, end_pos, w0 / w1 of bin 1024 as float bits [lane 31 only])   512 B
 //   comb  [cmax][n_bands_pad] uint16   float index into the stash, padded with zero_idx
+//   fast  [32][4][4] uint32  (header.fast_off != 0: <= 128 bands, cmax <= 4) byte offsets into the stash of the
+//                            entries of bands l, l + 32, l + 64, l + 96 for lane l
 #pragma once
 
 #include <stdint.h>
@@ -36,7 +38,7 @@ constexpr int kBandMaxComb = 16;
 
 struct BandPlanHeader {
   uint32_t magic;
-  int32_t n_bins, n_bands, n_stored, cmax, n_bands_pad, zero_idx, reserved;
+  int32_t n_bins, n_bands, n_stored, cmax, n_bands_pad, zero_idx, reserved;   // reserved = fast_off
 };
 constexpr int kBandOffW = 32;
 constexpr int kBandOffMeta = kBandOffW + 16 * 32 * 16;
@@ -44,7 +46,7 @@ constexpr int kBandOffComb = kBandOffMeta + 32 * 16;
 
 static inline int64_t band_plan_capacity(int n_bands) {
   const int64_t pad = ((int64_t)n_bands + 31) / 32 * 32;
-  return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 128;
+  return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 32 * 16 * 4 + 128;
 }
 
 // Returns the bytes written at `dst` (multiple of 16), or 0 when the matrix is not of the two-adjacent-bands

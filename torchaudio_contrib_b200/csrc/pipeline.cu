@@ -9,6 +9,7 @@
 
 #include <math.h>
 
+#include "bandplan.cuh"
 #include "stft_params.cuh"
 #include "tac_common.cuh"
 
@@ -86,6 +87,8 @@ static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, 
   sp.band_cmax = cmax;
   sp.n_bands = n_bands;
   sp.n_bands_pad = (n_bands + 31) / 32 * 32;
+  sp.band_fast = (n_bands <= 128 && cmax <= 4) ? 1 : 0;             // the per-lane 4 x 4 list form follows `comb`
+  sp.band_off_fast = (kBandOffComb + cmax * sp.n_bands_pad * 2 + 15) & ~15;
   sp.to_db = to_db ? 1 : 0;
   sp.amin = amin;
   sp.log10_ref = log10f(ref);

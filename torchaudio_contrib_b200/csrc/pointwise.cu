@@ -4,8 +4,11 @@
 //
 //   complex_norm     functional.py:116-128   (n, 2) -> (n):  sqrt(re^2 + im^2), then .pow(power)
 //   amplitude_to_db  functional.py:277-296   10 * (log10(max(x^2, amin)) - log10(ref))
+//   db_to_amplitude  functional.py:299-314   sqrt(10^(x / 10 + log10(ref)))
+//   angle            functional.py:187-191   (n, 2) -> (n):  atan2(im, re)
+//   magphase         functional.py:194-201   (n, 2) -> (n), (n):  complex_norm and angle in one pass
 //
-// Pure streaming: 12 B / element (complex_norm) and 8 B / element (amplitude_to_db).
+// Pure streaming: 12 B / element (complex_norm, angle), 16 (magphase), 8 (amplitude_to_db, db_to_amplitude).
 #include "tac_common.cuh"
 
 namespace tac {
@@ -79,6 +82,62 @@ amplitude_to_db_kernel(const float* __restrict__ x, int64_t n, float amin, float
   }
 }
 
+// functional.py:310-314: torch.pow(10.0, x / 10.0 + log10(ref)) then .pow(0.5)
+__device__ __forceinline__ float from_db(float x, float log10_ref) {
+  return sqrtf(powf(10.0f, x / 10.0f + log10_ref));
+}
+
+__global__ void __launch_bounds__(kPwThreads)
+db_to_amplitude_kernel(const float* __restrict__ x, int64_t n, float log10_ref, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kPwThreads;
+  const int64_t n4 = n >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n4; i += stride) {
+      const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
+      float4 r;
+      r.x = from_db(v.x, log10_ref);
+      r.y = from_db(v.y, log10_ref);
+      r.z = from_db(v.z, log10_ref);
+      r.w = from_db(v.w, log10_ref);
+      __stcs(reinterpret_cast<float4*>(out) + i, r);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride)
+      out[i] = from_db(x[i], log10_ref);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride) out[i] = from_db(x[i], log10_ref);
+  }
+}
+
+// angle (mag == nullptr) or magphase: one read of z, one or two coalesced writes
+__global__ void __launch_bounds__(kPwThreads)
+magphase_kernel(const float2* __restrict__ z, int64_t n, float power, int mode, float* __restrict__ mag,
+                float* __restrict__ phase) {
+  const int64_t stride = (int64_t)gridDim.x * kPwThreads;
+  const int64_t n2 = n >> 1;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(z) & 15) == 0) && ((reinterpret_cast<uintptr_t>(phase) & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(mag) & 7) == 0);
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n2; i += stride) {
+      const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(z) + i);
+      __stcs(reinterpret_cast<float2*>(phase) + i, make_float2(atan2f(v.y, v.x), atan2f(v.w, v.z)));
+      if (mag) __stcs(reinterpret_cast<float2*>(mag) + i,
+                      make_float2(norm_then_pow(v.x, v.y, power, mode), norm_then_pow(v.z, v.w, power, mode)));
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const float2 v = z[n - 1];
+      phase[n - 1] = atan2f(v.y, v.x);
+      if (mag) mag[n - 1] = norm_then_pow(v.x, v.y, power, mode);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride) {
+      const float2 v = z[i];
+      phase[i] = atan2f(v.y, v.x);
+      if (mag) mag[i] = norm_then_pow(v.x, v.y, power, mode);
+    }
+  }
+}
+
 static int pw_grid(int64_t n_vec) {
   const int64_t want = (n_vec + kPwThreads - 1) / kPwThreads;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -106,6 +165,29 @@ extern "C" int tac_amplitude_to_db_f32(const float* x, int64_t n, float ref, flo
   TAC_REQUIRE(x && out, TAC_ERR_INVALID, "amplitude_to_db: null pointer");
   LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
   amplitude_to_db_kernel<<<pw_grid((n + 3) / 4), kPwThreads, 0, as_stream(stream)>>>(x, n, amin, log10f(ref), out);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_db_to_amplitude_f32(const float* x, int64_t n, float ref, float* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "db_to_amplitude: n=%lld", (long long)n);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(x && out, TAC_ERR_INVALID, "db_to_amplitude: null pointer");
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
+  db_to_amplitude_kernel<<<pw_grid((n + 3) / 4), kPwThreads, 0, as_stream(stream)>>>(x, n, log10f(ref), out);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_magphase_f32(const float* z, int64_t n, float power, float* mag, float* phase, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0, TAC_ERR_INVALID, "magphase: n=%lld", (long long)n);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(z && phase, TAC_ERR_INVALID, "magphase: null pointer");
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
+  magphase_kernel<<<pw_grid((n + 1) / 2), kPwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(z), n, power,
+                                                                              power_mode(power), mag, phase);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
 }

@@ -100,15 +100,26 @@ __device__ __forceinline__ void fft2048_front(float2 (&v)[32], float2* slab, con
 // Real-FFT untangling of bin k = 32 K1 + lane from v[bit_reverse(k1)] = Z[32 k1 + lane] / 2: pairs with bin
 // 1024 - k, held by lane (32 - lane) % 32 in register 31 - K1 (lane 0 pairs with itself, register (32 - K1) % 32).
 template <int K1>
-__device__ __forceinline__ float2 fft2048_untangle(const float2 (&v)[32], const float2* s_tw2, int lane, int partner) {
+__device__ __forceinline__ float2 fft2048_untangle(const float2 (&v)[32], const float2 w, int lane, int partner) {
   const float2 z = v[bit_reverse<32>(K1)];
   float2 q;
   q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - K1)].x, partner);
   q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - K1)].y, partner);
   if (lane == 0) q = v[bit_reverse<32>((32 - K1) & 31)];
   const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
-  const float2 w = s_tw2[((K1 >> 1) * 32 + lane) * 2 + (K1 & 1)];        // (c, d), W = c + i d
   return make_float2(fmaf(w.x, gs, fmaf(-w.y, h, a)), fmaf(w.x, h, fmaf(w.y, gs, b)));
+}
+
+// W_2048^(32 K1 + lane) = (c, d): the table is pair-interleaved, so even K1 fetch (K1, K1 + 1) with one LDS.128 into
+// `pair` and odd K1 take its second half (two LDS.64 16 bytes apart cost two wavefronts each)
+template <int K1>
+__device__ __forceinline__ float2 fft2048_tw2(const float2* s_tw2, int lane, float4& pair) {
+  if constexpr ((K1 & 1) == 0) {
+    pair = reinterpret_cast<const float4*>(s_tw2)[(K1 >> 1) * 32 + lane];
+    return make_float2(pair.x, pair.y);
+  } else {
+    return make_float2(pair.z, pair.w);
+  }
 }
 
 // table set-up shared by both kernels: pair-interleaved [j / 2][lane][j % 2] so one LDS.128 serves two registers
@@ -131,6 +142,15 @@ __device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_wi
 // Replaces apply_filterbank's transpose + matmul + transpose (functional.py:183-184) for such matrices.
 __device__ __forceinline__ void band_contract(const StftParams& p, float* stash, int lane, uint32_t seq, uint32_t t) {
   __syncwarp();                                    // the stash holds the whole frame
+  // per-band lists of this lane's four bands (fast form: <= 128 bands, <= 4 entries each), fetched now so the
+  // loads are long done when the sums are needed (a dependent index -> shared -> add chain per band cost 16 % of
+  // the kernel's stall samples in the first version)
+  uint4 ci[4];
+  const bool fast = p.band_fast != 0;
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ci[j] = __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j);
+  }
   float pw[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) pw[i] = stash[lane * kStashStride + i];     // lane <- bins 32 lane + i
@@ -167,6 +187,29 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
   // lane = band: add up the band's slots in list order
   const uint16_t* comb = reinterpret_cast<const uint16_t*>(p.band_plan + kBandOffComb);
   float* dst = p.out + (int64_t)seq * p.out_seq_stride + (int64_t)t * p.out_t_stride;
+  if (fast) {
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(stash);
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                  // byte offsets into the stash; unused entries point at the zero
+      const float a = *reinterpret_cast<const float*>(sb + ci[j].x), b = *reinterpret_cast<const float*>(sb + ci[j].y);
+      const float c = *reinterpret_cast<const float*>(sb + ci[j].z), d = *reinterpret_cast<const float*>(sb + ci[j].w);
+      acc[j] = ((a + b) + c) + d;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r = acc[j];
+      if (p.to_db) {
+        float s2 = r * r;
+        s2 = (s2 < p.amin) ? p.amin : s2;
+        r = 10.0f * (log10f(s2) - p.log10_ref);
+      }
+      const int m = lane + 32 * j;
+      if (m < p.n_bands) __stcs(dst + (int64_t)m * p.out_band_stride, r);
+    }
+    __syncwarp();
+    return;
+  }
   for (int m = lane; m < p.n_bands; m += 32) {
     float acc = 0.0f;
     for (int c = 0; c < p.band_cmax; ++c) acc += stash[__ldg(comb + c * p.n_bands_pad + m)];
@@ -307,9 +350,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       dst_stride = 64 * p.frames;
     }
     const int partner = (32 - lane) & 31;
+    float4 tw2_pair;
     auto emit = [&](auto k1c) {
       constexpr int k1 = decltype(k1c)::value;
-      const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
+      const float2 x = fft2048_untangle<k1>(v, fft2048_tw2<k1>(s_tw2, lane, tw2_pair), lane, partner);
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
         st_global_hint(dst + k1 * 4096, fast_power<PMODE>(x.x, x.y, half_power), pol_keep);
       } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
@@ -411,9 +455,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_public_kernel(const 
     __syncthreads();                                        // every slab is free: together they hold the output tile
 
     if (active) {
+      float4 tw2_pair;
       auto stash = [&](auto k1c) {
         constexpr int k1 = decltype(k1c)::value;
-        const float2 x = fft2048_untangle<k1>(v, s_tw2, lane, partner);
+        const float2 x = fft2048_untangle<k1>(v, fft2048_tw2<k1>(s_tw2, lane, tw2_pair), lane, partner);
         const int idx = (32 * k1 + lane) * kRow + warp;
         if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) s_slab[idx] = x;
         else reinterpret_cast<float*>(s_slab)[idx] = fast_power<PMODE>(x.x, x.y, half_power);
@@ -650,6 +695,7 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.debug = debug;
   p.band_plan = nullptr;
   p.band_cmax = p.n_bands = p.n_bands_pad = p.to_db = 0;
+  p.band_fast = p.band_off_fast = 0;
   p.amin = 0.0f;
   p.log10_ref = 0.0f;
   p.out_seq_stride = p.out_t_stride = p.out_band_stride = 0;

@@ -32,6 +32,7 @@ struct StftParams {
   //   out[seq * out_seq_stride + t * out_t_stride + m * out_band_stride]
   const unsigned char* band_plan;
   int band_cmax, n_bands, n_bands_pad, to_db;
+  int band_fast, band_off_fast;   // per-lane 4 x 4 list form present (<= 128 bands, <= 4 entries), its byte offset
   float amin, log10_ref;
   int64_t out_seq_stride, out_t_stride, out_band_stride;
 };

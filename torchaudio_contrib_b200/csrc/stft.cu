@@ -351,22 +351,47 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     }
     const int partner = (32 - lane) & 31;
     float4 tw2_pair;
-    auto emit = [&](auto k1c) {
-      constexpr int k1 = decltype(k1c)::value;
-      const float2 x = fft2048_untangle<k1>(v, fft2048_tw2<k1>(s_tw2, lane, tw2_pair), lane, partner);
-      if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-        st_global_hint(dst + k1 * 4096, fast_power<PMODE>(x.x, x.y, half_power), pol_keep);
-      } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
-        dst[k1 * kStashStride] = fast_power<PMODE>(x.x, x.y, half_power);
-      } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
-        *reinterpret_cast<float2*>(dst) = x;
-        dst += dst_stride;
-      } else {
-        *dst = fast_power<PMODE>(x.x, x.y, half_power);
-        dst += dst_stride;
-      }
-    };
-    static_for<32>(emit);
+    if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+      // Only |X|^p is needed, so bins k and 1024 - k are produced together from the pair (Z[k], Z[1024 - k]) that
+      // one shuffle exchange brings together: with E = (a, b), T = W^k O,  X[k] = E + T and X[1024 - k] = conj(E - T).
+      // Steps k1 = 0 .. 15 cover every bin but 512 (its own mirror): half the shuffles, 10.5 instead of 15
+      // instructions per bin.  The mirror of bin 32 k1 + lane sits in stash row 31 - k1, column 32 - lane
+      // (lane 0: row 32 - k1, column 0, i.e. 33 floats after the row start; k1 = 0 gives the Nyquist slot).
+      float* dmir = stash + (lane == 0 ? kStashStride : 32 - lane);
+      auto emit2 = [&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        const float2 w = fft2048_tw2<k1>(s_tw2, lane, tw2_pair);
+        const float2 z = v[bit_reverse<32>(k1)];
+        float2 q;
+        q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].x, partner);
+        q.y = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].y, partner);
+        if (lane == 0) q = v[bit_reverse<32>((32 - k1) & 31)];
+        const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+        const float tr = fmaf(w.x, gs, -w.y * h), ti = fmaf(w.x, h, w.y * gs);
+        dst[k1 * kStashStride] = fast_power<PMODE>(a + tr, b + ti, half_power);
+        dmir[(31 - k1) * kStashStride] = fast_power<PMODE>(a - tr, b - ti, half_power);
+      };
+      static_for<16>(emit2);
+      const float2 x512 = fft2048_untangle<16>(v, fft2048_tw2<16>(s_tw2, lane, tw2_pair), lane, partner);
+      if (lane == 0) dst[16 * kStashStride] = fast_power<PMODE>(x512.x, x512.y, half_power);
+    } else {
+      auto emit = [&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        const float2 x = fft2048_untangle<k1>(v, fft2048_tw2<k1>(s_tw2, lane, tw2_pair), lane, partner);
+        if constexpr (OUT_MODE == OUT_POWER_ROWS) {
+          st_global_hint(dst + k1 * 4096, fast_power<PMODE>(x.x, x.y, half_power), pol_keep);
+        } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
+          dst[k1 * kStashStride] = fast_power<PMODE>(x.x, x.y, half_power);
+        } else if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) {
+          *reinterpret_cast<float2*>(dst) = x;
+          dst += dst_stride;
+        } else {
+          *dst = fast_power<PMODE>(x.x, x.y, half_power);
+          dst += dst_stride;
+        }
+      };
+      static_for<32>(emit);
+    }
     // Nyquist bin (and zero fill of the row padding in frame-major mode); dst now points at bin 1024 + lane
     {
       const float2 z0 = v[0];
@@ -374,7 +399,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       if constexpr (OUT_MODE == OUT_POWER_ROWS) {
         st_global_hint(dst + 32 * 4096, (lane == 0) ? fast_power<PMODE>(nyq, 0.0f, half_power) : 0.0f, pol_keep);   // slice 32: Nyquist + zero fill
       } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
-        if (lane == 0) stash[kStashNyquist] = fast_power<PMODE>(nyq, 0.0f, half_power);
+        (void)nyq;                                   // bin 1024 came out of step k1 = 0 as the mirror of bin 0
       } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
         if (lane == 0) *dst = fast_power<PMODE>(nyq, 0.0f, half_power);
       } else {

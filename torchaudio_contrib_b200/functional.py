@@ -338,7 +338,8 @@ class PreparedMelspectrogram(object):
     `(*, channel, num_bands, frames)` (`empty_output()` allocates one)."""
 
     def __init__(self, shape, device, filterbank, fft_length, hop_length=None, win_length=None, window=None,
-                 center=True, pad_mode='reflect', normalized=False, power=2.0, to_db=False, ref=1.0, amin=1e-7):
+                 center=True, pad_mode='reflect', normalized=False, power=2.0, to_db=False, ref=1.0, amin=1e-7,
+                 layout="contiguous"):
         self.device = torch.device(device)
         self.shape = tuple(int(d) for d in shape)
         self.n_samples = self.shape[-1]
@@ -355,13 +356,17 @@ class PreparedMelspectrogram(object):
                                % (self.plan.num_freqs, fft_length // 2 + 1))
         if pad_mode not in _cabi.PAD_MODES:
             raise NotImplementedError("stft: pad_mode=%r" % (pad_mode,))
-        self.out_shape = self.shape[:-1] + (self.plan.num_bands, self.frames)
         self.fused = bool(self.plan.band_handle) and int(fft_length) == 2048 and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0"
+        if layout not in ("contiguous", "reference"):
+            raise ValueError("layout must be 'contiguous' or 'reference', got %r" % (layout,))
+        self.frame_major = layout == "reference" and self.fused     # `out` is then (*, frames, num_bands); view it transposed
+        self.out_shape = self.shape[:-1] + ((self.frames, self.plan.num_bands) if self.frame_major
+                                            else (self.plan.num_bands, self.frames))
         head = [self.n_seq, self.n_samples, self.n_samples, _cabi.ptr(self.window), int(fft_length), self.hop,
                 int(bool(center)), _cabi.PAD_MODES[pad_mode], int(bool(normalized)), float(power), _cabi.ptr(self.plan.blob)]
         tail = [self.plan.num_bands, int(bool(to_db)), float(ref), float(amin)]
         if self.fused:
-            self._fn, self._head, self._tail = lib.tac_melspec_banded_f32, head + [self.plan.band_handle] + tail, [0]
+            self._fn, self._head, self._tail = lib.tac_melspec_banded_f32, head + [self.plan.band_handle] + tail, [int(self.frame_major)]
             self._ws = None
         else:
             nbytes = int(lib.tac_melspec_workspace_bytes(self.n_seq, self.n_samples, int(fft_length), self.hop, int(bool(center))))

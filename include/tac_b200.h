@@ -73,6 +73,19 @@ int tac_db_to_amplitude_f32(const float* x, int64_t n, float ref, float* out, vo
  * when mag != NULL, mag (n) = |z|^power in the same pass. */
 int tac_magphase_f32(const float* z, int64_t n, float power, float* mag, float* phase, void* stream);
 
+/* ---- N2: phase_vocoder (functional.py:204-274) ---------------------------------------------
+ * spec: (n_seq, n_bins, n_in, 2); out: (n_seq, n_bins, n_out, 2), n_out = ceil(n_in / rate).
+ * idx0[j] = long(j*rate), idx1[j] = long(j*rate + 1), alpha[j] = frac(j*rate) for j < n_out are device
+ * tables the caller builds with the reference's own expressions (:239-243, :250-253); an index >= n_in
+ * reads the zero padding (:247-248).  advance: (n_bins) expected phase advance per bin.
+ * Angles, the wrap, the running phase sum and sin/cos are evaluated in float64 in both variants. */
+int tac_phase_vocoder_f32(const float* spec, int64_t n_seq, int n_bins, int64_t n_in,
+                          const int32_t* idx0, const int32_t* idx1, const double* alpha,
+                          const float* advance, int64_t n_out, float* out, void* stream);
+int tac_phase_vocoder_f64(const double* spec, int64_t n_seq, int n_bins, int64_t n_in,
+                          const int32_t* idx0, const int32_t* idx1, const double* alpha,
+                          const double* advance, int64_t n_out, double* out, void* stream);
+
 /* ---- a3: apply_filterbank (functional.py:172-184) on tcgen05 tensor cores ---------------
  * The (n_bins, n_bands) row-major matrix is first turned into a "plan": per 32-bin K slice
  * the range of non-zero bands, plus the tf32 hi/lo split of that block laid out as the

@@ -61,3 +61,26 @@ def melspectrogram(x, fb, n_fft, hop, power=2.0, **kw):
     """|stft|^power contracted with a (bins, bands) matrix -> (..., bands, frames)."""
     p = np.abs(stft(x, n_fft, hop, **kw)) ** power
     return np.einsum('...ft,fm->...mt', p, np.asarray(fb, dtype=np.float64))
+
+
+def phase_vocoder(d, rate, hop):
+    """librosa.phase_vocoder(D, rate, hop_length) as published with librosa 0.6 / 0.7 (the oracle of the
+    reference's tests/test_functional.py:100-112; librosa itself is not installable here): a sequential walk
+    over the output steps with a running phase -- an independent formulation of what the reference computes
+    with gathers and a cumsum.  d: complex128 (bins, frames) -> complex128 (bins, ceil(frames / rate))."""
+    d = np.asarray(d, dtype=np.complex128)
+    bins, frames = d.shape
+    steps = np.arange(0, frames, rate, dtype=np.float64)
+    out = np.zeros((bins, len(steps)), dtype=np.complex128)
+    expected = np.linspace(0, np.pi * hop, bins)
+    running = np.angle(d[:, 0])
+    d = np.pad(d, [(0, 0), (0, 2)], mode='constant')
+    for t, step in enumerate(steps):
+        cols = d[:, int(step):int(step + 2)]
+        frac = np.mod(step, 1.0)
+        mag = (1.0 - frac) * np.abs(cols[:, 0]) + frac * np.abs(cols[:, 1])
+        out[:, t] = mag * np.exp(1.0j * running)
+        dphase = np.angle(cols[:, 1]) - np.angle(cols[:, 0]) - expected
+        dphase = dphase - 2.0 * np.pi * np.round(dphase / (2.0 * np.pi))
+        running = running + expected + dphase
+    return out

@@ -61,10 +61,64 @@ def _save(name, **arrays):
     print("wrote", name, {k: tuple(np.shape(v)) for k, v in arrays.items()})
 
 
+def widen(ref, oc):
+    """Fixtures of the rows SURVEY 8(f) marks "next": N2 phase_vocoder / TimeStretch, N4 db_to_amplitude,
+    angle, magphase.  Own seed, own files: `python oracle/gen_golden.py widen` leaves the others untouched."""
+    g = torch.Generator().manual_seed(20261017)
+
+    def randn(*shape, dtype=torch.float32):
+        return torch.randn(*shape, generator=g, dtype=dtype)
+
+    # ---- angle / magphase / db_to_amplitude -------------------------------------------------
+    z = randn(3, 129, 40, 2)
+    z[0, 0, 0] = torch.tensor([0.0, 0.0])
+    z[0, 0, 1] = torch.tensor([-1.0, 0.0])
+    z[0, 0, 2] = torch.tensor([-1.0, -0.0])
+    ang = ref.angle(z)
+    _same(ang, oc.angle(z), "angle")
+    mag, ph = ref.magphase(z, 2.0)
+    m2, p2 = oc.magphase(z, 2.0)
+    _same(mag, m2, "magphase mag")
+    _same(ph, p2, "magphase phase")
+    db = torch.cat([torch.tensor([-60.0, -40.0, -10.0, 0.0, 10.0, 60.0]), randn(500) * 30])
+    amp = ref.db_to_amplitude(db, ref=1.0)
+    _same(amp, oc.db_to_amplitude(db, 1.0), "db_to_amplitude")
+    amp3 = ref.db_to_amplitude(db, ref=3.0)
+    _same(amp3, oc.db_to_amplitude(db, 3.0), "db_to_amplitude ref 3")
+    _save("pointwise_next.npz", z=z.numpy(), angle=ang.numpy(), mag_p2=mag.numpy(), db=db.numpy(), amp_ref1=amp.numpy(),
+          amp_ref3=amp3.numpy())
+
+    # ---- phase vocoder: the reference in float64 (its own test's precision) and in float32 -----
+    hop, bins, frames = 256, 65, 90
+    spec32 = randn(2, 2, bins, frames, 2)
+    blob = {"spec": spec32.numpy(), "hop": np.int64(hop)}
+    for rate in (0.5, 1.01, 1.3, 2.0):
+        prior = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)                 # as tests/test_functional.py:76-93 does
+        try:
+            spec64 = spec32.double()
+            adv64 = torch.linspace(0, np.pi * hop, bins)[..., None]
+            y64 = ref.phase_vocoder(spec64, rate, adv64)
+            _same(y64, oc.phase_vocoder(spec64, rate, adv64), "phase_vocoder f64 rate %g" % rate)
+        finally:
+            torch.set_default_dtype(prior)
+        adv32 = torch.linspace(0, np.pi * hop, bins)[..., None]
+        y32 = ref.phase_vocoder(spec32, rate, adv32)
+        _same(y32, oc.phase_vocoder(spec32, rate, adv32), "phase_vocoder f32 rate %g" % rate)
+        tag = ("%g" % rate).replace(".", "p")
+        blob["out64_" + tag] = y64.numpy()
+        blob["out32_" + tag] = y32.numpy()
+    _save("phase_vocoder.npz", **blob)
+    print("widening fixtures reproduce under oracle.ref_chain")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
     ref = _load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "widen":
+        widen(ref, oc)
+        return
     g = torch.Generator().manual_seed(20260925)
 
     def randn(*shape):
@@ -184,6 +238,7 @@ def main():
     _save("mulaw.npz", x=xs.numpy(), enc256=enc.numpy(), dec256=dec.numpy(), roundtrip256=rt.numpy(),
           enc64=enc64.numpy(), dec64=dec64.numpy())
     print("all fixtures reproduce under oracle.ref_chain")
+    widen(ref, oc)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,7 @@ __all__ = [
     "stft", "complex_norm", "hertz_to_mel", "mel_to_hertz", "create_mel_filter",
     "apply_filterbank", "amplitude_to_db", "mu_law_encoding", "mu_law_decoding",
     "spectrogram", "melspectrogram", "mel_filterbank_for",
+    "angle", "magphase", "db_to_amplitude", "phase_vocoder",
 ]
 
 _SLANEY_HZ_PER_MEL = 200.0 / 3          # linear region slope   (functional.py:15,37)
@@ -141,3 +142,42 @@ def melspectrogram(x, num_mels=128, sample_rate=22050, min_freq=0.0, max_freq=No
     p = spectrogram(x, power=2., **stft_kwargs)
     mel = apply_filterbank(p, fb)
     return amplitude_to_db(mel, ref, amin) if to_db else mel
+
+
+def angle(complex_tensor):
+    """functional.py:187-191."""
+    return torch.atan2(complex_tensor[..., 1], complex_tensor[..., 0])
+
+
+def magphase(complex_tensor, power=1.):
+    """functional.py:194-201."""
+    return complex_norm(complex_tensor, power), angle(complex_tensor)
+
+
+def db_to_amplitude(x, ref=1.0):
+    """functional.py:299-314: 10 ** (x / 10 + log10(ref)), then the square root."""
+    ref_t = torch.tensor(ref, device=x.device, requires_grad=False, dtype=x.dtype)
+    return torch.pow(10.0, x / 10.0 + torch.log10(ref_t)).pow(0.5)
+
+
+def phase_vocoder(complex_specgrams, rate, phase_advance):
+    """functional.py:204-274, dtype-generic like the reference (its value test runs it in float64 with
+    float64 as torch's default dtype, tests/test_functional.py:76-93).
+    (*, num_freqs, time, 2) -> (*, num_freqs, ceil(time / rate), 2)."""
+    spec = complex_specgrams
+    lead = [slice(None)] * (spec.dim() - 2)                                   # :236-237
+    steps = torch.arange(0, spec.size(-2), rate, device=spec.device)          # :239-240 (default dtype)
+    frac = torch.remainder(steps, torch.tensor(1., device=spec.device))       # :242-243
+    first_phase = angle(spec[tuple(lead + [slice(1)])])                              # :244
+    padded = torch.nn.functional.pad(spec, [0, 0, 0, 2])                      # :247-248
+    lo = padded[tuple(lead + [steps.long()])]                                        # :250-251
+    hi = padded[tuple(lead + [(steps + 1).long()])]                                  # :253-254
+    ang_lo, ang_hi = angle(lo), angle(hi)                                     # :256-257
+    mag_lo, mag_hi = torch.norm(lo, dim=-1), torch.norm(hi, dim=-1)           # :259-260
+    dphi = ang_hi - ang_lo - phase_advance                                    # :262
+    dphi = dphi - 2 * math.pi * torch.round(dphi / (2 * math.pi))             # :263
+    dphi = dphi + phase_advance                                               # :266
+    dphi = torch.cat([first_phase, dphi[tuple(lead + [slice(-1)])]], dim=-1)         # :267
+    running = torch.cumsum(dphi, -1)                                          # :268
+    mag = frac * mag_hi + (1 - frac) * mag_lo                                 # :270
+    return torch.stack([mag * torch.cos(running), mag * torch.sin(running)], dim=-1)   # :272-279

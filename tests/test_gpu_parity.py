@@ -453,3 +453,109 @@ def test_fused_mel_few_wide_bands(tac, oc, num_mels, sr):
     got = m(dev(x)).cpu()
     want = oc.melspectrogram(x, num_mels, sr, fft_length=2048, hop_length=512)
     assert got.shape == want.shape and pure_rel_err(got, want) < REL
+
+
+# ------------------------------------------------------------------------------------------ N4 / N2
+def test_pointwise_next_golden(tac):
+    g = golden("pointwise_next.npz")
+    z = dev(g["z"])
+    assert (tac.angle(z).cpu() - g["angle"]).abs().max().item() < 2e-6
+    mag, phase = tac.magphase(z, 2.0)
+    assert rel_err(mag.cpu(), g["mag_p2"]) < 1e-6 and (phase.cpu() - g["angle"]).abs().max().item() < 2e-6
+    assert pure_rel_err(tac.db_to_amplitude(dev(g["db"]), 1.0).cpu(), g["amp_ref1"]) < 2e-6
+    assert pure_rel_err(tac.DbToAmplitude(ref=3.0).cuda()(dev(g["db"])).cpu(), g["amp_ref3"]) < 2e-6
+
+
+def test_db_to_amplitude_known_answers(tac):
+    """tests/test_functional.py:144-158, both directions and both round trips."""
+    power = torch.tensor([0.000001, 0.0001, 0.1, 1.0, 10.0, 1000000.0])
+    db = torch.tensor([-60.0, -40.0, -10.0, 0.0, 10.0, 60.0])
+    amp = power.sqrt()
+    assert torch.allclose(tac.db_to_amplitude(dev(db), ref=1.0).cpu(), amp, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(tac.db_to_amplitude(tac.amplitude_to_db(dev(amp), ref=1.0), ref=1.0).cpu(), amp, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(tac.amplitude_to_db(tac.db_to_amplitude(dev(db), ref=1.0), ref=1.0).cpu(), db, atol=1e-5)
+
+
+def test_magphase_reference_test_formula(tac):
+    """tests/test_functional.py:44-47, 62-66: magphase(stft) gives |.| and the angle, and re-assembles."""
+    torch.manual_seed(67)
+    x = torch.randn(1, 2, 20000)
+    z = tac.stft(dev(x), 512, 256, window=dev(torch.hann_window(512)))
+    mag, phase = tac.magphase(z)
+    back = torch.stack([mag * torch.cos(phase), mag * torch.sin(phase)], dim=-1)
+    assert (back - z).abs().max().item() < 1e-4
+    assert (mag - tac.complex_norm(z)).abs().max().item() == 0.0
+    assert (phase - tac.angle(z)).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("tag,rate", [("0p5", 0.5), ("1p01", 1.01), ("1p3", 1.3), ("2", 2.0)])
+def test_phase_vocoder_golden(tac, tag, rate):
+    """Against the reference run in float64 (the precision of its own test, tests/test_functional.py:85-93):
+    float64 tensors to 1e-8, float32 tensors (float64 inside the kernel) to float32 rounding of the result."""
+    g = golden("phase_vocoder.npz")
+    spec32, hop = g["spec"], int(g["hop"])
+    bins = spec32.shape[-3]
+    want = g["out64_" + tag]
+    adv = torch.linspace(0, np.pi * hop, bins)[..., None]
+    y32 = tac.phase_vocoder(dev(spec32), rate, dev(adv))
+    assert y32.dtype == torch.float32 and y32.shape == want.shape
+    assert (y32.cpu().double() - want).abs().max().item() < 2e-5       # the reference's own atol vs librosa is 1e-5
+    prior = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)                              # as the reference's test does
+    try:
+        adv64 = torch.linspace(0, np.pi * hop, bins)[..., None]
+        y64 = tac.phase_vocoder(dev(spec32.double()), rate, dev(adv64))
+    finally:
+        torch.set_default_dtype(prior)
+    assert y64.dtype == torch.float64 and (y64.cpu() - want).abs().max().item() < 1e-8
+    # the reference's float32 run is only good to ~1e-2 after 90 frames; early frames must still agree
+    assert (y32.cpu() - g["out32_" + tag])[..., :8, :].abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 1025, 400, 2), (1025, 400, 2)])
+@pytest.mark.parametrize("rate", [0.5, 1.01, 1.3])
+def test_phase_vocoder_reference_test(tac, oc, shape, rate):
+    """tests/test_functional.py:69-116 restated: float64, shape ceil(T / rate), values against the librosa
+    algorithm (oracle/f64_chain.py) at the reference's atol 1e-5, and against the oracle."""
+    from oracle import f64_chain
+    torch.manual_seed(71)
+    spec = torch.randn(*shape)
+    prior = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        spec64 = spec.double()
+        adv = torch.linspace(0, np.pi * 256, spec64.shape[-3])[..., None]
+        got = tac.phase_vocoder(dev(spec64), rate=rate, phase_advance=dev(adv)).cpu()
+        want = oc.phase_vocoder(spec64, rate, adv)
+    finally:
+        torch.set_default_dtype(prior)
+    expected = list(spec.shape)
+    expected[-2] = int(np.ceil(expected[-2] / rate))
+    assert list(got.shape) == expected and got.dim() == spec.dim()
+    assert (got - want).abs().max().item() < 1e-7
+    mono = spec64[(0,) * (spec.dim() - 3)].numpy()
+    lib = f64_chain.phase_vocoder(mono[..., 0] + 1j * mono[..., 1], rate, 256)
+    g0 = got[(0,) * (spec.dim() - 3)].numpy()
+    assert np.allclose(g0[..., 0] + 1j * g0[..., 1], lib, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 100000), (4, 100000)])
+def test_melspectrogram_stretch_pipeline(tac, oc, shape):
+    """tests/test_layers.py:86-106 as written: STFT -> TimeStretch(0.7) -> ComplexNorm(2) -> ApplyFilterbank;
+    shape as the reference asserts, values against the oracle chain evaluated in float64 for the vocoder."""
+    torch.manual_seed(73)
+    x = torch.randn(*shape)
+    fft, hop, rate = 512, 256, 0.7
+    fb = tac.MelFilterbank(num_freqs=fft // 2 + 1, num_mels=128, max_freq=1.0).get_filterbank()
+    model = torch.nn.Sequential(tac.STFT(fft, hop_length=hop), tac.TimeStretch(hop_length=hop, num_freqs=fft // 2 + 1, fixed_rate=rate),
+                                tac.ComplexNorm(power=2.0), tac.ApplyFilterbank(fb)).cuda()
+    y = model(dev(x)).cpu()
+    frames = (x.size(-1) + 2 * (fft // 2) - fft + hop) // hop
+    assert y.size(-2) == 128 and y.size(-1) == int(np.ceil(frames / rate))
+    z = oc.stft(x, fft, hop)
+    adv = torch.linspace(0, np.pi * hop, fft // 2 + 1)[..., None]
+    steps = torch.arange(0, z.size(-2), rate)                       # float32 steps, as the float32 pipeline has them
+    stretched = oc.phase_vocoder(z.double(), rate, adv.double())
+    want = oc.apply_filterbank(oc.complex_norm(stretched.float(), 2.0), fb)
+    assert stretched.size(-2) == steps.numel()
+    assert rel_err(y, want) < 5e-4                                   # |.|^2 does not see the phase; magnitudes interpolate in fp32

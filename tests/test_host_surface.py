@@ -141,6 +141,13 @@ def test_signatures_match_the_reference(tac):
     assert params(tac.amplitude_to_db) == [("x", E), ("ref", 1.0), ("amin", 1e-7)]
     assert params(tac.mu_law_encoding) == [("x", E), ("n_quantize", 256)]
     assert params(tac.mu_law_decoding)[:2] == [("x_mu", E), ("n_quantize", 256)]
+    # rows SURVEY 8(f) N2 / N4
+    assert params(tac.TimeStretch.__init__) == [("hop_length", E), ("num_freqs", E), ("fixed_rate", None)]    # layers.py:228
+    assert params(tac.TimeStretch.forward) == [("complex_specgrams", E), ("overriding_rate", None)]           # layers.py:238
+    assert params(tac.DbToAmplitude.__init__) == [("ref", 1.0)]                                                # layers.py:396
+    assert params(tac.phase_vocoder) == [("complex_specgrams", E), ("rate", E), ("phase_advance", E)]          # functional.py:204
+    assert params(tac.db_to_amplitude) == [("x", E), ("ref", 1.0)]                                             # functional.py:299
+    assert params(tac.angle) == [("complex_tensor", E)] and params(tac.magphase) == [("complex_tensor", E), ("power", 1.0)]
 
 
 def test_module_structure_and_state(tac):
@@ -184,6 +191,23 @@ def test_repr_strings(tac):
                                                           "max_freq=8000), htk=False")
     assert repr(tac.AmplitudeToDb()) == "AmplitudeToDb(ref=1.0, amin=1e-07)"
     assert repr(tac.MuLawEncoding()) == "MuLawEncoding(n_quantize=256)" and repr(tac.MuLawDecoding(64)) == "MuLawDecoding(n_quantize=64)"
+
+
+def test_time_stretch_and_db_to_amplitude_modules(tac):
+    """tests/test_layers.py:41-52 (buffer attributes) + the reference's repr / state / error behaviour."""
+    layer = tac.TimeStretch(hop_length=256, num_freqs=1025)
+    assert torch.is_tensor(layer.phase_advance) and not layer.phase_advance.requires_grad
+    assert layer.phase_advance.shape == (1025, 1)
+    assert torch.equal(layer.phase_advance, torch.linspace(0, np.pi * 256, 1025)[..., None])       # layers.py:232-233
+    assert layer.state_dict() == {} and "phase_advance" in dict(layer.named_buffers())
+    assert repr(tac.TimeStretch(256, 257, fixed_rate=0.7)) == "TimeStretch(fixed_rate=0.7)"
+    assert repr(tac.DbToAmplitude(ref=2.0)) == "DbToAmplitude(ref=2.0)" and tac.DbToAmplitude().state_dict() == {}
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 1025, 4, 2))                                                              # layers.py:251-253
+    same = torch.zeros(1, 1025, 4, 2)
+    assert tac.TimeStretch(256, 1025, fixed_rate=1.0)(same) is same                                    # layers.py:257-258
+    with pytest.raises(RuntimeError):
+        tac.TimeStretch(256, 1025, fixed_rate=0.7)(same)                                               # CPU tensor: no fallback
 
 
 def test_constructor_errors(tac):

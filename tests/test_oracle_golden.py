@@ -126,3 +126,48 @@ def test_spectrogram_db_against_float64():
     got = oc.amplitude_to_db(oc.spectrogram(x, 512, 256, window=torch.hann_window(512)), 1.0, 1e-7).numpy()
     want = f64_chain.power_to_db(np.abs(f64_chain.stft(x.numpy(), 512, 256)) ** 2, 1.0, 1e-7)
     assert np.allclose(got, want, atol=1e-2)
+
+
+# ---- rows SURVEY 8(f) marks "next": N2 phase vocoder, N4 db_to_amplitude / angle / magphase --------------
+def test_pointwise_next_fixtures_bit_exact():
+    g = golden("pointwise_next.npz")
+    assert torch.equal(oc.angle(g["z"]), g["angle"])
+    mag, phase = oc.magphase(g["z"], 2.0)
+    assert torch.equal(mag, g["mag_p2"]) and torch.equal(phase, g["angle"])
+    assert torch.equal(oc.db_to_amplitude(g["db"], 1.0), g["amp_ref1"])
+    assert torch.equal(oc.db_to_amplitude(g["db"], 3.0), g["amp_ref3"])
+
+
+def test_db_to_amplitude_known_answers_and_round_trips():
+    """tests/test_functional.py:144-158: dB [-60..60] -> amplitude sqrt(power), and both round trips."""
+    power = torch.tensor([0.000001, 0.0001, 0.1, 1.0, 10.0, 1000000.0])
+    db = torch.tensor([-60.0, -40.0, -10.0, 0.0, 10.0, 60.0])
+    amp = power.sqrt()
+    assert torch.allclose(oc.db_to_amplitude(db, ref=1.0), amp, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(oc.db_to_amplitude(oc.amplitude_to_db(amp, ref=1.0), ref=1.0), amp, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(oc.amplitude_to_db(oc.db_to_amplitude(db, ref=1.0), ref=1.0), db, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,rate", [("0p5", 0.5), ("1p01", 1.01), ("1p3", 1.3), ("2", 2.0)])
+def test_phase_vocoder_fixtures(tag, rate):
+    """The oracle reproduces the reference's float64 and float32 runs bit for bit, and the float64 run agrees
+    with the librosa algorithm restated in numpy (the oracle of tests/test_functional.py:100-116, atol 1e-5)."""
+    g = golden("phase_vocoder.npz")
+    spec32, hop = g["spec"], int(g["hop"])
+    bins = spec32.shape[-3]
+    prior = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        adv = torch.linspace(0, np.pi * hop, bins)[..., None]
+        y64 = oc.phase_vocoder(spec32.double(), rate, adv)
+    finally:
+        torch.set_default_dtype(prior)
+    assert torch.equal(y64, g["out64_" + tag])
+    adv32 = torch.linspace(0, np.pi * hop, bins)[..., None]
+    assert torch.equal(oc.phase_vocoder(spec32, rate, adv32), g["out32_" + tag])
+    want_frames = int(np.ceil(spec32.shape[-2] / rate))
+    assert y64.shape == spec32.shape[:-2] + (want_frames, 2)                      # tests/test_functional.py:95-99
+    z = spec32[0, 1].double().numpy()
+    lib = f64_chain.phase_vocoder(z[..., 0] + 1j * z[..., 1], rate, hop)
+    got = y64[0, 1].numpy()
+    assert np.allclose(got[..., 0] + 1j * got[..., 1], lib, atol=1e-7)

@@ -34,6 +34,10 @@ SIGNATURES = {
     "tac_spectrogram_f32": (_int, _STFT_ARGS + [_int, _f32, _ptr, _ptr]),
     "tac_complex_norm_f32": (_int, [_ptr, _i64, _f32, _ptr, _ptr]),
     "tac_amplitude_to_db_f32": (_int, [_ptr, _i64, _f32, _f32, _ptr, _ptr]),
+    "tac_db_to_amplitude_f32": (_int, [_ptr, _i64, _f32, _ptr, _ptr]),
+    "tac_magphase_f32": (_int, [_ptr, _i64, _f32, _ptr, _ptr, _ptr]),
+    "tac_phase_vocoder_f32": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "tac_phase_vocoder_f64": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
     "tac_fbplan_bytes": (_i64, [_int, _int]),
     "tac_fbplan_build_host": (_int, [_ptr, _int, _int, _ptr, _i64, _c.POINTER(_i64)]),
     "tac_fbplan_band_handle": (_i64, [_ptr]),

@@ -17,7 +17,7 @@ from . import _cabi, _mulaw_tables
 __all__ = [
     "stft", "complex_norm", "create_mel_filter", "apply_filterbank", "amplitude_to_db",
     "mu_law_encoding", "mu_law_decoding", "spectrogram", "melspectrogram", "FilterbankPlan",
-    "PreparedMelspectrogram",
+    "PreparedMelspectrogram", "angle", "magphase", "phase_vocoder", "db_to_amplitude",
 ]
 
 
@@ -262,6 +262,101 @@ def amplitude_to_db(x, ref=1.0, amin=1e-7):
     with torch.cuda.device(a.device):
         _cabi.check(_cabi.lib().tac_amplitude_to_db_f32(_cabi.ptr(a), a.numel(), float(ref), float(amin), _cabi.ptr(out),
                                                         _cabi.stream_ptr(a.device)))
+    return out
+
+
+def db_to_amplitude(x, ref=1.0):
+    """`sqrt(10 ** (x / 10 + log10(ref)))` (functional.py:299-314): the inverse of `amplitude_to_db`."""
+    _forward_only(x, "db_to_amplitude")
+    a = _as_f32_cuda(x, "x")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _cabi.check(_cabi.lib().tac_db_to_amplitude_f32(_cabi.ptr(a), a.numel(), float(ref), _cabi.ptr(out),
+                                                        _cabi.stream_ptr(a.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N4: angle / magphase
+# ------------------------------------------------------------------------------------------------
+def _magphase(complex_tensor, power, want_mag, name):
+    _forward_only(complex_tensor, name)
+    z = _as_f32_cuda(complex_tensor, "complex_tensor")
+    if z.dim() < 1 or z.size(-1) != 2:
+        raise RuntimeError("%s: expected a (*, 2) tensor, got %s" % (name, tuple(z.shape)))
+    phase = torch.empty(z.shape[:-1], dtype=torch.float32, device=z.device)
+    mag = torch.empty_like(phase) if want_mag else None
+    with torch.cuda.device(z.device):
+        _cabi.check(_cabi.lib().tac_magphase_f32(_cabi.ptr(z), phase.numel(), float(power),
+                                                 _cabi.ptr(mag) if want_mag else None, _cabi.ptr(phase),
+                                                 _cabi.stream_ptr(z.device)))
+    return mag, phase
+
+
+def angle(complex_tensor):
+    """`atan2(im, re)` of a `(*, 2)` tensor (functional.py:187-191)."""
+    return _magphase(complex_tensor, 1.0, False, "angle")[1]
+
+
+def magphase(complex_tensor, power=1.):
+    """`(complex_norm(z, power), angle(z))` (functional.py:194-201), one pass over `z`."""
+    return _magphase(complex_tensor, power, True, "magphase")
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: phase vocoder
+# ------------------------------------------------------------------------------------------------
+_pv_tables = {}
+
+
+def _phase_vocoder_tables(n_in, rate, device):
+    """Index / interpolation tables of functional.py:239-243 and :250-253, built with the reference's own
+    expressions in the reference's dtype (torch's default dtype, as `torch.arange(0, T, rate)` has there), on
+    the host, once per (T, rate): `time_steps.long()`, `(time_steps + 1).long()`, `remainder(time_steps, 1)`."""
+    key = (int(n_in), float(rate), torch.get_default_dtype(), str(device))
+    hit = _pv_tables.get(key)
+    if hit is None:
+        time_steps = torch.arange(0, n_in, rate)
+        alphas = torch.remainder(time_steps, torch.tensor(1.))
+        hit = (time_steps.long().to(torch.int32).to(device), (time_steps + 1).long().to(torch.int32).to(device),
+               alphas.to(torch.float64).to(device))
+        if len(_pv_tables) > 64:
+            _pv_tables.clear()
+        _pv_tables[key] = hit
+    return hit
+
+
+def phase_vocoder(complex_specgrams, rate, phase_advance):
+    """Time-stretch a complex STFT by `rate` without changing pitch (functional.py:204-274).
+    `(*, channel, num_freqs, time, 2) -> (*, channel, num_freqs, ceil(time / rate), 2)`; `phase_advance` is the
+    `(num_freqs, 1)` expected phase advance per bin.  float32 or float64 tensors; angles, the phase wrap, the
+    running phase sum and sin / cos are evaluated in float64 either way (the reference's float32 evaluation
+    loses the accumulated phase, which is why its own test runs in float64 -- tests/test_functional.py:85-88),
+    so the result matches the reference called in float64 on the same values."""
+    _forward_only(complex_specgrams, "phase_vocoder")
+    _cabi.require_cuda(complex_specgrams, "complex_specgrams")
+    if complex_specgrams.dtype not in (torch.float32, torch.float64):
+        raise NotImplementedError("phase_vocoder: dtype %s (float32 and float64 are implemented)" % complex_specgrams.dtype)
+    spec = complex_specgrams.contiguous()
+    if spec.dim() < 3 or spec.size(-1) != 2:
+        raise RuntimeError("phase_vocoder: expected (*, num_freqs, time, 2), got %s" % (tuple(spec.shape),))
+    if not rate > 0:
+        raise ValueError("phase_vocoder: rate must be positive, got %r" % (rate,))
+    n_bins, n_in = int(spec.size(-3)), int(spec.size(-2))
+    adv = phase_advance.to(device=spec.device, dtype=spec.dtype).reshape(-1).contiguous()
+    if adv.numel() != n_bins:
+        raise RuntimeError("phase_vocoder: phase_advance has %d entries for %d frequency bins" % (adv.numel(), n_bins))
+    idx0, idx1, alphas = _phase_vocoder_tables(n_in, rate, spec.device)
+    n_out = int(idx0.numel())
+    lead = tuple(spec.shape[:-3])
+    n_seq = 1
+    for d in lead:
+        n_seq *= int(d)
+    out = torch.empty(lead + (n_bins, n_out, 2), dtype=spec.dtype, device=spec.device)
+    fn = _cabi.lib().tac_phase_vocoder_f32 if spec.dtype == torch.float32 else _cabi.lib().tac_phase_vocoder_f64
+    with torch.cuda.device(spec.device):
+        _cabi.check(fn(_cabi.ptr(spec), n_seq, n_bins, n_in, _cabi.ptr(idx0), _cabi.ptr(idx1), _cabi.ptr(alphas),
+                       _cabi.ptr(adv), n_out, _cabi.ptr(out), _cabi.stream_ptr(spec.device)))
     return out
 
 

@@ -4,6 +4,8 @@ exceptions; `Spectrogram` / `Melspectrogram` still return an iterable `nn.Sequen
 `STFT, ComplexNorm[, ApplyFilterbank]`, but of the `FusedSequential` flavour whose forward runs
 the fused kernels when its children form a known chain.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -12,6 +14,7 @@ from . import functional as F
 __all__ = [
     "STFT", "ComplexNorm", "ApplyFilterbank", "Filterbank", "MelFilterbank", "Spectrogram",
     "Melspectrogram", "AmplitudeToDb", "MuLawEncoding", "MuLawDecoding", "FusedSequential", "Sequential",
+    "TimeStretch", "DbToAmplitude",
 ]
 
 
@@ -150,6 +153,48 @@ class AmplitudeToDb(_ModuleNoStateBuffers):
 
     def __repr__(self):
         return self.__class__.__name__ + '(ref={}, amin={})'.format(self.ref, self.amin)
+
+
+class DbToAmplitude(_ModuleNoStateBuffers):
+    """`sqrt(10 ** (x / 10 + log10(ref)))` (reference layers.py:384-412)."""
+
+    def __init__(self, ref=1.0):
+        super(DbToAmplitude, self).__init__()
+        self.ref = ref
+
+    def forward(self, x):
+        return F.db_to_amplitude(x, ref=self.ref)
+
+    def __repr__(self):
+        return self.__class__.__name__ + '(ref={})'.format(self.ref)
+
+
+class TimeStretch(_ModuleNoStateBuffers):
+    """Stretch a complex STFT in time by `rate` without changing pitch (reference layers.py:215-264).
+    `phase_advance = linspace(0, pi * hop_length, num_freqs)[..., None]` is a buffer; `forward(spec,
+    overriding_rate=None)` uses `fixed_rate` unless a rate is passed, returns the input itself for rate 1.0 and
+    raises `ValueError` when neither rate is given."""
+
+    def __init__(self, hop_length, num_freqs, fixed_rate=None):
+        super(TimeStretch, self).__init__()
+        self.fixed_rate = fixed_rate
+        phase_advance = torch.linspace(0, math.pi * hop_length, num_freqs)[..., None]
+        self.register_buffer('phase_advance', phase_advance)
+
+    def forward(self, complex_specgrams, overriding_rate=None):
+        if overriding_rate is None:
+            rate = self.fixed_rate
+            if rate is None:
+                raise ValueError("If no fixed_rate is specified"
+                                 ", must pass a valid rate to the forward method.")
+        else:
+            rate = overriding_rate
+        if rate == 1.0:
+            return complex_specgrams
+        return F.phase_vocoder(complex_specgrams, rate, self.phase_advance)
+
+    def __repr__(self):
+        return self.__class__.__name__ + '(fixed_rate={})'.format(self.fixed_rate)
 
 
 class MuLawEncoding(_ModuleNoStateBuffers):

@@ -379,13 +379,19 @@ def test_fused_mel_reference_layout(tac, oc):
     torch.manual_seed(43)
     x = torch.randn(3, 2, 30000)
     fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
-    got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512, layout="reference")
+    got = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512)                    # default layout
     want = oc.melspectrogram(x, 128, 16000, fft_length=2048, hop_length=512)
     assert got.shape == want.shape == (3, 2, 128, 59)
     assert got.stride()[-2:] == (1, 128) == want.stride()[-2:]
     assert pure_rel_err(got.cpu(), want) < REL
-    same = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512)
+    same = tac.functional.melspectrogram(dev(x), dev(fb), 2048, 512, layout="contiguous")
     assert same.is_contiguous() and torch.equal(same, got.contiguous())
+    module_out = tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512).cuda()(dev(x))
+    assert module_out.stride() == got.stride() and torch.equal(module_out, got)
+    prep = tac.PreparedMelspectrogram(x.shape, "cuda", fb, 2048, 512)
+    assert torch.equal(prep(dev(x), prep.empty_output()), got)
+    prep_c = tac.PreparedMelspectrogram(x.shape, "cuda", fb, 2048, 512, layout="contiguous")
+    assert torch.equal(prep_c(dev(x), prep_c.empty_output()), same)
 
 
 @pytest.mark.parametrize("power", [1.0, 2.0, 0.7])

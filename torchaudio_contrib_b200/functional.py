@@ -377,7 +377,7 @@ def _workspace(device, nbytes):
 
 def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_length=None, window=None,
                    center=True, pad_mode='reflect', normalized=False, power=2.0,
-                   to_db=False, ref=1.0, amin=1e-7, layout="contiguous", _cache=None):
+                   to_db=False, ref=1.0, amin=1e-7, layout="reference", _cache=None):
     """`Melspectrogram(...)(x)` (layers.py:307-347), optionally with `AmplitudeToDb` appended
     (layers.py:350-381).  `(*, channel, time) -> (*, channel, num_bands, frames)`.
 
@@ -387,9 +387,11 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     Otherwise two back-to-back kernels: stft + |.|^power into frame-major power tiles that stay in
     L2, then the tensor-core filterbank with the dB clamp in its epilogue.
 
-    `layout="reference"` (one-kernel path only) returns the reference's memory order -- a transposed
-    view of a `(*, frames, num_bands)` buffer, exactly the strides of `apply_filterbank`'s
-    `matmul(...).transpose(-2, -1)` (functional.py:183-184); the default is a contiguous tensor."""
+    `layout="reference"` (default; one-kernel path only) returns the reference's memory order -- a
+    transposed view of a `(*, frames, num_bands)` buffer, exactly the strides of `apply_filterbank`'s
+    `matmul(...).transpose(-2, -1)` (functional.py:183-184; a frame's bands are one 512-byte store);
+    `layout="contiguous"` returns a contiguous `(*, num_bands, frames)` tensor (4-byte stores, ~9 % slower
+    at BASELINE config 2).  The two-kernel path always returns a contiguous tensor."""
     _forward_only(waveforms, "melspectrogram")
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
@@ -429,13 +431,17 @@ class PreparedMelspectrogram(object):
     """The `melspectrogram` call with everything shape-independent resolved once (window on the device,
     filterbank plan, argument marshalling): `prepared(x, out)` is then a single C-ABI call into a
     caller-owned output -- what a serving loop or a CUDA-graph capture wants.  `x`: contiguous float32
-    CUDA tensor `(*, channel, time)` of the shape given at construction; `out`: contiguous
-    `(*, channel, num_bands, frames)` (`empty_output()` allocates one)."""
+    CUDA tensor `(*, channel, time)` of the shape given at construction; `out`: a buffer from
+    `empty_output()`.  Returns the `(*, channel, num_bands, frames)` result: `out` itself, or with
+    `layout="reference"` on the one-kernel path the transposed view of the `(*, frames, num_bands)` buffer
+    (the reference's memory order, see `melspectrogram`)."""
 
     def __init__(self, shape, device, filterbank, fft_length, hop_length=None, win_length=None, window=None,
                  center=True, pad_mode='reflect', normalized=False, power=2.0, to_db=False, ref=1.0, amin=1e-7,
-                 layout="contiguous"):
+                 layout="reference"):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.shape = tuple(int(d) for d in shape)
         self.n_samples = self.shape[-1]
         self.n_seq = 1
@@ -479,7 +485,7 @@ class PreparedMelspectrogram(object):
                                % (self.shape, self.out_shape, self.device))
         _cabi.check(self._fn(_cabi.ptr(x), *self._head, _cabi.ptr(out), *self._tail,
                              ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
-        return out
+        return out.transpose(-2, -1) if self.frame_major else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -67,13 +67,15 @@ def main():
                 hdr = rows[0]
                 ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
                 per = {}
+                fused = False
                 for r in rows[1:]:
                     if "stft2048_kernel" in r[ki] and r[mi].startswith("dram__bytes"):
+                        fused = fused or "stft2048_kernel<3," in r[ki]        # OUT_MEL_FUSED: the one-kernel mel path
                         per.setdefault(r[ii], 0.0)
                         per[r[ii]] += float(r[vi].replace(",", ""))
                 vals = list(per.values())[1:] or list(per.values())      # drop the first launch (follows the RNG fill)
                 if vals:
-                    with open(os.path.join(dst, "%s_stft2048_dram_bytes.json" % tag), "w") as fh:
+                    with open(os.path.join(dst, "%s_%s_dram_bytes.json" % (tag, "melfused" if fused else "stft2048")), "w") as fh:
                         json.dump({"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals), "source": name,
                                    "note": "dram__bytes_read.sum + dram__bytes_write.sum per stft2048_kernel launch, ncu --cache-control none "
                                            "(steady state of bench.py, 20032 frames per launch)"}, fh)

@@ -160,27 +160,34 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
   const float4* wtab = reinterpret_cast<const float4*>(p.band_plan + kBandOffW) + lane;
   const uint32_t mask = meta.x;
   float* row = stash + lane * kStashStride;        // this lane's own (consumed) row takes what it stores
+  // Running sums without a store inside the dependency chain: the sum after every bin gets its own register
+  // (us[i]), the band step only selects what the next bin continues from, and the stores follow in a batch.
+  // (Storing u and then overwriting the same register made every step wait for the store to read its operand.)
+  float us[32];
   float u = 0.0f, v = 0.0f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float4 w = __ldg(wtab + j * 32);
-    u = fmaf(pw[2 * j], w.x, u);
-    v = fmaf(pw[2 * j], w.y, v);
-    if (mask & (1u << (2 * j))) {                  // band b -> b + 1
-      row[2 * j] = u;
-      u = v;
-      v = 0.0f;
+    {
+      const float un = fmaf(pw[2 * j], w.x, u), vn = fmaf(pw[2 * j], w.y, v);
+      const bool step = (mask >> (2 * j)) & 1u;    // band b -> b + 1 after this bin
+      us[2 * j] = un;
+      u = step ? vn : un;
+      v = step ? 0.0f : vn;
     }
-    u = fmaf(pw[2 * j + 1], w.z, u);
-    v = fmaf(pw[2 * j + 1], w.w, v);
-    if (mask & (1u << (2 * j + 1))) {
-      row[2 * j + 1] = u;
-      u = v;
-      v = 0.0f;
+    {
+      const float un = fmaf(pw[2 * j + 1], w.z, u), vn = fmaf(pw[2 * j + 1], w.w, v);
+      const bool step = (mask >> (2 * j + 1)) & 1u;
+      us[2 * j + 1] = un;
+      u = step ? vn : un;
+      v = step ? 0.0f : vn;
     }
   }
   u = fmaf(p_last, __uint_as_float(meta.z), u);    // bin 1024 (weights are zero except on lane 31)
   v = fmaf(p_last, __uint_as_float(meta.w), v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if ((mask >> i) & 1u) row[i] = us[i];
   stash[meta.y] = u;
   stash[meta.y + 1] = v;
   __syncwarp();
@@ -227,8 +234,16 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
 // unrolled instructions and has to stay resident in the instruction caches while 16 warps run
 // through it at different phases (a first version that branched on these at run time was 12k
 // instructions and spent most of its time stalled on instruction fetch).
-__device__ long long g_k1_trace[64];      // TAC_K1_TRACE: clock64 stamps of CTA 0 / warp 0
+// clock64 stamps of CTA 0 / warp 0 for timing experiments: compiled in only with -DTAC_K1_TRACE_BUILD (the counter and
+// the run-time test cost two registers and ~10 instructions per frame in a kernel that sits at the 128-register cap)
+__device__ long long g_k1_trace[64];
+#ifdef TAC_K1_TRACE_BUILD
 #define K1_TRACE(i) do { if (p.debug && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_k1_trace[i] = clock64(); } while (0)
+#define K1_TRACE_NEXT() do { K1_TRACE(trace_i); ++trace_i; } while (0)
+#else
+#define K1_TRACE(i) do { } while (0)
+#define K1_TRACE_NEXT() do { } while (0)
+#endif
 
 template <int OUT_MODE, int PMODE>
 __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
@@ -252,11 +267,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   }
   __syncthreads();
   K1_TRACE(1);
+#ifdef TAC_K1_TRACE_BUILD
   int trace_i = 2;
+#endif
 
   float2* slab = s_slab + warp * kSlabComplex;
   float* slab_f = reinterpret_cast<float*>(slab);
-  const int64_t step = (int64_t)gridDim.x * kFastWarps;
+  const uint32_t step = gridDim.x * kFastWarps;              // frame indices fit 31 bits (checked by the host)
   const float half_power = 0.5f * p.power;
   uint32_t parity = 0;
   // OUT_MEL_FUSED: this warp's power-spectrum stash, row k1 = bins 32 k1 .. 32 k1 + 31, stride 33
@@ -269,7 +286,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   // (sequence, frame-in-sequence) of this warp's frames advance incrementally: a 64-bit division per frame
   // costs ~100 instructions in the hot loop (it did, twice per frame, in the first version)
   const uint32_t frames_u = (uint32_t)p.frames;
-  const uint32_t step_seq = (uint32_t)(step / p.frames), step_t = (uint32_t)(step % p.frames);
+  const uint32_t step_seq = step / frames_u, step_t = step % frames_u;
   auto advance = [&](uint32_t& seq, uint32_t& t) {
     seq += step_seq;
     t += step_t;
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   span_cur.lo = 0; span_cur.hi = 2048; span_cur.bulk = false;
   span_next = span_cur;
   auto stage_bulk = [&](uint32_t seq, uint32_t t, FrameSpan& span) -> bool {   // true: bulk copy in flight; false: needs the gather
-    const int64_t start = (int64_t)t * p.hop - p.pad;
+    const int start = (int)t * p.hop - p.pad;                   // 32-bit: n_samples + 2 n_fft < 2^31 (host check)
     span = frame_span<2048>(p, start);
     if (span.bulk && elect_one()) {
       fence_proxy_async();
@@ -299,36 +316,40 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     return span.bulk;
   };
   auto stage_gather = [&](uint32_t seq, uint32_t t) {
-    const int64_t start = (int64_t)t * p.hop - p.pad;
-    gather_padded<64, 32>(slab_f, p.x + (int64_t)seq * p.seq_stride, (int)start, (int)p.n_samples, p.pad_mode, lane);
+    const int start = (int)t * p.hop - p.pad;
+    gather_padded<64, 32>(slab_f, p.x + (int64_t)seq * p.seq_stride, start, (int)p.n_samples, p.pad_mode, lane);
   };
 
-  int64_t g = p.g0 + (int64_t)blockIdx.x * kFastWarps + warp;
-  uint32_t seq = (uint32_t)(g / p.frames), t = (uint32_t)(g % p.frames);      // once per warp
+  const uint32_t n_launch = (uint32_t)(p.g1 - p.g0);          // frames of this launch; gi indexes them
+  uint32_t gi = blockIdx.x * kFastWarps + warp;
+  const int64_t g_first = p.g0 + gi;
+  uint32_t seq = (uint32_t)(g_first / p.frames), t = (uint32_t)(g_first % p.frames);      // once per warp
   bool in_flight = false;
-  if (g < p.g1) {
+  if (gi < n_launch) {
     in_flight = stage_bulk(seq, t, span_cur);
     if (!in_flight) stage_gather(seq, t);
   }
 
 #pragma unroll 1
-  for (; g < p.g1; g += step) {
+  for (; gi < n_launch; gi += step) {
     if (in_flight) {
       mbar_wait(bar, parity);
       parity ^= 1u;
-      fill_padding<2048>(slab_f, span_cur, p.pad_mode, lane, p.x + (int64_t)seq * p.seq_stride, (int64_t)t * p.hop - p.pad);
+      fill_padding<2048>(slab_f, span_cur, p.pad_mode, lane, p.x + (int64_t)seq * p.seq_stride, (int)t * p.hop - p.pad);
     } else {
       __syncwarp();
     }
 
-    K1_TRACE(trace_i); ++trace_i;                  // sample data arrived
+    K1_TRACE_NEXT();                               // sample data arrived
+#ifdef TAC_K1_TRACE_BUILD
     if (p.debug && blockIdx.x == 0 && lane == 0 && g_k1_trace[40 + warp] == 0) g_k1_trace[40 + warp] = clock64();
+#endif
     float2 v[32];
     fft2048_front(v, slab, s_win, s_tw1, lane);    // slab free again afterwards: prefetch the next frame
-    K1_TRACE(trace_i); ++trace_i;                  // front half done
+    K1_TRACE_NEXT();                               // front half done
     uint32_t seq_next = seq, t_next = t;
     advance(seq_next, t_next);
-    const bool has_next = g + step < p.g1;
+    const bool has_next = gi + step < n_launch;
     in_flight = has_next ? stage_bulk(seq_next, t_next, span_next) : false;
     // ---- pass 2: 32-point FFT over n1 for fixed k2 = lane ---------------------------------------------
     dit_fft_fma<32>(v);
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     float* dst;
     int64_t dst_stride = 0;                        // floats between consecutive k1 (public layouts only)
     if constexpr (OUT_MODE == OUT_POWER_ROWS) {
-      dst = p.out + power_tile_index(g - p.g0, lane, p.kpad);      // + k1 * 4096 floats: immediate offsets below
+      dst = p.out + power_tile_index(gi, lane, p.kpad);            // + k1 * 4096 floats: immediate offsets below
     } else if constexpr (OUT_MODE == OUT_MEL_FUSED) {
       dst = stash + lane;                                          // + k1 * 33 floats
     } else if constexpr (OUT_MODE == OUT_POWER_PUBLIC) {
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       }
     }
     if constexpr (OUT_MODE == OUT_MEL_FUSED) band_contract(p, stash, lane, seq, t);
-    K1_TRACE(trace_i); ++trace_i;                  // frame done
+    K1_TRACE_NEXT();                               // frame done
     if (has_next && !in_flight) stage_gather(seq_next, t_next);
     seq = seq_next;
     t = t_next;

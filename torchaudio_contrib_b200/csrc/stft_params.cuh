@@ -110,12 +110,13 @@ struct FrameSpan {
   bool bulk;
 };
 template <int N>
-__device__ __forceinline__ FrameSpan frame_span(const StftParams& p, int64_t start) {
+__device__ __forceinline__ FrameSpan frame_span(const StftParams& p, int start) {   // 32-bit: n_samples + 2 n_fft < 2^31
   FrameSpan f;
-  const int64_t lo = start < 0 ? -start : 0;
-  const int64_t hi = (start + N > p.n_samples) ? p.n_samples - start : N;
-  f.lo = (int)lo;
-  f.hi = (int)hi;
+  const int n = (int)p.n_samples;
+  const int lo = start < 0 ? -start : 0;
+  const int hi = (start + N > n) ? n - start : N;
+  f.lo = lo;
+  f.hi = hi;
   const bool interior = lo == 0 && hi == N;
   f.bulk = p.bulk_ok && hi > lo && (interior || (p.pad_mode != 3 && (p.n_samples & 3) == 0 && !(lo > 0 && hi < N)));
   return f;
@@ -126,7 +127,7 @@ __device__ __forceinline__ FrameSpan frame_span(const StftParams& p, int64_t sta
 // read from global memory.
 template <int N>
 __device__ __forceinline__ void fill_padding(float* slab_f, const FrameSpan f, int pad_mode, int lane,
-                                             const float* __restrict__ row, int64_t start) {
+                                             const float* __restrict__ row, int start) {
   if (f.lo == 0 && f.hi == N) return;
   if (pad_mode == 0) {                                   // reflect: x[-k] = x[k], x[n-1+k] = x[n-1-k]
     for (int j = lane; j < f.lo; j += 32) {

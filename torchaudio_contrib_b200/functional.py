@@ -37,13 +37,24 @@ def _as_f32_cuda(t, name):
     return t.contiguous()
 
 
+_default_windows = {}
+
+
 def _frame_window(window, win_length, fft_length, device):
     """The n_fft-long window torch.stft effectively multiplies by: Hann(win_length) when none is
     given (functional.py:93-97), zero-padded on both sides to sit in the middle of the frame."""
     if win_length is None:
         win_length = fft_length
     if window is None:
-        window = torch.hann_window(win_length, device=device)
+        key = (win_length, fft_length, str(device))
+        cached = _default_windows.get(key)
+        if cached is not None:
+            return cached
+        # evaluated on the host like the reference's (functional.py:93-97, layers.py:76-82): the CUDA
+        # hann_window differs from it in the last bit, which would make functional and module outputs differ
+        window = torch.hann_window(win_length)
+    else:
+        key = None
     if window.dim() != 1 or window.size(0) != win_length:
         raise RuntimeError("stft: expected a 1-D window of size win_length=%d, got %s"
                            % (win_length, tuple(window.shape)))
@@ -54,7 +65,10 @@ def _frame_window(window, win_length, fft_length, device):
     if win_length < fft_length:
         left = (fft_length - win_length) // 2
         window = torch.nn.functional.pad(window, (left, fft_length - win_length - left))
-    return window.contiguous()
+    window = window.contiguous()
+    if key is not None and 0 < win_length <= fft_length:
+        _default_windows[key] = window
+    return window
 
 
 def _stft_geometry(waveforms, fft_length, hop_length, center):

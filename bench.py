@@ -373,10 +373,46 @@ def run_ours(args, rank, world, local):
             barrier()
         gather_ms = g0.elapsed_time(g1)
 
-    t = torch.tensor([ms, e2e_s * 1e3, gather_ms], dtype=torch.float64, device=dev)
+    # the same gather done by the mel kernel itself: every frame's bands stored into all ranks' full outputs over
+    # NVLink from the epilogue (tac_melspec_banded_peers_f32), one flag barrier per step instead of the collective
+    peer_ms, peer_err = 0.0, None
+    if world > 1 and prepared.fused:
+        from torchaudio_contrib_b200.distributed import PeerGatheredOutput
+        try:
+            fulls = [PeerGatheredOutput((world * batch,) + prepared.out_shape[1:], dev) for _ in range(2)]
+            with torch.no_grad():
+                def peer_step(i):
+                    prepared.gather_into(inputs[i % n_sets], fulls[i % 2])
+                    fulls[i % 2].barrier()
+                for i in range(4):
+                    peer_step(i)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for i in range(args.steps):
+                    peer_step(i)
+                g1.record()
+                barrier()
+            peer_ms = g0.elapsed_time(g1)
+            for f in fulls:
+                f.check()
+            # the gathered tensor equals an NCCL all-gather of what the plain call returns on every rank
+            last = (args.steps - 1) % n_sets
+            local = prepared.empty_output()
+            prepared(inputs[last], local)
+            want = torch.empty_like(fulls[0].tensor)
+            torch.distributed.all_gather_into_tensor(want, local)
+            if not torch.equal(want, fulls[(args.steps - 1) % 2].tensor):
+                peer_err = "gathered tensor differs from the all-gather of the single-GPU calls"
+            for f in fulls:
+                f.close()
+        except Exception as exc:                                # report, do not lose the whole bench line
+            peer_err = "%s: %s" % (type(exc).__name__, exc)
+
+    t = torch.tensor([ms, e2e_s * 1e3, gather_ms, peer_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_ms, gather_ms, peer_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -424,6 +460,15 @@ def run_ours(args, rank, world, local):
                 "ms_per_step": gather_ms / args.steps,
                 "what": "same steps + one NCCL all_gather_into_tensor of the (batch,C,128,frames) output per step on a side stream",
                 "bytes_received_per_rank_per_step": (world - 1) * out_bytes}
+            if peer_ms > 0.0 and peer_err is None:
+                line["with_peer_gather"] = {
+                    "value": world * args.steps * frames_per_step / (peer_ms * 1e-3), "unit": "frames/s",
+                    "ms_per_step": peer_ms / args.steps,
+                    "what": "tac_melspec_banded_peers_f32: the kernel's epilogue stores every frame into all ranks' "
+                            "(world*batch,C,frames,128) buffers over NVLink + one flag barrier kernel per step; no collective",
+                    "bytes_sent_per_rank_per_step": (world - 1) * out_bytes}
+            elif peer_err is not None:
+                line["with_peer_gather"] = {"error": peer_err}
         traffic_file = os.path.join(ROOT, "profiles", "r01_melfused_dram_bytes.json" if prepared.fused else "r01_stft2048_dram_bytes.json")
         if os.path.exists(traffic_file):
             with open(traffic_file) as fh:

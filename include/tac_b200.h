@@ -134,6 +134,39 @@ int tac_melspec_banded_f32(const float* x, int64_t n_seq, int64_t n_samples, int
                            int to_db, float ref, float amin,
                            float* out, int frame_major, void* stream);
 
+/* ---- row (e) / N3: batch split over the GPUs of one box, output gathered by the kernel ---
+ * The reference has no multi-GPU path; SURVEY 8(e) shards the flattened batch
+ * (functional.py:89-91) over one process per GPU and gathers the output.  Instead of a trailing
+ * all-gather, tac_melspec_banded_peers_f32 stores every frame's bands straight into the output
+ * buffers of ALL ranks (its own and the peer-mapped ones) over NVLink.
+ *
+ * Peer memory: tac_peer_alloc returns a device allocation of TAC_PEER_HEADER_BYTES + bytes and
+ * its 64-byte IPC handle; the payload starts TAC_PEER_HEADER_BYTES after *dev_ptr.  Other
+ * processes of the box map it with tac_peer_open (and unmap with tac_peer_close); the owner
+ * releases it with tac_peer_free after the peers have closed it.
+ * tac_peer_barrier (stream-ordered): tell every rank that this rank's stores of round `epoch`
+ * (epochs must increase) are complete, then wait for the same from every rank; gives up after
+ * timeout_s (<= 60) and records it -- tac_peer_timed_out reads that flag (synchronises). */
+#define TAC_PEER_HANDLE_BYTES 64
+#define TAC_PEER_HEADER_BYTES 128
+int tac_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle_out /*[64]*/);
+int tac_peer_open(const unsigned char* handle /*[64]*/, void** dev_ptr);
+int tac_peer_close(void* dev_ptr);
+int tac_peer_free(void* dev_ptr);
+int tac_peer_barrier(void* const* peer_base /* host array [n_peers], index = rank */, int n_peers,
+                     int rank, uint32_t epoch, double timeout_s, void* stream);
+int tac_peer_timed_out(const void* own_base, int* timed_out);
+/* As tac_melspec_banded_f32 for this rank's n_seq sequences; peer_out: host array of n_peers
+ * (<= 8) device pointers, the payload of every rank's FULL output ((total_seq, n_bands, frames),
+ * or (total_seq, frames, n_bands) when frame_major); this rank's rows start at seq_offset. */
+int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64_t n_samples,
+                                 int64_t seq_stride, const float* window, int n_fft, int hop,
+                                 int center, int pad_mode, int normalized, float power,
+                                 const void* plan_dev, int64_t band_handle, int n_bands,
+                                 int to_db, float ref, float amin,
+                                 float* const* peer_out, int n_peers, int64_t seq_offset,
+                                 int frame_major, void* stream);
+
 /* ---- a7: mu_law_encoding (functional.py:317-335) ----------------------------------------
  * The quantiser is evaluated as a table of decision levels: thresholds[j] is the smallest
  * float whose code is >= idx_min + j (thresholds[0] = -inf); |x| > x_limit or NaN gives

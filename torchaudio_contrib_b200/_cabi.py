@@ -45,6 +45,13 @@ SIGNATURES = {
     "tac_melspec_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),
     "tac_melspec_f32": (_int, _STFT_ARGS + [_f32, _ptr, _int, _int, _f32, _f32, _ptr, _i64, _ptr, _ptr]),
     "tac_melspec_banded_f32": (_int, _STFT_ARGS + [_f32, _ptr, _i64, _int, _int, _f32, _f32, _ptr, _int, _ptr]),
+    "tac_melspec_banded_peers_f32": (_int, _STFT_ARGS + [_f32, _ptr, _i64, _int, _int, _f32, _f32, _ptr, _int, _i64, _int, _ptr]),
+    "tac_peer_alloc": (_int, [_i64, _c.POINTER(_ptr), _ptr]),
+    "tac_peer_open": (_int, [_ptr, _c.POINTER(_ptr)]),
+    "tac_peer_close": (_int, [_ptr]),
+    "tac_peer_free": (_int, [_ptr]),
+    "tac_peer_barrier": (_int, [_ptr, _int, _int, _c.c_uint32, _c.c_double, _ptr]),
+    "tac_peer_timed_out": (_int, [_ptr, _c.POINTER(_int)]),
     "tac_mulaw_encode_f32_i64": (_int, [_ptr, _i64, _int, _ptr, _int, _int, _f32, _ptr, _ptr]),
     "tac_mulaw_decode_i64_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
     "tac_mulaw_decode_f32_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),

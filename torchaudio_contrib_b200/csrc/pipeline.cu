@@ -72,7 +72,8 @@ static bool fused_enabled() {
 // Fused path: STFT + |.|^p + two-band filterbank [+ dB] in ONE kernel, the spectrum never leaves the SM
 // (stft.cu, OUT_MEL_FUSED).  n_fft = 2048 and a plan that carries a band plan (tac_fbplan_band_handle != 0).
 static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, int64_t band_handle, int n_bands, int to_db,
-                              float ref, float amin, float* out, int frame_major, cudaStream_t stream) {
+                              float ref, float amin, float* out, int frame_major, cudaStream_t stream,
+                              float* const* peer_out = nullptr, int n_peers = 0, int64_t peer_seq0 = 0) {
   TAC_REQUIRE(sp.n_fft == 2048, TAC_ERR_UNSUPPORTED, "melspec_banded: the fused kernel exists for n_fft = 2048 only (got %d)", sp.n_fft);
   const int64_t off = band_handle & (((int64_t)1 << 48) - 1);
   const int cmax = (int)(band_handle >> 48);
@@ -101,10 +102,36 @@ static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, 
     sp.out_t_stride = 1;
     sp.out_band_stride = sp.frames;
   }
+  if (n_peers > 0) {                     // every rank's full output takes this rank's frames (stores over NVLink)
+    sp.out_mode = OUT_MEL_FUSED_PEERS;
+    sp.out = nullptr;
+    sp.n_peers = n_peers;
+    sp.peer_seq0 = peer_seq0;
+    for (int q = 0; q < n_peers; ++q) sp.peer_out[q] = peer_out[q];
+  }
   return launch_stft(sp, stream);
 }
 
 }  // namespace tac
+
+extern "C" int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                                            const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
+                                            float power, const void* plan_dev, int64_t band_handle, int n_bands, int to_db,
+                                            float ref, float amin, float* const* peer_out, int n_peers, int64_t seq_offset,
+                                            int frame_major, void* stream) {
+  using namespace tac;
+  StftParams sp;
+  const int rc = fill_stft_params(sp, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(plan_dev && n_bands > 0, TAC_ERR_INVALID, "melspec_banded_peers: missing filterbank plan");
+  TAC_REQUIRE(peer_out && n_peers >= 1 && n_peers <= kMaxPeers, TAC_ERR_INVALID,
+              "melspec_banded_peers: %d output buffers given, 1..%d supported (the GPUs of one box)", n_peers, kMaxPeers);
+  TAC_REQUIRE(seq_offset >= 0, TAC_ERR_INVALID, "melspec_banded_peers: negative sequence offset");
+  for (int q = 0; q < n_peers; ++q)
+    TAC_REQUIRE(peer_out[q] || sp.g1 == 0, TAC_ERR_INVALID, "melspec_banded_peers: null output pointer for rank %d", q);
+  return run_melspec_banded(sp, power, plan_dev, band_handle, n_bands, to_db, ref, amin, nullptr, frame_major, as_stream(stream),
+                            peer_out, n_peers, seq_offset);
+}
 
 extern "C" int tac_melspec_banded_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
                                       int n_fft, int hop, int center, int pad_mode, int normalized, float power,

@@ -140,6 +140,7 @@ __device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_wi
 // OUT_MEL_FUSED: the frame's power spectrum (in this warp's stash) times a two-band filterbank (bandplan.cuh),
 // optional dB epilogue (amplitude_to_db, functional.py:291-296), result to global memory.
 // Replaces apply_filterbank's transpose + matmul + transpose (functional.py:183-184) for such matrices.
+template <bool PEERS>
 __device__ __forceinline__ void band_contract(const StftParams& p, float* stash, int lane, uint32_t seq, uint32_t t) {
   __syncwarp();                                    // the stash holds the whole frame
   // per-band lists of this lane's four bands (fast form: <= 128 bands, <= 4 entries each), fetched now so the
@@ -193,7 +194,19 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
   __syncwarp();
   // lane = band: add up the band's slots in list order
   const uint16_t* comb = reinterpret_cast<const uint16_t*>(p.band_plan + kBandOffComb);
-  float* dst = p.out + (int64_t)seq * p.out_seq_stride + (int64_t)t * p.out_t_stride;
+  // PEERS: the same offset inside every rank's full output; the stores below go out over NVLink to the peers'
+  // memory as they are produced (no gather pass afterwards)
+  const int64_t dst_off = (int64_t)(seq + (PEERS ? p.peer_seq0 : 0)) * p.out_seq_stride + (int64_t)t * p.out_t_stride;
+  float* dst = (PEERS ? p.peer_out[0] : p.out) + dst_off;
+  auto store = [&](int m, float r) {
+    if constexpr (PEERS) {
+      const int64_t o = dst_off + (int64_t)m * p.out_band_stride;
+#pragma unroll 1
+      for (int q = 0; q < p.n_peers; ++q) __stcs(p.peer_out[q] + o, r);
+    } else {
+      __stcs(dst + (int64_t)m * p.out_band_stride, r);
+    }
+  };
   if (fast) {
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(stash);
     float acc[4];
@@ -212,7 +225,7 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
         r = 10.0f * (log10f(s2) - p.log10_ref);
       }
       const int m = lane + 32 * j;
-      if (m < p.n_bands) __stcs(dst + (int64_t)m * p.out_band_stride, r);
+      if (m < p.n_bands) store(m, r);
     }
     __syncwarp();
     return;
@@ -225,7 +238,7 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
       s2 = (s2 < p.amin) ? p.amin : s2;
       acc = 10.0f * (log10f(s2) - p.log10_ref);
     }
-    __stcs(dst + (int64_t)m * p.out_band_stride, acc);
+    store(m, acc);
   }
   __syncwarp();                                    // slots consumed before the next frame's spectrum lands
 }
@@ -245,8 +258,10 @@ __device__ long long g_k1_trace[64];
 #define K1_TRACE_NEXT() do { } while (0)
 #endif
 
-template <int OUT_MODE, int PMODE>
+template <int OUT_MODE_T, int PMODE>
 __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftParams p) {
+  constexpr bool kPeers = OUT_MODE_T == OUT_MEL_FUSED_PEERS;
+  constexpr int OUT_MODE = kPeers ? (int)OUT_MEL_FUSED : OUT_MODE_T;      // same body, only the band stores differ
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // tables are stored pair-interleaved, [j / 2][lane][j % 2], so that one LDS.128 fetches the entries of two
   // consecutive register indices of a lane (conflict free: consecutive lanes are 16 bytes apart)
@@ -427,7 +442,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
         if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(nyq, 0.0f);
       }
     }
-    if constexpr (OUT_MODE == OUT_MEL_FUSED) band_contract(p, stash, lane, seq, t);
+    if constexpr (OUT_MODE == OUT_MEL_FUSED) band_contract<kPeers>(p, stash, lane, seq, t);
     K1_TRACE_NEXT();                               // frame done
     if (has_next && !in_flight) stage_gather(seq_next, t_next);
     seq = seq_next;
@@ -670,9 +685,11 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
       k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_PUBLIC, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_PUBLIC, 1> : stft2048_kernel<OUT_POWER_PUBLIC, 0>);
     else if (p.out_mode == OUT_MEL_FUSED)
       k = p.power_mode == 2 ? stft2048_kernel<OUT_MEL_FUSED, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_MEL_FUSED, 1> : stft2048_kernel<OUT_MEL_FUSED, 0>);
+    else if (p.out_mode == OUT_MEL_FUSED_PEERS)
+      k = p.power_mode == 2 ? stft2048_kernel<OUT_MEL_FUSED_PEERS, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_MEL_FUSED_PEERS, 1> : stft2048_kernel<OUT_MEL_FUSED_PEERS, 0>);
     else
       k = p.power_mode == 2 ? stft2048_kernel<OUT_POWER_ROWS, 2> : (p.power_mode == 1 ? stft2048_kernel<OUT_POWER_ROWS, 1> : stft2048_kernel<OUT_POWER_ROWS, 0>);
-    const size_t smem = p.out_mode == OUT_MEL_FUSED ? kFusedSmemBytes : kFastSmemBytes;
+    const size_t smem = (p.out_mode == OUT_MEL_FUSED || p.out_mode == OUT_MEL_FUSED_PEERS) ? kFusedSmemBytes : kFastSmemBytes;
     TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchProbe probe(KIND_STFT, stream);
     k<<<grid, kFastThreads, smem, stream>>>(p);
@@ -745,6 +762,9 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.amin = 0.0f;
   p.log10_ref = 0.0f;
   p.out_seq_stride = p.out_t_stride = p.out_band_stride = 0;
+  for (int q = 0; q < kMaxPeers; ++q) p.peer_out[q] = nullptr;
+  p.n_peers = 0;
+  p.peer_seq0 = 0;
   return TAC_OK;
 }
 

@@ -10,8 +10,10 @@ enum StftOutMode {
   OUT_COMPLEX_PUBLIC = 0,   // (n_seq, bins, frames, 2)   -- reference layout of `stft`
   OUT_POWER_PUBLIC = 1,     // (n_seq, bins, frames)      -- reference layout of `Spectrogram`
   OUT_POWER_ROWS = 2,       // |X|^p in "power tiles": the swizzled tensor-core operand layout (below)
-  OUT_MEL_FUSED = 3         // |X|^p contracted with a two-band filterbank inside the kernel (bandplan.cuh) [+ dB]
+  OUT_MEL_FUSED = 3,        // |X|^p contracted with a two-band filterbank inside the kernel (bandplan.cuh) [+ dB]
+  OUT_MEL_FUSED_PEERS = 4   // the same, every frame's bands stored into the output buffers of all ranks of the box (peers.cu)
 };
+constexpr int kMaxPeers = 8;           // GPUs of one NVSwitch box
 
 struct StftParams {
   const float* x;          // (n_seq, n_samples), rows seq_stride apart
@@ -35,6 +37,11 @@ struct StftParams {
   int band_fast, band_off_fast;   // per-lane 4 x 4 list form present (<= 128 bands, <= 4 entries), its byte offset
   float amin, log10_ref;
   int64_t out_seq_stride, out_t_stride, out_band_stride;
+  // OUT_MEL_FUSED_PEERS only: base of every rank's full output (its own included, peer-mapped pointers for the
+  // others); `out` is unused and the strides above address the full (all ranks) tensor from peer_seq0 on
+  float* peer_out[kMaxPeers];
+  int n_peers;
+  int64_t peer_seq0;       // first sequence of this rank inside the full output
 };
 
 // Power tiles (OUT_POWER_ROWS): frames are grouped in tiles of 128; for each tile and each 32-bin slice the

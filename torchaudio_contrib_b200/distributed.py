@@ -4,11 +4,20 @@ split contiguously across ranks, no data-path collective; an optional all-gather
 Every (batch, channel) sequence is independent (reference functional.py:89-91 flattens all leading
 dims into one batch), so rank r of W simply owns a contiguous range of batch items.  The only
 collective is the optional `all_gather_output`, NCCL over NVLink on GPUs (gloo in the CPU tests).
+
+`PeerGatheredOutput` is the same gather done by the mel kernel itself: every rank's
+full output buffer is mapped into every other rank (CUDA IPC), `PreparedMelspectrogram.gather_into`
+stores each frame's bands into all of them over NVLink while it computes, and one flag barrier
+(`tac_peer_barrier`) replaces the collective.  torch.distributed only carries the 64-byte handles.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_batch", "all_gather_output"]
+from . import _cabi
+
+__all__ = ["shard_range", "shard_batch", "all_gather_output", "PeerGatheredOutput"]
 
 
 def shard_range(n_items, rank, world):
@@ -52,3 +61,114 @@ def all_gather_output(local_out, n_items, group=None):
     buf = torch.empty((world * biggest,) + tail, dtype=local_out.dtype, device=local_out.device)
     dist.all_gather_into_tensor(buf, padded, group=group)
     return torch.cat([buf[r * biggest:r * biggest + sizes[r]] for r in range(world)], dim=0)
+
+
+class _PeerBlock(object):
+    """Owner of one tac_peer_alloc allocation, exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, shape, device):
+        self.shape = tuple(int(d) for d in shape)
+        n = 1
+        for d in self.shape:
+            n *= d
+        self.device = device
+        self.base = ctypes.c_void_p()
+        self.handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.lib().tac_peer_alloc(4 * n, ctypes.byref(self.base), ctypes.cast(self.handle, ctypes.c_void_p)))
+        self.payload = self.base.value + 128                 # TAC_PEER_HEADER_BYTES
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self.payload, False),
+                                         "version": 2, "strides": None}
+
+    def __del__(self):
+        base, self.base = getattr(self, "base", None), None
+        if base is not None and base.value:
+            try:
+                with torch.cuda.device(self.device):
+                    _cabi.lib().tac_peer_free(base)
+            except Exception:                                 # interpreter shutdown
+                pass
+
+
+class PeerGatheredOutput(object):
+    """The full `(n_items, ...)` output of a batch-sharded call, resident on every rank and written by
+    every rank's kernel directly (no collective on the data path).
+
+        buf = PeerGatheredOutput((B, C, frames, num_bands), device)        # collective: all ranks construct it
+        prep.gather_into(x_local, buf)                                     # kernel stores to all ranks
+        buf.barrier()                                                      # every rank's frames have landed
+        full = buf.tensor                                                  # (B, C, frames, num_bands) on this rank
+
+    `barrier()` is stream-ordered (a kernel that publishes a flag to every peer and waits for theirs).
+    Call it a second time after consuming `tensor` and before the next `gather_into` if ranks run at
+    different paces (a fast rank would otherwise overwrite what a slow rank is still reading), or
+    alternate between two buffers.  All ranks must be processes on GPUs of one box."""
+
+    def __init__(self, shape, device, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("PeerGatheredOutput needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise NotImplementedError("PeerGatheredOutput: %d ranks; peer stores cover the 8 GPUs of one box" % self.world)
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._own = _PeerBlock(shape, self.device)
+        self.tensor = torch.as_tensor(self._own, device=self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(self._own.handle), group=group)
+        self._bases = []
+        lib = _cabi.lib()
+        failure = None
+        try:
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self._bases.append(self._own.base.value)
+                        continue
+                    mapped = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                    _cabi.check(lib.tac_peer_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(mapped)))
+                    self._bases.append(mapped.value)
+        except Exception as exc:                               # tell the others instead of leaving them in a collective
+            failure = "rank %d: %s" % (self.rank, exc)
+        failures = [None] * self.world
+        dist.all_gather_object(failures, failure, group=group)   # also: every rank has mapped every buffer
+        failures = [f for f in failures if f]
+        if failures:
+            raise RuntimeError("PeerGatheredOutput: mapping peer memory failed (%s)" % "; ".join(failures))
+        self.base_array = (ctypes.c_void_p * self.world)(*self._bases)
+        self.payload_array = (ctypes.c_void_p * self.world)(*[b + 128 for b in self._bases])
+        self.epoch = 0
+
+    def barrier(self, timeout_s=20.0):
+        """Enqueue the flag barrier on the current stream: after it, every rank's stores issued before its own
+        `barrier()` call are visible in this rank's `tensor`."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().tac_peer_barrier(ctypes.cast(self.base_array, ctypes.c_void_p), self.world, self.rank,
+                                                     self.epoch, float(timeout_s), _cabi.stream_ptr(self.device)))
+
+    def check(self):
+        """Synchronise and raise if a barrier gave up waiting for a peer."""
+        flag = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().tac_peer_timed_out(ctypes.c_void_p(self._own.base.value), ctypes.byref(flag)))
+        if flag.value:
+            raise RuntimeError("PeerGatheredOutput: a barrier timed out waiting for a peer rank")
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then release this rank's (after every peer has unmapped it)."""
+        if self._bases is None:
+            return
+        torch.cuda.synchronize(self.device)
+        lib = _cabi.lib()
+        with torch.cuda.device(self.device):
+            for r, b in enumerate(self._bases):
+                if r != self.rank:
+                    _cabi.check(lib.tac_peer_close(ctypes.c_void_p(b)))
+        self._bases = None
+        dist.barrier(group=self.group)
+        self.tensor = None
+        self._own = None

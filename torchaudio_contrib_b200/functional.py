@@ -501,6 +501,34 @@ class PreparedMelspectrogram(object):
                              ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out.transpose(-2, -1) if self.frame_major else out
 
+    def gather_into(self, x, gathered, item_offset=None):
+        """Batch-sharded call (BASELINE config 4): compute this rank's `x` and store the result into the full
+        output of EVERY rank (`gathered`: a `distributed.PeerGatheredOutput` of shape
+        `(total_items,) + out_shape[1:]`) from the kernel's epilogue, over NVLink -- the all-gather of SURVEY 8(e)
+        without a collective.  `item_offset`: this rank's first batch item in the full output (default:
+        `shard_range` of equal shards).  Follow with `gathered.barrier()`.  One-kernel path only."""
+        if not self.fused:
+            raise NotImplementedError("gather_into: only the one-kernel mel path (fft_length 2048, triangular filterbank) "
+                                      "stores to peer buffers")
+        if tuple(x.shape) != self.shape or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            raise RuntimeError("PreparedMelspectrogram: expected contiguous float32 x %s on %s" % (self.shape, self.device))
+        if len(self.shape) < 2:
+            raise RuntimeError("gather_into: x needs a leading batch dimension to shard")
+        full = tuple(gathered.tensor.shape)
+        if len(full) != len(self.out_shape) or full[1:] != self.out_shape[1:] or gathered.device != self.device:
+            raise RuntimeError("gather_into: gathered buffer %s does not match (*,) + %s" % (full, self.out_shape[1:]))
+        if item_offset is None:
+            item_offset = gathered.rank * self.shape[0]
+        if item_offset < 0 or item_offset + self.shape[0] > full[0]:
+            raise RuntimeError("gather_into: items [%d, %d) outside the gathered batch of %d"
+                               % (item_offset, item_offset + self.shape[0], full[0]))
+        seq_per_item = self.n_seq // max(self.shape[0], 1)
+        _cabi.check(_cabi.lib().tac_melspec_banded_peers_f32(
+            _cabi.ptr(x), *self._head, ctypes.cast(gathered.payload_array, ctypes.c_void_p), gathered.world,
+            int(item_offset) * seq_per_item, int(self.frame_major),
+            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return gathered.tensor.transpose(-2, -1) if self.frame_major else gathered.tensor
+
 
 # ------------------------------------------------------------------------------------------------
 # a7 / a8: mu-law

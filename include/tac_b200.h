@@ -167,6 +167,33 @@ int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64_t n_sample
                                  float* const* peer_out, int n_peers, int64_t seq_offset,
                                  int frame_major, void* stream);
 
+/* ---- N4 / H7: backward passes (the reference is differentiable w.r.t. the waveform) ---------
+ * tac_stft_backward_f32: adjoint of tac_stft_f32.  grad_out: (n_seq, bins, frames, 2) contiguous;
+ * grad_x: (n_seq, n_samples) contiguous, overwritten.
+ * tac_spectrogram_backward_f32: adjoint of tac_spectrogram_f32 (stft then |.|^power); the spectrum
+ * is recomputed from x.  grad_out: (n_seq, bins, frames) contiguous.
+ * tac_filterbank_backward_f32: adjoint of the contraction of functional.py:183-184 w.r.t. its
+ * input: grad_spec[s,k,t] = sum_m grad_y[s,m,t] fb[k,m]; grad_y is addressed through element
+ * strides (so the reference's transposed view needs no copy), fb_dev: (n_bins, n_bands) row-major,
+ * grad_spec: (n_seq, n_bins, frames) contiguous.
+ * tac_amplitude_to_db_backward_f32 / tac_complex_norm_backward_f32: pointwise adjoints of
+ * functional.py:291-296 and :126-128 (x, z: the forward inputs). */
+int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_samples,
+                          const float* window, int n_fft, int hop, int center, int pad_mode,
+                          int normalized, int onesided, float* grad_x, void* stream);
+int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                                 const float* window, int n_fft, int hop, int center, int pad_mode,
+                                 int normalized, int onesided, float power,
+                                 const float* grad_out, float* grad_x, void* stream);
+int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band,
+                                int64_t stride_frame, const float* fb_dev, int64_t n_seq,
+                                int64_t frames, int n_bins, int n_bands, float* grad_spec,
+                                void* stream);
+int tac_amplitude_to_db_backward_f32(const float* x, const float* grad_out, int64_t n, float amin,
+                                     float* grad_x, void* stream);
+int tac_complex_norm_backward_f32(const float* z, const float* grad_out, int64_t n, float power,
+                                  float* grad_z, void* stream);
+
 /* ---- a7: mu_law_encoding (functional.py:317-335) ----------------------------------------
  * The quantiser is evaluated as a table of decision levels: thresholds[j] is the smallest
  * float whose code is >= idx_min + j (thresholds[0] = -inf); |x| > x_limit or NaN gives

@@ -112,12 +112,94 @@ def widen(ref, oc):
     print("widening fixtures reproduce under oracle.ref_chain")
 
 
+def grads(ref, oc):
+    """Fixtures of the backward passes: d loss / d input of the UNMODIFIED reference under torch
+    autograd for a fixed upstream gradient, and the check that oracle.ref_chain's autograd gives the same bits.
+    `python oracle/gen_golden.py grads` writes tests/golden/grads.npz only."""
+    g = torch.Generator().manual_seed(20261018)
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g)
+
+    blob = {}
+
+    def record(tag, x, run_ref, run_oc):
+        xr = x.clone().requires_grad_(True)
+        with _shimmed(ref):
+            yr = run_ref(xr)
+        gy = randn(*yr.shape)
+        (gxr,) = torch.autograd.grad(yr, xr, gy)
+        xo = x.clone().requires_grad_(True)
+        yo = run_oc(xo)
+        (gxo,) = torch.autograd.grad(yo, xo, gy)
+        _same(yr.detach(), yo.detach(), "grads/%s forward" % tag)
+        _same(gxr, gxo, "grads/%s backward" % tag)
+        blob[tag + "_x"] = x.numpy()
+        blob[tag + "_gy"] = gy.numpy()
+        blob[tag + "_gx"] = gxr.numpy()
+
+    x = randn(2, 2, 3000)
+    stft_cases = {
+        "stft_512_128": dict(fft_length=512, hop_length=128),
+        "stft_winlen_norm": dict(fft_length=256, hop_length=64, win_length=200, normalized=True),
+        "stft_nocenter": dict(fft_length=512, hop_length=100, center=False),
+        "stft_constant": dict(fft_length=256, hop_length=64, pad_mode='constant'),
+        "stft_replicate": dict(fft_length=256, hop_length=64, pad_mode='replicate'),
+        "stft_circular": dict(fft_length=256, hop_length=64, pad_mode='circular'),
+        "stft_twosided": dict(fft_length=128, hop_length=32, onesided=False),
+        "stft_2048": dict(fft_length=2048, hop_length=512),
+    }
+    for tag, kw in stft_cases.items():
+        win = torch.hann_window(kw.get("win_length", kw["fft_length"]))
+        record(tag, x, lambda t, kw=kw, win=win: ref.stft(t, window=win, **kw), lambda t, kw=kw, win=win: oc.stft(t, window=win, **kw))
+    for power in (1.0, 2.0, 0.7):
+        tag = "spec_p%s" % ("%g" % power).replace(".", "_")
+        record(tag, x, lambda t, power=power: ref.Spectrogram(fft_length=512, hop_length=128, power=power)(t),
+               lambda t, power=power: oc.spectrogram(t, 512, 128, power=power))
+    record("spec_twosided", x, lambda t: ref.Spectrogram(fft_length=128, hop_length=32, onesided=False, power=2.0)(t),
+           lambda t: oc.spectrogram(t, 128, 32, onesided=False, power=2.0))
+
+    x = randn(2, 2, 12000)
+    record("mel_2048", x, lambda t: ref.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512)(t),
+           lambda t: oc.melspectrogram(t, 128, 16000, fft_length=2048, hop_length=512))
+    db = ref.AmplitudeToDb()
+    record("mel_2048_db", x,
+           lambda t: db(ref.Melspectrogram(num_mels=128, sample_rate=48000, fft_length=2048, hop_length=512)(t)),
+           lambda t: oc.melspectrogram(t, 128, 48000, to_db=True, fft_length=2048, hop_length=512))
+    record("mel_1024_64", x, lambda t: ref.Melspectrogram(num_mels=64, sample_rate=22050, fft_length=1024, hop_length=256)(t),
+           lambda t: oc.melspectrogram(t, 64, 22050, fft_length=1024, hop_length=256))
+
+    # the separate stages
+    z = randn(2, 65, 40, 2)
+    z[0, 0, 0] = 0.0                                                        # |z| = 0: torch.norm's subgradient is 0
+    for power in (1.0, 2.0, 0.5):
+        tag = "cnorm_p%s" % ("%g" % power).replace(".", "_")
+        if power < 1.0:
+            zz = z.clone()
+            zz[0, 0, 0] = 1.0                                               # 0^(p-1) is inf for p < 1: keep the fixture finite
+        else:
+            zz = z
+        record(tag, zz, lambda t, power=power: ref.complex_norm(t, power), lambda t, power=power: oc.complex_norm(t, power))
+    fb = randn(65, 20)
+    blob["fb_dense"] = fb.numpy()
+    spec = randn(3, 2, 65, 50).abs()
+    record("fbank_dense", spec, lambda t: ref.apply_filterbank(t, fb), lambda t: oc.apply_filterbank(t, fb))
+    amp = randn(4, 30, 70)
+    amp[0, 0, :8] = torch.tensor([0.0, 1e-5, -1e-5, 3.1622776e-4, 3.2e-4, -3.2e-4, 1.0, -2.0])   # around sqrt(amin)
+    record("todb", amp, lambda t: ref.amplitude_to_db(t, ref=1.0, amin=1e-7), lambda t: oc.amplitude_to_db(t, 1.0, 1e-7))
+    _save("grads.npz", **blob)
+    print("gradient fixtures reproduce under oracle.ref_chain autograd")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
     ref = _load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "widen":
         widen(ref, oc)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":
+        grads(ref, oc)
         return
     g = torch.Generator().manual_seed(20260925)
 

@@ -1,0 +1,326 @@
+// Backward passes of the hot path (the reference is differentiable w.r.t. the waveform through
+// torch.stft, torch.norm/.pow, torch.matmul and the dB chain -- functional.py:99-107, :126-128, :183-184, :291-296).
+//
+//   stft_backward_kernel        d loss / d waveform from d loss / d stft (complex) or from d loss / d |stft|^p
+//                               (the spectrum is recomputed from the waveform instead of being saved: 164 MB at
+//                               config 2); one CTA per frame, any power-of-two n_fft, both through the Stockham
+//                               FFT of fft_stockham.cuh.  The frame's gradient is scattered with atomicAdd through
+//                               the same index map the forward pass gathers through (adjoint of the centre padding).
+//   filterbank_backward_kernel  d loss / d spec[k, t] = sum_m d loss / d y[m, t] * fb[k, m]
+//   pointwise                   amplitude_to_db and complex_norm
+//
+// Maths of the first: X_k = sum_n x_n w_n e^{-i theta}, theta = 2 pi k n / N, k = 0 .. N/2 (onesided).  With
+// G_k = dL/dRe X_k + i dL/dIm X_k:  dL/d(x_n w_n) = Re sum_k G_k e^{+i theta}.  Put H_0 = Re G_0, H_{N/2} = Re G_{N/2},
+// H_k = G_k / 2 otherwise, extend Hermitian: the sum is the inverse real FFT y = sum_{k < N} H_k e^{+i theta}, evaluated
+// as one complex inverse FFT of size C = N/2:  Zt_k = (H_k + conj H_{C-k}) + i e^{+2 pi i k / N} (H_k - conj H_{C-k}),
+// z = IFFT_C(Zt), y_{2n} = Re z_n, y_{2n+1} = Im z_n; and IFFT(v) = conj(FFT(conj v)).
+// For |X|^p outputs G_k = g_k p |X_k|^(p-2) X_k (0 where X_k = 0); two-sided outputs fold bin N-k onto k first.
+#include <math.h>
+
+#include "fft_stockham.cuh"
+#include "stft_params.cuh"
+#include "tac_common.cuh"
+
+namespace tac {
+
+constexpr int kBwdThreads = 256;
+
+struct StftBwdParams {
+  StftParams f;            // geometry of the forward call (x may be null in complex mode)
+  const float* grad_out;   // complex mode: (n_seq, bins, frames, 2); power mode: (n_seq, bins, frames); contiguous
+  float* grad_x;           // (n_seq, n_samples) contiguous, zeroed before the launch
+  int power_mode;          // -1: gradient of the complex spectrum; 2 / 1 / 0 as in the forward kernels
+  float power;
+};
+
+static size_t bwd_smem_bytes(int n_fft) {
+  const size_t c = (size_t)n_fft / 2;
+  return sizeof(float2) * (2 * c + (c + 1) + c / 2 + (c + 1)) + sizeof(float) * (size_t)n_fft + 16;
+}
+
+__global__ void __launch_bounds__(kBwdThreads) stft_backward_kernel(const StftBwdParams bp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const StftParams& p = bp.f;
+  const int n_fft = p.n_fft, C = n_fft >> 1;
+  float2* buf_a = reinterpret_cast<float2*>(smem_raw);
+  float2* buf_b = buf_a + C;
+  float2* spec = buf_b + C;                // C + 1 bins: X, then H
+  float2* tw_c = spec + C + 1;             // W_C^m, m < C/2
+  float2* tw_n = tw_c + (C >> 1);          // W_N^k, k <= C
+  float* win = reinterpret_cast<float*>(tw_n + C + 1);      // window * scale (no 1/2: see the untangling below)
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < n_fft; i += kBwdThreads) win[i] = p.window[i] * p.scale;
+  for (int i = tid; i < (C >> 1); i += kBwdThreads) {
+    float sn, cs;
+    sincospif(-2.0f * (float)i / (float)C, &sn, &cs);
+    tw_c[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i <= C; i += kBwdThreads) {
+    float sn, cs;
+    sincospif(-2.0f * (float)i / (float)n_fft, &sn, &cs);
+    tw_n[i] = make_float2(cs, sn);
+  }
+  __syncthreads();
+
+  const int64_t plane = p.frames;                                      // elements between consecutive bins of grad_out
+  for (int64_t g = p.g0 + blockIdx.x; g < p.g1; g += gridDim.x) {
+    const int64_t seq = g / p.frames, t = g - seq * p.frames, start = t * p.hop - p.pad;
+    const int64_t gbase = seq * p.bins * plane + t;                   // grad_out[seq, 0, t]
+
+    if (bp.power_mode >= 0) {
+      // ---- recompute X_k of this frame (same arithmetic as stft_generic_kernel) ----
+      const float* row = p.x + seq * p.seq_stride;
+      for (int n = tid; n < C; n += kBwdThreads) {
+        const float x0 = fetch_padded(row, start + 2 * n, p.n_samples, p.pad_mode);
+        const float x1 = fetch_padded(row, start + 2 * n + 1, p.n_samples, p.pad_mode);
+        buf_a[n] = make_float2(0.5f * x0 * win[2 * n], 0.5f * x1 * win[2 * n + 1]);
+      }
+      __syncthreads();
+      const float2* z_fft = stockham_forward<kBwdThreads>(buf_a, buf_b, tw_c, C, tid);
+      for (int k = tid; k <= C; k += kBwdThreads) {
+        const float2 z = z_fft[k & (C - 1)];
+        const float2 q = z_fft[(C - k) & (C - 1)];
+        const float a = z.x + q.x, b = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+        const float2 w = tw_n[k];
+        const float xr = fmaf(w.x, gs, fmaf(-w.y, h, a));
+        float xi = fmaf(w.x, h, fmaf(w.y, gs, b));
+        if (k == 0 || k == C) xi = 0.0f;
+        // G_k = g_k p |X|^(p-2) X  (two-sided: bin N - k holds conj X_k, its gradient folds onto k)
+        float gk = __ldg(bp.grad_out + gbase + (int64_t)k * plane);
+        if (!p.onesided && k > 0 && k < C) gk += __ldg(bp.grad_out + gbase + (int64_t)(n_fft - k) * plane);
+        float coef;
+        if (bp.power_mode == 2) {
+          coef = 2.0f * gk;
+        } else {
+          const float n2 = xr * xr + xi * xi;
+          if (n2 > 0.0f) coef = (bp.power_mode == 1) ? gk * rsqrtf(n2) : gk * bp.power * powf(n2, 0.5f * bp.power - 1.0f);
+          else coef = 0.0f;
+        }
+        spec[k] = make_float2(coef * xr, coef * xi);
+      }
+    } else {
+      const float2* go = reinterpret_cast<const float2*>(bp.grad_out);
+      for (int k = tid; k <= C; k += kBwdThreads) {
+        float2 gk = __ldg(go + gbase + (int64_t)k * plane);
+        if (!p.onesided && k > 0 && k < C) {                         // Re(G_k e^{i th} + G_{N-k} e^{-i th}) = Re((G_k + conj G_{N-k}) e^{i th})
+          const float2 gm = __ldg(go + gbase + (int64_t)(n_fft - k) * plane);
+          gk.x += gm.x;
+          gk.y -= gm.y;
+        }
+        spec[k] = gk;
+      }
+    }
+    __syncthreads();
+    // ---- H_k, then conj(Zt_k) into buf_a ----
+    for (int k = tid; k < C; k += kBwdThreads) {
+      float2 hk = spec[k], hc = spec[C - k];
+      if (k == 0) {
+        hk = make_float2(hk.x, 0.0f);                                // H_0 = Re G_0, H_C = Re G_C
+        hc = make_float2(hc.x, 0.0f);
+      } else {
+        hk = make_float2(0.5f * hk.x, 0.5f * hk.y);
+        hc = make_float2(0.5f * hc.x, 0.5f * hc.y);
+      }
+      // s = H_k + conj H_{C-k},  d = H_k - conj H_{C-k},  Zt = s + i conj(W_N^k) d   (tw_n holds W_N^k = e^{-2 pi i k / N})
+      const float sx = hk.x + hc.x, sy = hk.y - hc.y, dx = hk.x - hc.x, dy = hk.y + hc.y;
+      const float2 w = tw_n[k];
+      const float ex = w.x * dx + w.y * dy, ey = w.x * dy - w.y * dx;            // conj(w) * d
+      buf_a[k] = make_float2(sx - ey, -(sy + ex));                              // conj(s + i e)
+    }
+    __syncthreads();
+    const float2* r = stockham_forward<kBwdThreads>(buf_a, buf_b, tw_c, C, tid);   // z_n = conj(r_n)
+    float* grow = bp.grad_x + seq * p.n_samples;
+    const int n_samples = (int)p.n_samples;
+    for (int n = tid; n < C; n += kBwdThreads) {
+      const float2 v = r[n];
+      const float y0 = v.x * win[2 * n], y1 = -v.y * win[2 * n + 1];
+      const int s0 = (int)start + 2 * n, s1 = s0 + 1;
+      const bool in0 = s0 >= 0 && s0 < n_samples, in1 = s1 >= 0 && s1 < n_samples;
+      if (in0 || p.pad_mode != 1) atomicAdd(grow + padded_index(s0, n_samples, p.pad_mode), y0);
+      if (in1 || p.pad_mode != 1) atomicAdd(grow + padded_index(s1, n_samples, p.pad_mode), y1);
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_stft_backward(StftBwdParams& bp, cudaStream_t stream) {
+  const StftParams& p = bp.f;
+  TAC_CUDA_OK(cudaMemsetAsync(bp.grad_x, 0, (size_t)p.n_seq * p.n_samples * sizeof(float), stream));
+  const int64_t n_frames = p.g1 - p.g0;
+  if (n_frames <= 0) return TAC_OK;
+  const size_t smem = bwd_smem_bytes(p.n_fft);
+  TAC_CUDA_OK(cudaFuncSetAttribute(stft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)((200 * 1024) / (smem + 1024));
+  const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+  const int grid = (int)(n_frames < cap ? n_frames : cap);
+  LaunchProbe probe(KIND_STFT, stream);
+  stft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// filterbank: grad_spec[s, k, t] = sum_m grad_y[s, m, t] * fb[k, m]        (adjoint of functional.py:183-184)
+// One CTA per (sequence, 64 frames): the grad_y tile (n_bands x 64) sits in shared memory, thread (ty, tx) walks bins
+// ty, ty + 4, ... for frame tx; fb[k, :] is read as a warp-wide broadcast and rows of zeros (outside the band range
+// of bin k) are skipped through the per-bin [lo, hi) range computed once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFbTileT = 64;
+constexpr int kFbThreads = 256;
+
+__global__ void __launch_bounds__(kFbThreads)
+filterbank_backward_kernel(const float* __restrict__ grad_y, int64_t sy_seq, int64_t sy_band, int64_t sy_frame,
+                           const float* __restrict__ fb, int n_bins, int n_bands, int64_t frames, int tiles_per_seq,
+                           int64_t n_jobs, float* __restrict__ grad_spec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                       // [n_bands][kFbTileT + 1]
+  int2* range = reinterpret_cast<int2*>(tile + (size_t)n_bands * (kFbTileT + 1));   // [n_bins]: non-zero columns [lo, hi)
+  const int tid = threadIdx.x;
+  for (int k = tid; k < n_bins; k += kFbThreads) {
+    int lo = n_bands, hi = 0;
+    for (int m = 0; m < n_bands; ++m)
+      if (__ldg(fb + (int64_t)k * n_bands + m) != 0.0f) {
+        lo = m < lo ? m : lo;
+        hi = m + 1;
+      }
+    range[k] = make_int2(lo, hi);
+  }
+  for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int64_t seq = job / tiles_per_seq;
+    const int64_t t0 = (job - seq * tiles_per_seq) * kFbTileT;
+    __syncthreads();                                                      // previous tile consumed / ranges written
+    const float* gy = grad_y + seq * sy_seq;
+    if (sy_band == 1) {                                                   // frame-major gradient: bands are contiguous
+      for (int i = tid; i < n_bands * kFbTileT; i += kFbThreads) {
+        const int tt = i / n_bands, m = i - tt * n_bands;
+        tile[m * (kFbTileT + 1) + tt] = (t0 + tt < frames) ? __ldg(gy + (t0 + tt) * sy_frame + m) : 0.0f;
+      }
+    } else {
+      for (int i = tid; i < n_bands * kFbTileT; i += kFbThreads) {
+        const int m = i / kFbTileT, tt = i - m * kFbTileT;
+        tile[m * (kFbTileT + 1) + tt] = (t0 + tt < frames) ? __ldg(gy + (int64_t)m * sy_band + (t0 + tt) * sy_frame) : 0.0f;
+      }
+    }
+    __syncthreads();
+    const int tx = tid & (kFbTileT - 1), ty = tid / kFbTileT;
+    const bool live = t0 + tx < frames;
+    float* out = grad_spec + seq * (int64_t)n_bins * frames + t0 + tx;
+    for (int k = ty; k < n_bins; k += kFbThreads / kFbTileT) {
+      const int2 rg = range[k];
+      const float* w = fb + (int64_t)k * n_bands;
+      float acc = 0.0f;
+      for (int m = rg.x; m < rg.y; ++m) acc = fmaf(__ldg(w + m), tile[m * (kFbTileT + 1) + tx], acc);
+      if (live) out[(int64_t)k * frames] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pointwise backward
+// ---------------------------------------------------------------------------------------------------------------
+// amplitude_to_db (functional.py:291-296): y = 10 log10(max(x^2, amin)) - c  ->  dy/dx = 20 / (ln 10 x) where x^2 >= amin
+__global__ void amplitude_to_db_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t n, float amin,
+                                                float* __restrict__ out) {
+  const float k = 8.685889638065035f;                                   // 20 / ln 10
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = (v * v >= amin) ? g[i] * k / v : 0.0f;
+  }
+}
+// complex_norm (functional.py:126-128): n = |z|, y = n^p  ->  dz = g p n^(p-2) z (0 at z = 0)
+__global__ void complex_norm_backward_kernel(const float2* __restrict__ z, const float* __restrict__ g, int64_t n, float power,
+                                             float2* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = z[i];
+    const float n2 = v.x * v.x + v.y * v.y;
+    float c = 0.0f;
+    if (n2 > 0.0f) c = (power == 2.0f) ? 2.0f * g[i] : ((power == 1.0f) ? g[i] * rsqrtf(n2) : g[i] * power * powf(n2, 0.5f * power - 1.0f));
+    out[i] = make_float2(c * v.x, c * v.y);
+  }
+}
+
+static int pointwise_grid(int64_t n) {
+  const int64_t want = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace tac
+
+extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_samples, const float* window, int n_fft,
+                                     int hop, int center, int pad_mode, int normalized, int onesided, float* grad_x,
+                                     void* stream) {
+  using namespace tac;
+  StftBwdParams bp;
+  TAC_REQUIRE(grad_out && grad_x, TAC_ERR_INVALID, "stft_backward: null gradient pointer");
+  const int rc = fill_stft_params(bp.f, grad_x /* placeholder, never read */, n_seq, n_samples, n_samples, window, n_fft, hop,
+                                  center, pad_mode, normalized, onesided);
+  if (rc != TAC_OK) return rc;
+  bp.f.x = nullptr;
+  bp.grad_out = grad_out;
+  bp.grad_x = grad_x;
+  bp.power_mode = -1;
+  bp.power = 1.0f;
+  return launch_stft_backward(bp, as_stream(stream));
+}
+
+extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                                            const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
+                                            int onesided, float power, const float* grad_out, float* grad_x, void* stream) {
+  using namespace tac;
+  StftBwdParams bp;
+  TAC_REQUIRE(grad_out && grad_x, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
+  const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
+  if (rc != TAC_OK) return rc;
+  bp.grad_out = grad_out;
+  bp.grad_x = grad_x;
+  bp.power = power;
+  bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  return launch_stft_backward(bp, as_stream(stream));
+}
+
+extern "C" int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,
+                                           const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands,
+                                           float* grad_spec, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(grad_y && fb_dev && grad_spec, TAC_ERR_INVALID, "filterbank_backward: null pointer");
+  TAC_REQUIRE(n_seq >= 0 && frames >= 0 && n_bins > 0 && n_bands > 0, TAC_ERR_INVALID, "filterbank_backward: bad shape");
+  if (n_seq == 0 || frames == 0) return TAC_OK;
+  const size_t smem = sizeof(float) * (size_t)n_bands * (kFbTileT + 1) + sizeof(int2) * (size_t)n_bins;
+  TAC_REQUIRE(smem <= 200 * 1024, TAC_ERR_UNSUPPORTED, "filterbank_backward: %d bands x %d bins exceed one CTA's shared memory",
+              n_bands, n_bins);
+  TAC_CUDA_OK(cudaFuncSetAttribute(filterbank_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles_per_seq = (int)((frames + kFbTileT - 1) / kFbTileT);
+  const int64_t jobs = n_seq * tiles_per_seq;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  const int grid = (int)(jobs < cap ? jobs : cap);
+  LaunchProbe probe(KIND_MELBANK, as_stream(stream));
+  filterbank_backward_kernel<<<grid, kFbThreads, smem, as_stream(stream)>>>(grad_y, stride_seq, stride_band, stride_frame, fb_dev,
+                                                                           n_bins, n_bands, frames, tiles_per_seq, jobs, grad_spec);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_amplitude_to_db_backward_f32(const float* x, const float* grad_out, int64_t n, float amin, float* grad_x,
+                                                void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0 && (n == 0 || (x && grad_out && grad_x)), TAC_ERR_INVALID, "amplitude_to_db_backward: bad arguments");
+  if (n == 0) return TAC_OK;
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
+  amplitude_to_db_backward_kernel<<<pointwise_grid(n), 256, 0, as_stream(stream)>>>(x, grad_out, n, amin, grad_x);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_complex_norm_backward_f32(const float* z, const float* grad_out, int64_t n, float power, float* grad_z,
+                                             void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0 && (n == 0 || (z && grad_out && grad_z)), TAC_ERR_INVALID, "complex_norm_backward: bad arguments");
+  if (n == 0) return TAC_OK;
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
+  complex_norm_backward_kernel<<<pointwise_grid(n), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(z), grad_out, n,
+                                                                                power, reinterpret_cast<float2*>(grad_z));
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}

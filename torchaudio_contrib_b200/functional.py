@@ -24,6 +24,16 @@ __all__ = [
 # ------------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------------
+def _wants_grad(t):
+    return torch.is_grad_enabled() and isinstance(t, torch.Tensor) and t.requires_grad
+
+
+def _no_param_grad(t, name):
+    if isinstance(t, torch.Tensor) and torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError("%s requires grad: the B200 backward kernels differentiate w.r.t. the signal only "
+                           "(window and filterbank are constants, as the reference's buffers are)" % name)
+
+
 def _forward_only(t, name):
     if torch.is_grad_enabled() and t.requires_grad:
         raise RuntimeError("%s: the B200 kernels are forward-only; call under torch.no_grad() or detach "
@@ -100,7 +110,9 @@ def stft(waveforms, fft_length, hop_length=None, win_length=None, window=None,
     of two in [32, 8192].  Unlike the reference, a missing `window` is created on the input's
     device.  The result is a contiguous tensor of the reference's logical shape.
     """
-    _forward_only(waveforms, "stft")
+    if _wants_grad(waveforms):
+        _no_param_grad(window, "stft: window")
+        return _StftFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided))
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
     win = _frame_window(window, win_length, fft_length, x.device)
@@ -117,7 +129,10 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
                 pad_mode='reflect', normalized=False, onesided=True, power=1.):
     """`Spectrogram(...)(x)` in one kernel: stft then `|.|^power` (layers.py:294-304), the complex
     spectrum never reaches HBM.  Returns `(*, channel, num_freqs, frames)`."""
-    _forward_only(waveforms, "spectrogram")
+    if _wants_grad(waveforms):
+        _no_param_grad(window, "spectrogram: window")
+        return _SpectrogramFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized,
+                                                onesided, power))
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
     win = _frame_window(window, win_length, fft_length, x.device)
@@ -135,7 +150,8 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
 # ------------------------------------------------------------------------------------------------
 def complex_norm(complex_tensor, power=1.0):
     """`(*, 2) -> (*)`: sqrt(re^2 + im^2), then `.pow(power)` (functional.py:116-128)."""
-    _forward_only(complex_tensor, "complex_norm")
+    if _wants_grad(complex_tensor):
+        return _ComplexNormFn.apply(complex_tensor, float(power))
     z = _as_f32_cuda(complex_tensor, "complex_tensor")
     if z.dim() < 1 or z.size(-1) != 2:
         raise RuntimeError("complex_norm: expected a (*, 2) tensor, got %s" % (tuple(z.shape),))
@@ -259,7 +275,9 @@ def apply_filterbank(mag_specgrams, filterbank, _cache=None):
     """`(*, num_freqs, time) x (num_freqs, num_bands) -> (*, num_bands, time)`: contraction over
     the frequency axis (functional.py:172-184) on the tcgen05 tensor cores with 3xTF32 split
     accumulation (csrc/melbank.cu).  Any dense matrix is accepted; zero blocks are skipped."""
-    _forward_only(mag_specgrams, "apply_filterbank")
+    if _wants_grad(mag_specgrams):
+        _no_param_grad(filterbank, "apply_filterbank: filterbank")
+        return _ApplyFilterbankFn.apply(mag_specgrams, filterbank, _cache)
     spec = _as_f32_cuda(mag_specgrams, "mag_specgrams")
     plan = _plan_for(filterbank, spec.device, _cache)
     return _power_mel(spec, False, 1.0, plan, False, 1.0, 1e-7)
@@ -270,7 +288,8 @@ def apply_filterbank(mag_specgrams, filterbank, _cache=None):
 # ------------------------------------------------------------------------------------------------
 def amplitude_to_db(x, ref=1.0, amin=1e-7):
     """`10 * (log10(max(x^2, amin)) - log10(ref))` (functional.py:277-296; note the square)."""
-    _forward_only(x, "amplitude_to_db")
+    if _wants_grad(x):
+        return _AmplitudeToDbFn.apply(x, float(ref), float(amin))
     a = _as_f32_cuda(x, "x")
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):
@@ -406,7 +425,12 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     `matmul(...).transpose(-2, -1)` (functional.py:183-184; a frame's bands are one 512-byte store);
     `layout="contiguous"` returns a contiguous `(*, num_bands, frames)` tensor (4-byte stores, ~9 % slower
     at BASELINE config 2).  The two-kernel path always returns a contiguous tensor."""
-    _forward_only(waveforms, "melspectrogram")
+    if _wants_grad(waveforms):
+        _no_param_grad(window, "melspectrogram: window")
+        _no_param_grad(filterbank, "melspectrogram: filterbank")
+        return _MelspectrogramFn.apply(waveforms, filterbank, dict(
+            fft_length=fft_length, hop_length=hop_length, win_length=win_length, window=window, center=center,
+            pad_mode=pad_mode, normalized=normalized, power=power, to_db=to_db, ref=ref, amin=amin, layout=layout), _cache)
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
     win = _frame_window(window, win_length, fft_length, x.device)
@@ -439,6 +463,175 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
             float(power), _cabi.ptr(plan.blob), plan.num_bands, int(bool(to_db)), float(ref), float(amin),
             _cabi.ptr(ws), ws.numel(), _cabi.ptr(out), _cabi.stream_ptr(x.device)))
     return out.reshape(lead + out.shape[1:])
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 / H7: backward passes (csrc/stft_backward.cu).  The reference is differentiable through torch's
+# operators (functional.py:99-107, :126-128, :183-184, :291-296); these Functions give the same
+# d loss / d signal with hand-written adjoint kernels.  Forward = the kernels above (grad mode is
+# off inside Function.forward, so the public functions take their plain path).
+# ------------------------------------------------------------------------------------------------
+def _grad_f32(g):
+    if g.dtype != torch.float32:
+        g = g.float()
+    return g
+
+
+def _stft_backward_call(x_or_none, grad_out, shape, fft_length, hop_length, win_length, window, center, pad_mode,
+                        normalized, onesided, power):
+    """grad w.r.t. the waveform of `stft` (power None: grad_out (*, bins, frames, 2)) or `spectrogram`."""
+    device = grad_out.device
+    n_samples = int(shape[-1])
+    n_seq = 1
+    for d in shape[:-1]:
+        n_seq *= int(d)
+    hop = fft_length // 4 if hop_length is None else int(hop_length)
+    win = _frame_window(window, win_length, fft_length, device)
+    g = _grad_f32(grad_out).contiguous()
+    gx = torch.empty((n_seq, n_samples), dtype=torch.float32, device=device)
+    lib = _cabi.lib()
+    with torch.cuda.device(device):
+        if power is None:
+            _cabi.check(lib.tac_stft_backward_f32(
+                _cabi.ptr(g), n_seq, n_samples, _cabi.ptr(win), int(fft_length), hop, int(bool(center)),
+                _cabi.PAD_MODES[pad_mode], int(bool(normalized)), int(bool(onesided)), _cabi.ptr(gx), _cabi.stream_ptr(device)))
+        else:
+            flat = x_or_none.reshape(-1, n_samples)
+            _cabi.check(lib.tac_spectrogram_backward_f32(
+                *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized), int(bool(onesided)), float(power),
+                _cabi.ptr(g), _cabi.ptr(gx), _cabi.stream_ptr(device)))
+    return gx.reshape(shape)
+
+
+class _StftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, waveforms, args):
+        ctx.args, ctx.shape, ctx.in_dtype = args, tuple(waveforms.shape), waveforms.dtype
+        return stft(waveforms.detach(), *args)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided = ctx.args
+        gx = _stft_backward_call(None, grad_out, ctx.shape, fft_length, hop_length, win_length, window, center, pad_mode,
+                                 normalized, onesided, None)
+        return gx.to(ctx.in_dtype), None
+
+
+class _SpectrogramFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, waveforms, args):
+        x = _as_f32_cuda(waveforms.detach(), "waveforms")
+        ctx.save_for_backward(x)
+        ctx.args, ctx.shape = args, tuple(waveforms.shape)
+        return spectrogram(x, *args)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided, power = ctx.args
+        return _stft_backward_call(x, grad_out, ctx.shape, fft_length, hop_length, win_length, window, center, pad_mode,
+                                   normalized, onesided, power), None
+
+
+def _complex_norm_backward(z, grad_out, power):
+    g = _grad_f32(grad_out).contiguous()
+    gz = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _cabi.check(_cabi.lib().tac_complex_norm_backward_f32(_cabi.ptr(z), _cabi.ptr(g), g.numel(), float(power),
+                                                              _cabi.ptr(gz), _cabi.stream_ptr(z.device)))
+    return gz
+
+
+class _ComplexNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, complex_tensor, power):
+        z = _as_f32_cuda(complex_tensor.detach(), "complex_tensor")
+        ctx.save_for_backward(z)
+        ctx.power = power
+        return complex_norm(z, power)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (z,) = ctx.saved_tensors
+        return _complex_norm_backward(z, grad_out, ctx.power), None
+
+
+def _filterbank_backward(grad_y, filterbank):
+    """grad_y: (*, num_bands, frames) with any strides in its last two dims -> (*, num_freqs, frames) contiguous."""
+    g = _grad_f32(grad_y)
+    lead = tuple(g.shape[:-2])
+    n_bands, frames = int(g.size(-2)), int(g.size(-1))
+    g3 = g.reshape((-1, n_bands, frames))                 # a view whenever the leading dims are contiguous (the usual case)
+    fb = filterbank.detach().to(device=g.device, dtype=torch.float32).contiguous()
+    if fb.dim() != 2 or fb.size(1) != n_bands:
+        raise RuntimeError("apply_filterbank backward: filterbank %s does not match %d bands" % (tuple(fb.shape), n_bands))
+    out = torch.empty((g3.size(0), fb.size(0), frames), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _cabi.check(_cabi.lib().tac_filterbank_backward_f32(
+            _cabi.ptr(g3), g3.stride(0) if g3.size(0) > 1 else n_bands * frames, g3.stride(1), g3.stride(2), _cabi.ptr(fb),
+            g3.size(0), frames, int(fb.size(0)), n_bands, _cabi.ptr(out), _cabi.stream_ptr(g.device)))
+    return out.reshape(lead + (int(fb.size(0)), frames))
+
+
+class _ApplyFilterbankFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mag_specgrams, filterbank, cache):
+        ctx.filterbank = filterbank
+        return apply_filterbank(mag_specgrams.detach(), filterbank, cache)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return _filterbank_backward(grad_out, ctx.filterbank), None, None
+
+
+def _amplitude_to_db_backward(x, grad_out, amin):
+    g = _grad_f32(grad_out).contiguous()
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().tac_amplitude_to_db_backward_f32(_cabi.ptr(x), _cabi.ptr(g), g.numel(), float(amin),
+                                                                 _cabi.ptr(gx), _cabi.stream_ptr(x.device)))
+    return gx
+
+
+class _AmplitudeToDbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ref, amin):
+        a = _as_f32_cuda(x.detach(), "x")
+        ctx.save_for_backward(a)
+        ctx.amin = amin
+        return amplitude_to_db(a, ref, amin)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (a,) = ctx.saved_tensors
+        return _amplitude_to_db_backward(a, grad_out, ctx.amin), None, None
+
+
+class _MelspectrogramFn(torch.autograd.Function):
+    """Backward of the fused chain: [dB adjoint on the recomputed mel values ->] filterbank adjoint ->
+    spectrogram adjoint (which recomputes the spectrum from the saved waveform).  Nothing but the waveform is
+    saved by the forward pass."""
+
+    @staticmethod
+    def forward(ctx, waveforms, filterbank, kw, cache):
+        x = _as_f32_cuda(waveforms.detach(), "waveforms")
+        ctx.save_for_backward(x)
+        ctx.filterbank, ctx.kw, ctx.cache, ctx.shape = filterbank, kw, cache, tuple(waveforms.shape)
+        return melspectrogram(x, filterbank, _cache=cache, **kw)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        kw = ctx.kw
+        g = grad_out
+        if kw["to_db"]:
+            plain = dict(kw, to_db=False, layout="contiguous")
+            mel = melspectrogram(x, ctx.filterbank, _cache=ctx.cache, **plain)           # (*, bands, frames) contiguous
+            g = _amplitude_to_db_backward(mel, g, kw["amin"])
+        g_spec = _filterbank_backward(g, ctx.filterbank)
+        gx = _stft_backward_call(x, g_spec, ctx.shape, kw["fft_length"], kw["hop_length"], kw["win_length"], kw["window"],
+                                 kw["center"], kw["pad_mode"], kw["normalized"], True, kw["power"])
+        return gx, None, None, None
 
 
 class PreparedMelspectrogram(object):

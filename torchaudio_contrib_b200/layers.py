@@ -265,6 +265,8 @@ class FusedSequential(nn.Sequential):
                                      _cache=fb._plan_cache, **st.stft_kwargs())
                 return y, i + (4 if db is not None else 3)
             return F.spectrogram(x, st.fft_length, onesided=True, power=power, **st.stft_kwargs()), i + 2
+        if F._wants_grad(x):
+            return None                              # child by child: every child has its own backward kernel
         if kind(i, ComplexNorm) and kind(i + 1, ApplyFilterbank):
             fb = mods[i + 1]
             db = mods[i + 2] if kind(i + 2, AmplitudeToDb) else None

@@ -383,10 +383,12 @@ def run_ours(args, rank, world, local):
             with torch.no_grad():
                 def peer_step(i):
                     prepared.gather_into(inputs[i % n_sets], fulls[i % 2])
-                    fulls[i % 2].barrier()
+                    fulls[i % 2].barrier(timeout_s=2.0)
                 for i in range(4):
                     peer_step(i)
                 barrier()
+                for f in fulls:
+                    f.check()                                   # a barrier that timed out (dead peer) ends the leg here
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record()
                 for i in range(args.steps):

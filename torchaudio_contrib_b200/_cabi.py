@@ -10,7 +10,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libtac_b200.so")
+# TAC_B200_LIB: an alternative build of the same library (e.g. the -DTAC_K1_TRACE_BUILD timing build of scripts/)
+LIB_PATH = os.environ.get("TAC_B200_LIB") or os.path.join(_PKG, "lib", "libtac_b200.so")
 
 TAC_OK = 0
 TAC_ERR_INVALID = -1

@@ -254,9 +254,19 @@ __device__ long long g_k1_trace[64];
 #ifdef TAC_K1_TRACE_BUILD
 #define K1_TRACE(i) do { if (p.debug && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_k1_trace[i] = clock64(); } while (0)
 #define K1_TRACE_NEXT() do { K1_TRACE(trace_i); ++trace_i; } while (0)
+// per-warp wall-clock stamps (globaltimer, ns) of every CTA: 0 entry, 1 tables ready, 2 first samples arrived,
+// 3 first frame done, 4 second frame done, 5 last frame done, 6 frames processed
+__device__ unsigned long long g_k1_stamps[160 * 16 * 8];
+__device__ __forceinline__ unsigned long long k1_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define K1_STAMP(i) do { if (p.debug && (threadIdx.x & 31) == 0 && blockIdx.x < 160) g_k1_stamps[(blockIdx.x * 16 + (threadIdx.x >> 5)) * 8 + (i)] = k1_now(); } while (0)
 #else
 #define K1_TRACE(i) do { } while (0)
 #define K1_TRACE_NEXT() do { } while (0)
+#define K1_STAMP(i) do { } while (0)
 #endif
 
 template <int OUT_MODE_T, int PMODE>
@@ -274,22 +284,28 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   K1_TRACE(0);
+  K1_STAMP(0);
 
-  fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
+  // each warp owns its barrier and slab, so its first bulk copy can be issued before the tables are built: the
+  // copy's latency (1.5 us from a cold HBM page, up to 7 us for the unluckiest of 2368 simultaneous copies) then
+  // overlaps the table set-up instead of following it
   uint64_t* bar = s_bar + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  __syncthreads();
-  K1_TRACE(1);
+  __syncwarp();
 #ifdef TAC_K1_TRACE_BUILD
   int trace_i = 2;
+  int stamp_frames = 0;
 #endif
 
   float2* slab = s_slab + warp * kSlabComplex;
   float* slab_f = reinterpret_cast<float*>(slab);
-  const uint32_t step = gridDim.x * kFastWarps;              // frame indices fit 31 bits (checked by the host)
+  // A CTA owns a contiguous chunk of the launch's frames (sizes differ by at most one) and deals it round-robin to
+  // its warps.  (Dealing frame g to warp g % (16 gridDim) made 68 SMs run 9 rounds and 80 SMs 8 at config 2: the
+  // slowest warp finished 15 us after the fastest, measured with the globaltimer stamps of the timing build.)
+  constexpr uint32_t step = kFastWarps;                      // frame indices fit 31 bits (checked by the host)
   const float half_power = 0.5f * p.power;
   uint32_t parity = 0;
   // OUT_MEL_FUSED: this warp's power-spectrum stash, row k1 = bins 32 k1 .. 32 k1 + 31, stride 33
@@ -336,8 +352,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     gather_padded<64, 32>(slab_f, p.x + (int64_t)seq * p.seq_stride, start, (int)p.n_samples, p.pad_mode, lane);
   };
 
-  const uint32_t n_launch = (uint32_t)(p.g1 - p.g0);          // frames of this launch; gi indexes them
-  uint32_t gi = blockIdx.x * kFastWarps + warp;
+  const uint32_t n_all = (uint32_t)(p.g1 - p.g0);            // frames of this launch; gi indexes them
+  const uint32_t per_cta = n_all / gridDim.x, extra = n_all % gridDim.x;
+  const uint32_t chunk0 = blockIdx.x * per_cta + (blockIdx.x < extra ? blockIdx.x : extra);
+  const uint32_t n_launch = chunk0 + per_cta + (blockIdx.x < extra ? 1u : 0u);          // end of this CTA's chunk
+  uint32_t gi = chunk0 + warp;
   const int64_t g_first = p.g0 + gi;
   uint32_t seq = (uint32_t)(g_first / p.frames), t = (uint32_t)(g_first % p.frames);      // once per warp
   bool in_flight = false;
@@ -345,6 +364,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     in_flight = stage_bulk(seq, t, span_cur);
     if (!in_flight) stage_gather(seq, t);
   }
+  fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
+  __syncthreads();
+  K1_TRACE(1);
+  K1_STAMP(1);
 
 #pragma unroll 1
   for (; gi < n_launch; gi += step) {
@@ -359,6 +382,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     K1_TRACE_NEXT();                               // sample data arrived
 #ifdef TAC_K1_TRACE_BUILD
     if (p.debug && blockIdx.x == 0 && lane == 0 && g_k1_trace[40 + warp] == 0) g_k1_trace[40 + warp] = clock64();
+    if (stamp_frames == 0) K1_STAMP(2);
 #endif
     float2 v[32];
     fft2048_front(v, slab, s_win, s_tw1, lane);    // slab free again afterwards: prefetch the next frame
@@ -445,6 +469,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
     }
     if constexpr (OUT_MODE == OUT_MEL_FUSED) band_contract<kPeers>(p, stash, lane, seq, t);
     K1_TRACE_NEXT();                               // frame done
+#ifdef TAC_K1_TRACE_BUILD
+    if (stamp_frames == 0) K1_STAMP(3);
+    if (stamp_frames == 1) K1_STAMP(4);
+    K1_STAMP(5);
+    ++stamp_frames;
+    if (p.debug && lane == 0 && blockIdx.x < 160) g_k1_stamps[(blockIdx.x * 16 + warp) * 8 + 6] = stamp_frames;
+#endif
     if (has_next && !in_flight) stage_gather(seq_next, t_next);
     seq = seq_next;
     t = t_next;
@@ -613,6 +644,37 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
 int dump_k1_trace() {
   long long h[64];
   TAC_CUDA_OK(cudaDeviceSynchronize());
+#ifdef TAC_K1_TRACE_BUILD
+  {
+    static unsigned long long st[160 * 16 * 8];
+    TAC_CUDA_OK(cudaMemcpyFromSymbol(st, g_k1_stamps, sizeof(st)));
+    unsigned long long base = ~0ull;
+    for (int w = 0; w < 160 * 16; ++w) if (st[w * 8] && st[w * 8] < base) base = st[w * 8];
+    const char* names[6] = {"entry", "tables ready", "first samples", "frame 1 done", "frame 2 done", "last frame done"};
+    for (int i = 0; i < 6; ++i) {
+      double mn = 1e30, mx = 0, sum = 0;
+      int n = 0;
+      for (int w = 0; w < 160 * 16; ++w) {
+        if (!st[w * 8] || !st[w * 8 + i]) continue;
+        const double v = (double)(st[w * 8 + i] - base) * 1e-3;
+        mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; ++n;
+      }
+      printf("stamp %-16s warps %4d  min %7.2f  mean %7.2f  max %7.2f us\n", names[i], n, mn, n ? sum / n : 0.0, mx);
+    }
+    int hist[16] = {0};
+    double last_by_frames[16] = {0};
+    for (int w = 0; w < 160 * 16; ++w) {
+      if (!st[w * 8]) continue;
+      const int f = (int)st[w * 8 + 6];
+      if (f < 16) { ++hist[f]; const double v = (double)(st[w * 8 + 5] - base) * 1e-3; if (v > last_by_frames[f]) last_by_frames[f] = v; }
+    }
+    for (int f = 0; f < 16; ++f) if (hist[f]) printf("warps with %2d frames: %4d, latest finish %7.2f us\n", f, hist[f], last_by_frames[f]);
+    // CTA 0: per-warp finish times
+    printf("CTA 0 per-warp last-frame-done:");
+    for (int w = 0; w < 16; ++w) printf(" %.1f", (double)(st[w * 8 + 5] - base) * 1e-3);
+    printf("\n");
+  }
+#endif
   TAC_CUDA_OK(cudaMemcpyFromSymbol(h, g_k1_trace, sizeof(h)));
   printf("k1 trace (cycles since kernel entry of CTA 0):");
   for (int i = 0; i < 40; ++i) printf(" %lld", h[i] ? h[i] - h[0] : -1);

@@ -15,7 +15,7 @@ import torch
 from torchaudio_contrib_b200 import _cabi
 from torchaudio_contrib_b200 import functional as F
 
-STRIDE, NYQ, ZERO, FLOATS = 33, 32 * 33, 1060, 1064
+STRIDE, NYQ, ZERO, FLOATS, SHIFT_ROW = 33, 32 * 33 - 1, 1060, 1064, 17
 OFF_W, OFF_META, OFF_COMB = 32, 32 + 8192, 32 + 8192 + 512
 
 
@@ -51,9 +51,12 @@ def kernel_model(blob, handle, power_rows, n_bands):
         stash = np.full(FLOATS, np.nan, dtype=np.float32)
         stash[ZERO] = 0.0
         for k1 in range(32):                                   # emit: lane = column, k1 = row
-            stash[k1 * STRIDE:k1 * STRIDE + 32] = p[32 * k1:32 * k1 + 32]
+            stash[k1 * STRIDE + 1:k1 * STRIDE + 32] = p[32 * k1 + 1:32 * k1 + 32]
+            stash[k1 * STRIDE - (1 if k1 >= SHIFT_ROW else 0)] = p[32 * k1]     # column 0 of rows >= 17 sits one float lower
         stash[NYQ] = p[1024]
         pw = np.stack([stash[l * STRIDE:l * STRIDE + 32].copy() for l in range(32)])
+        for l in range(SHIFT_ROW, 32):
+            pw[l, 0] = stash[l * STRIDE - 1]
         p_last = stash[NYQ]
         stash[:] = np.nan                                      # anything read later must have been stored
         stash[ZERO] = 0.0

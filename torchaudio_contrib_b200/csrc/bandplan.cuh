@@ -30,8 +30,13 @@ namespace tac {
 constexpr uint32_t kBandPlanMagic = 0x7ac0ba2du;
 constexpr int kBandBins = 1025;                    // n_fft = 2048
 constexpr int kStashStride = 33;                   // stash row stride (floats): odd -> conflict-free both ways
-constexpr int kStashNyquist = 32 * kStashStride;   // where bin 1024 sits
-constexpr int kStashEnd31 = kStashNyquist + 1;     // end-of-run pair of lane 31 (its row's last columns are taken)
+// Column 0 of rows 17 .. 32 (bins 544, 576 .. 1024) sits ONE FLOAT BELOW its natural place, in the padding slot of
+// the previous row: those 16 values are all written by lane 0 as the mirrors of its bins 32 k1, in the same store
+// instruction in which lane L >= 1 writes (row 31 - k1, column 32 - L); at the natural address lane 0 and lane 31 hit
+// the same bank every step (16 extra shared-memory wavefronts per frame).
+constexpr int kStashShiftRow = 17;
+constexpr int kStashNyquist = 32 * kStashStride - 1;   // where bin 1024 sits (row 32, column 0, shifted)
+constexpr int kStashEnd31 = 32 * kStashStride + 1;     // end-of-run pair of lane 31 (its row's last columns are taken)
 constexpr int kStashZero = 1060;                   // a float that is always 0 (padding entries of `comb`)
 constexpr int kStashFloats = 1064;                 // per warp
 constexpr int kBandMaxComb = 16;

@@ -155,7 +155,8 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
   }
   float pw[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) pw[i] = stash[lane * kStashStride + i];     // lane <- bins 32 lane + i
+  for (int i = 1; i < 32; ++i) pw[i] = stash[lane * kStashStride + i];     // lane <- bins 32 lane + i
+  pw[0] = stash[lane * kStashStride - (lane >= kStashShiftRow ? 1 : 0)];   // column 0 of rows >= 17: see bandplan.cuh
   const float p_last = (lane == 31) ? stash[kStashNyquist] : 0.0f;
   __syncwarp();                                    // stash consumed: it now takes the partial sums
   const uint4 meta = __ldg(reinterpret_cast<const uint4*>(p.band_plan + kBandOffMeta) + lane);
@@ -214,7 +215,8 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {                  // byte offsets into the stash; unused entries point at the zero
       const float a = *reinterpret_cast<const float*>(sb + ci[j].x), b = *reinterpret_cast<const float*>(sb + ci[j].y);
-      const float c = *reinterpret_cast<const float*>(sb + ci[j].z), d = *reinterpret_cast<const float*>(sb + ci[j].w);
+      const float c = *reinterpret_cast<const float*>(sb + ci[j].z);
+      const float d = (p.band_cmax > 3) ? *reinterpret_cast<const float*>(sb + ci[j].w) : 0.0f;   // same bits: + 0
       acc[j] = ((a + b) + c) + d;
     }
 #pragma unroll
@@ -418,7 +420,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       // Steps k1 = 0 .. 15 cover every bin but 512 (its own mirror): half the shuffles, 10.5 instead of 15
       // instructions per bin.  The mirror of bin 32 k1 + lane sits in stash row 31 - k1, column 32 - lane
       // (lane 0: row 32 - k1, column 0, i.e. 33 floats after the row start; k1 = 0 gives the Nyquist slot).
-      float* dmir = stash + (lane == 0 ? kStashStride : 32 - lane);
+      // (lane 0's mirror, column 0 of row 32 - k1 >= 17, goes one float lower: bank 31 - k1, the one bank the other
+      // lanes' stores of this step leave free; at the natural place it shared a bank with lane 31's)
+      float* dmir = stash + (lane == 0 ? kStashStride - 1 : 32 - lane);
       auto emit2 = [&](auto k1c) {
         constexpr int k1 = decltype(k1c)::value;
         const float2 w = fft2048_tw2<k1>(s_tw2, lane, tw2_pair);

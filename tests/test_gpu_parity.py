@@ -565,3 +565,60 @@ def test_melspectrogram_stretch_pipeline(tac, oc, shape):
     want = oc.apply_filterbank(oc.complex_norm(stretched.float(), 2.0), fb)
     assert stretched.size(-2) == steps.numel()
     assert rel_err(y, want) < 5e-4                                   # |.|^2 does not see the phase; magnitudes interpolate in fp32
+
+
+# ------------------------------------------------------------------------------------------ empty / ragged / strided inputs
+def test_empty_batch_everywhere(tac):
+    """Zero sequences: every entry point returns an empty tensor of the reference's shape without launching."""
+    x = torch.zeros(0, 1, 4000, device="cuda")
+    assert tac.stft(x, 512, 128).shape == (0, 1, 257, 32, 2)
+    assert tac.Spectrogram(512, 128).cuda()(x).shape == (0, 1, 257, 32)
+    assert tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512).cuda()(x).shape == (0, 1, 128, 8)
+    assert tac.Melspectrogram(num_mels=40, sample_rate=16000, fft_length=512, hop_length=128).cuda()(x).shape == (0, 1, 40, 32)
+    assert tac.mu_law_encoding(torch.zeros(0, 7, device="cuda")).shape == (0, 7)
+    assert tac.mu_law_decoding(torch.zeros(0, 7, dtype=torch.int64, device="cuda")).shape == (0, 7)
+    assert tac.amplitude_to_db(torch.zeros(0, 3, device="cuda")).shape == (0, 3)
+
+
+@pytest.mark.parametrize("n_samples", [2049, 16001, 40003, 3 * 512 + 2048])
+def test_fused_mel_ragged_lengths(tac, oc, n_samples):
+    """Lengths that are not a multiple of 4 / of the hop: rows lose their 16-byte alignment, so interior frames take
+    the gather instead of the bulk copy; the last frame ends exactly at / before the end of the row."""
+    torch.manual_seed(n_samples)
+    x = torch.randn(3, 1, n_samples)
+    m = _mel_chain(tac, hop_length=512)
+    want = oc.melspectrogram(x, 128, 16000, fft_length=2048, hop_length=512)
+    got = m(dev(x)).cpu()
+    assert got.shape == want.shape
+    assert pure_rel_err(got, want) < REL
+
+
+def test_fused_mel_tiny_and_strided_inputs(tac, oc):
+    """Fewer frames than warps / than SMs (most CTAs get an empty chunk), 1-D and 2-D inputs (functional.py:89-91
+    flattens whatever leads), and a batch that is a strided view (every other row of a larger tensor)."""
+    torch.manual_seed(77)
+    m = _mel_chain(tac, hop_length=512)
+    for shape in [(2048,), (1, 2500), (2, 1, 5000), (1, 1, 1, 9000)]:
+        x = torch.randn(*shape)
+        want = oc.melspectrogram(x, 128, 16000, fft_length=2048, hop_length=512)
+        got = m(dev(x)).cpu()
+        assert got.shape == want.shape, shape
+        assert pure_rel_err(got, want) < REL, shape
+    big = torch.randn(8, 1, 30000)
+    view = dev(big)[::2]                                    # stride 2 * 30000 between sequences
+    assert not view.is_contiguous()
+    want = oc.melspectrogram(big[::2], 128, 16000, fft_length=2048, hop_length=512)
+    assert pure_rel_err(m(view).cpu(), want) < REL
+    st = tac.stft(view, 2048, 512).cpu()
+    assert rel_err(st, oc.stft(big[::2], 2048, 512)) < REL
+
+
+def test_repeated_calls_are_bit_identical(tac):
+    """Fixed summation order everywhere on the forward path: the same input gives the same bits, call after call and
+    through every entry point (module, functional, prepared)."""
+    torch.manual_seed(3)
+    x = dev(torch.randn(6, 2, 50000))
+    m = _mel_chain(tac, to_db=True, hop_length=512)
+    a = m(x)
+    for _ in range(3):
+        assert torch.equal(m(x), a)

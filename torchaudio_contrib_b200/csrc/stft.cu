@@ -123,6 +123,20 @@ __device__ __forceinline__ float2 fft2048_tw2(const float2* s_tw2, int lane, flo
   }
 }
 
+// The same twiddle without the table, for the mel kernel (which only needs K1 = 0 .. 16 and is bound by shared-memory
+// bandwidth, not by the fp32 pipe): W_2048^(32 K1 + lane) = W_64^K1 * W_2048^lane, the first factor a compile-time
+// constant, the second one float2 per lane (`base`, table row K1 = 0).  Four FP instructions instead of half an LDS.128.
+__device__ constexpr float kW64[17][2] = {{1.000000000e+00f, -0.000000000e+00f}, {9.951847267e-01f, -9.801714033e-02f}, {9.807852804e-01f, -1.950903220e-01f}, {9.569403357e-01f, -2.902846773e-01f}, {9.238795325e-01f, -3.826834324e-01f}, {8.819212643e-01f, -4.713967368e-01f}, {8.314696123e-01f, -5.555702330e-01f}, {7.730104534e-01f, -6.343932842e-01f}, {7.071067812e-01f, -7.071067812e-01f}, {6.343932842e-01f, -7.730104534e-01f}, {5.555702330e-01f, -8.314696123e-01f}, {4.713967368e-01f, -8.819212643e-01f}, {3.826834324e-01f, -9.238795325e-01f}, {2.902846773e-01f, -9.569403357e-01f}, {1.950903220e-01f, -9.807852804e-01f}, {9.801714033e-02f, -9.951847267e-01f}, {6.123233996e-17f, -1.000000000e+00f}};
+template <int K1>
+__device__ __forceinline__ float2 fft2048_tw2_computed(const float2 base) {
+  if constexpr (K1 == 0) return base;
+  else if constexpr (K1 == 16) return make_float2(base.y, -base.x);           // W_64^16 = -i
+  else {
+    constexpr float c = kW64[K1][0], s = kW64[K1][1];
+    return make_float2(fmaf(c, base.x, -s * base.y), fmaf(c, base.y, s * base.x));
+  }
+}
+
 // table set-up shared by both kernels: pair-interleaved [j / 2][lane][j % 2] so one LDS.128 serves two registers
 __device__ __forceinline__ void fft2048_tables(const StftParams& p, float2* s_win, float2* s_tw1, float2* s_tw2, int tid, int nthreads) {
   for (int i = tid; i < 1024; i += nthreads) {
@@ -423,9 +437,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
       // (lane 0's mirror, column 0 of row 32 - k1 >= 17, goes one float lower: bank 31 - k1, the one bank the other
       // lanes' stores of this step leave free; at the natural place it shared a bank with lane 31's)
       float* dmir = stash + (lane == 0 ? kStashStride - 1 : 32 - lane);
+      const float2 tw2_base = s_tw2[2 * lane];                     // W_2048^lane (table row k1 = 0)
       auto emit2 = [&](auto k1c) {
         constexpr int k1 = decltype(k1c)::value;
-        const float2 w = fft2048_tw2<k1>(s_tw2, lane, tw2_pair);
+        const float2 w = fft2048_tw2_computed<k1>(tw2_base);
         const float2 z = v[bit_reverse<32>(k1)];
         float2 q;
         q.x = __shfl_sync(0xffffffffu, v[bit_reverse<32>(31 - k1)].x, partner);
@@ -437,7 +452,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
         dmir[(31 - k1) * kStashStride] = fast_power<PMODE>(a - tr, b - ti, half_power);
       };
       static_for<16>(emit2);
-      const float2 x512 = fft2048_untangle<16>(v, fft2048_tw2<16>(s_tw2, lane, tw2_pair), lane, partner);
+      const float2 x512 = fft2048_untangle<16>(v, fft2048_tw2_computed<16>(tw2_base), lane, partner);
       if (lane == 0) dst[16 * kStashStride] = fast_power<PMODE>(x512.x, x512.y, half_power);
     } else {
       auto emit = [&](auto k1c) {
@@ -731,7 +746,7 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
 int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                      const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
                      int onesided) {
-  TAC_REQUIRE(x && window, TAC_ERR_INVALID, "stft: null input or window pointer");
+  TAC_REQUIRE((x || n_seq == 0) && window, TAC_ERR_INVALID, "stft: null input or window pointer");   // an empty batch has no storage
   TAC_REQUIRE(n_seq >= 0 && n_samples >= 0 && seq_stride >= n_samples, TAC_ERR_INVALID,
               "stft: bad shape n_seq=%lld n_samples=%lld stride=%lld", (long long)n_seq, (long long)n_samples,
               (long long)seq_stride);

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kBwdThreads) stft_backward_kernel(const StftBw
 
 static int launch_stft_backward(StftBwdParams& bp, cudaStream_t stream) {
   const StftParams& p = bp.f;
+  if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
   TAC_CUDA_OK(cudaMemsetAsync(bp.grad_x, 0, (size_t)p.n_seq * p.n_samples * sizeof(float), stream));
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
@@ -253,7 +254,7 @@ extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64
                                      void* stream) {
   using namespace tac;
   StftBwdParams bp;
-  TAC_REQUIRE(grad_out && grad_x, TAC_ERR_INVALID, "stft_backward: null gradient pointer");
+  TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "stft_backward: null gradient pointer");
   const int rc = fill_stft_params(bp.f, grad_x /* placeholder, never read */, n_seq, n_samples, n_samples, window, n_fft, hop,
                                   center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
@@ -270,7 +271,7 @@ extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64
                                             int onesided, float power, const float* grad_out, float* grad_x, void* stream) {
   using namespace tac;
   StftBwdParams bp;
-  TAC_REQUIRE(grad_out && grad_x, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
+  TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
   bp.grad_out = grad_out;
@@ -284,9 +285,9 @@ extern "C" int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_s
                                            const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands,
                                            float* grad_spec, void* stream) {
   using namespace tac;
-  TAC_REQUIRE(grad_y && fb_dev && grad_spec, TAC_ERR_INVALID, "filterbank_backward: null pointer");
   TAC_REQUIRE(n_seq >= 0 && frames >= 0 && n_bins > 0 && n_bands > 0, TAC_ERR_INVALID, "filterbank_backward: bad shape");
   if (n_seq == 0 || frames == 0) return TAC_OK;
+  TAC_REQUIRE(grad_y && fb_dev && grad_spec, TAC_ERR_INVALID, "filterbank_backward: null pointer");
   const size_t smem = sizeof(float) * (size_t)n_bands * (kFbTileT + 1) + sizeof(int2) * (size_t)n_bins;
   TAC_REQUIRE(smem <= 200 * 1024, TAC_ERR_UNSUPPORTED, "filterbank_backward: %d bands x %d bins exceed one CTA's shared memory",
               n_bands, n_bins);

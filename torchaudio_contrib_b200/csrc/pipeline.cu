@@ -174,9 +174,14 @@ extern "C" int tac_melspec_f32(const float* x, int64_t n_seq, int64_t n_samples,
 // ---------------------------------------------------------------------------------------------
 // host-buffer pipeline
 // ---------------------------------------------------------------------------------------------
-// Slots of the host pipeline: each owns a stream and a buffer set and runs H2D -> kernels -> D2H in order.  With
-// four in flight the H2D engine is never waiting for an earlier slice's D2H (two slots left PCIe idle half the time).
-constexpr int kHostSlots = 4;
+// Host pipeline: three streams -- one carries every H2D copy, in order and back to back (PCIe is the bottleneck:
+// measured 55 GB/s for one large pinned copy, less when copies of different streams interleave), one the kernels, one
+// the D2H copies -- and kHostSlots buffer sets handed round between them with events:
+//   H2D(i) waits until the kernel that last read slot's input is done;  kernel(i) waits for H2D(i) and for the D2H that
+//   last read the slot's output;  D2H(i) waits for kernel(i).
+// (The first version gave every slot its own stream running H2D -> kernel -> D2H; its H2D copies interleaved and the
+// step took 0.87 ms for 41 MB in, against 0.74 ms for the bare copy.)
+constexpr int kHostSlots = 8;
 
 struct tac_pipeline {
   tac_pipeline_config cfg;
@@ -184,7 +189,8 @@ struct tac_pipeline {
   float* d_window;
   void* d_plan;
   int64_t band_handle;                  // non-zero: the one-kernel path applies (n_fft = 2048, two-band matrix)
-  cudaStream_t stream[kHostSlots];
+  cudaStream_t s_in, s_run, s_out;
+  cudaEvent_t ev_in[kHostSlots], ev_run[kHostSlots], ev_out[kHostSlots];
   float* d_x[kHostSlots];
   float* d_out[kHostSlots];
   float* d_ws[kHostSlots];
@@ -245,7 +251,14 @@ extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* 
     free(host);
     if (rc != TAC_OK) return rc;
   }
-  for (int i = 0; i < kHostSlots; ++i) TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->stream[i], cudaStreamNonBlocking));
+  TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+  TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < kHostSlots; ++i) {
+    TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+    TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming));
+    TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+  }
   *out = p;
   return TAC_OK;
 }
@@ -260,10 +273,10 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   TAC_CUDA_OK(cudaSetDevice(p->device));
   const int64_t frames = tac_stft_num_frames(n_samples, c.n_fft, c.hop, c.center);
   const int out_rows = c.n_bands > 0 ? c.n_bands : c.n_fft / 2 + 1;
-  // slice = a few MB of input so that H2D(i+1), compute(i) and D2H(i-1) overlap
-  // Slice size: measured on the B200 boxes, one pinned H2D stream moves ~21 GB/s but three concurrent ones ~35-48,
-  // while slices under ~8 MB make the kernels too small to be efficient: cut the batch into at least three slices,
-  // each between 4 and 16 MB (TAC_HOST_SLICE_MB overrides).
+  // Slice size: small enough that the tail after the last H2D (that slice's kernel and D2H, which nothing overlaps) is
+  // short, large enough that a slice's kernel is still efficient and the per-copy overhead stays small: about one
+  // eighth of the batch, between 2 and 8 MB of input (TAC_HOST_SLICE_MB overrides); the last slice is halved again and
+  // again down to ~1 MB.
   static int64_t slice_override = -1;
   if (slice_override < 0) {
     const char* e = getenv("TAC_HOST_SLICE_MB");
@@ -271,9 +284,9 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   }
   int64_t slice_bytes = slice_override;
   if (slice_bytes == 0) {
-    slice_bytes = (n_seq * n_samples * 4 + 2) / 3;
-    if (slice_bytes < ((int64_t)4 << 20)) slice_bytes = (int64_t)4 << 20;
-    if (slice_bytes > ((int64_t)16 << 20)) slice_bytes = (int64_t)16 << 20;
+    slice_bytes = (n_seq * n_samples * 4 + 7) / 8;
+    if (slice_bytes < ((int64_t)2 << 20)) slice_bytes = (int64_t)2 << 20;
+    if (slice_bytes > ((int64_t)8 << 20)) slice_bytes = (int64_t)8 << 20;
   }
   int64_t per = (slice_bytes + n_samples * 4 - 1) / (n_samples * 4);
   if (per < 1) per = 1;
@@ -283,11 +296,19 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   const int64_t ws_bytes = (c.n_bands > 0 && !p->band_handle) ? tac_melspec_workspace_bytes(per, n_samples, c.n_fft, c.hop, c.center) : 0;
   int rc = pipeline_reserve(p, x_bytes, o_bytes, ws_bytes);
   if (rc != TAC_OK) return rc;
+  const int64_t min_tail = ((int64_t)1 << 20) / (n_samples * 4) + 1;      // sequences in ~1 MB
+  int64_t used[kHostSlots] = {0};                                         // slices a slot has carried in this call
   int slot = 0;
-  for (int64_t s0 = 0; s0 < n_seq; s0 += per, slot = (slot + 1) % kHostSlots) {
-    const int64_t ns = (s0 + per <= n_seq) ? per : n_seq - s0;
-    cudaStream_t st = p->stream[slot];
-    TAC_CUDA_OK(cudaMemcpyAsync(p->d_x[slot], x_host + s0 * n_samples, (size_t)(ns * n_samples * 4), cudaMemcpyHostToDevice, st));
+  for (int64_t s0 = 0, ns = 0; s0 < n_seq; s0 += ns, slot = (slot + 1) % kHostSlots) {
+    const int64_t left = n_seq - s0;
+    ns = left < per ? left : per;
+    if (left <= per && left > 2 * min_tail) ns = (left + 1) / 2;
+    if (used[slot]) TAC_CUDA_OK(cudaStreamWaitEvent(p->s_in, p->ev_run[slot], 0));      // slot's input consumed
+    TAC_CUDA_OK(cudaMemcpyAsync(p->d_x[slot], x_host + s0 * n_samples, (size_t)(ns * n_samples * 4), cudaMemcpyHostToDevice, p->s_in));
+    TAC_CUDA_OK(cudaEventRecord(p->ev_in[slot], p->s_in));
+    TAC_CUDA_OK(cudaStreamWaitEvent(p->s_run, p->ev_in[slot], 0));
+    if (used[slot]) TAC_CUDA_OK(cudaStreamWaitEvent(p->s_run, p->ev_out[slot], 0));     // slot's output copied out
+    cudaStream_t st = p->s_run;
     StftParams sp;
     rc = fill_stft_params(sp, p->d_x[slot], ns, n_samples, n_samples, p->d_window, c.n_fft, c.hop, c.center, c.pad_mode,
                           c.normalized, 1);
@@ -304,10 +325,16 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
       rc = launch_stft(sp, st);
     }
     if (rc != TAC_OK) return rc;
+    TAC_CUDA_OK(cudaEventRecord(p->ev_run[slot], p->s_run));
+    TAC_CUDA_OK(cudaStreamWaitEvent(p->s_out, p->ev_run[slot], 0));
     TAC_CUDA_OK(cudaMemcpyAsync(out_host + s0 * out_rows * frames, p->d_out[slot], (size_t)(ns * out_rows * frames * 4),
-                                cudaMemcpyDeviceToHost, st));
+                                cudaMemcpyDeviceToHost, p->s_out));
+    TAC_CUDA_OK(cudaEventRecord(p->ev_out[slot], p->s_out));
+    ++used[slot];
   }
-  for (int i = 0; i < kHostSlots; ++i) TAC_CUDA_OK(cudaStreamSynchronize(p->stream[i]));
+  TAC_CUDA_OK(cudaStreamSynchronize(p->s_out));          // every D2H follows its kernel, every kernel its H2D
+  TAC_CUDA_OK(cudaStreamSynchronize(p->s_run));
+  TAC_CUDA_OK(cudaStreamSynchronize(p->s_in));
   return TAC_OK;
 }
 
@@ -315,8 +342,13 @@ extern "C" int tac_pipeline_destroy(tac_pipeline* p) {
   using namespace tac;
   if (!p) return TAC_OK;
   cudaSetDevice(p->device);
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_run) cudaStreamDestroy(p->s_run);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
   for (int i = 0; i < kHostSlots; ++i) {
-    if (p->stream[i]) cudaStreamDestroy(p->stream[i]);
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
     if (p->d_x[i]) cudaFree(p->d_x[i]);
     if (p->d_out[i]) cudaFree(p->d_out[i]);
     if (p->d_ws[i]) cudaFree(p->d_ws[i]);

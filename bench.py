@@ -193,6 +193,49 @@ def time_cpu_chain(batch, channels, samples, sample_rate, to_db, budget_s):
             "sample": "%d passes of (%d,%d,%d) in %.1f s" % (done, nb, channels, samples, dt)}
 
 
+def time_reference_on_gpu(inputs, sample_rate, to_db, frames_per_step, steps=10):
+    """Second comparator: the UNMODIFIED reference modules from baseline/_ref moved to the GPU, i.e. its
+    torch path on cuFFT + cuBLAS (TF32 off) on the same device-resident inputs.  None when baseline/_ref is absent
+    (the oracle is never run on the GPU)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "torchaudio_contrib")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import torchaudio_contrib as ref
+    native = torch.stft
+
+    def legacy_stft(*a, **k):
+        k["return_complex"] = True
+        return torch.view_as_real(native(*a, **k))
+
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.stft = legacy_stft
+    try:
+        mods = list(ref.Melspectrogram(num_mels=N_MELS, sample_rate=sample_rate, fft_length=N_FFT, hop_length=HOP))
+        if to_db:
+            mods.append(ref.AmplitudeToDb())
+        model = torch.nn.Sequential(*mods).to(inputs[0].device)
+        with torch.no_grad():
+            for i in range(2):
+                model(inputs[i % len(inputs)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                model(inputs[i % len(inputs)])
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.stft = native
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return {"value": frames_per_step / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "what": "unmodified reference nn.Modules on the same GPU: torch.stft (cuFFT) + norm/pow + matmul (cuBLAS, TF32 off)"
+                    + (" + dB" if to_db else "") + ", device-resident inputs, %d steps" % steps}
+
+
 def run_reference_arm(args, rank, world):
     """`--impl reference`: the reference's own CPU implementation, rank 0 only."""
     if rank != 0:
@@ -416,6 +459,14 @@ def run_ours(args, rank, world, local):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms, gather_ms, peer_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
+    ref_gpu = None
+    if rank == 0 and world == 1:
+        try:
+            ref_gpu = time_reference_on_gpu(inputs, sr, to_db, frames_per_step)
+        except Exception as exc:                                # informational only
+            ref_gpu = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm_peak = float(peaks["hbm_gbs"])
@@ -453,6 +504,7 @@ def run_ours(args, rank, world, local):
             "e2e": {"value": world * e2e_steps * frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "tac_pipeline_run_host (HostPipeline), pinned host buffers"},
+            "reference_on_gpu": ref_gpu,
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }

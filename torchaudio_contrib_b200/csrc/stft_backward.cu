@@ -178,14 +178,18 @@ filterbank_backward_kernel(const float* __restrict__ grad_y, int64_t sy_seq, int
   float* tile = reinterpret_cast<float*>(smem_raw);                       // [n_bands][kFbTileT + 1]
   int2* range = reinterpret_cast<int2*>(tile + (size_t)n_bands * (kFbTileT + 1));   // [n_bins]: non-zero columns [lo, hi)
   const int tid = threadIdx.x;
-  for (int k = tid; k < n_bins; k += kFbThreads) {
+  // per-bin range of non-zero columns: a warp per bin, coalesced row reads, warp min / max
+  // (a thread per bin walking its row made this prologue as expensive as the contraction itself)
+  for (int k = tid >> 5; k < n_bins; k += kFbThreads / 32) {
     int lo = n_bands, hi = 0;
-    for (int m = 0; m < n_bands; ++m)
+    for (int m = tid & 31; m < n_bands; m += 32)
       if (__ldg(fb + (int64_t)k * n_bands + m) != 0.0f) {
         lo = m < lo ? m : lo;
         hi = m + 1;
       }
-    range[k] = make_int2(lo, hi);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) range[k] = make_int2(lo, hi);
   }
   for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
     const int64_t seq = job / tiles_per_seq;

@@ -178,13 +178,19 @@ int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64_t n_sample
  * grad_spec: (n_seq, n_bins, frames) contiguous.
  * tac_amplitude_to_db_backward_f32 / tac_complex_norm_backward_f32: pointwise adjoints of
  * functional.py:291-296 and :126-128 (x, z: the forward inputs). */
+/* workspace: device buffer of tac_stft_backward_workspace_bytes(...) bytes (the windowed frame
+ * gradients, n_fft floats per frame; summed into grad_x without atomics, so the result is
+ * deterministic). */
+int64_t tac_stft_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center);
 int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_samples,
                           const float* window, int n_fft, int hop, int center, int pad_mode,
-                          int normalized, int onesided, float* grad_x, void* stream);
+                          int normalized, int onesided, float* grad_x,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                                  const float* window, int n_fft, int hop, int center, int pad_mode,
                                  int normalized, int onesided, float power,
-                                 const float* grad_out, float* grad_x, void* stream);
+                                 const float* grad_out, float* grad_x,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
 int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band,
                                 int64_t stride_frame, const float* fb_dev, int64_t n_seq,
                                 int64_t frames, int n_bins, int n_bands, float* grad_spec,

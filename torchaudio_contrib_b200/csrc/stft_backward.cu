@@ -4,8 +4,13 @@
 //   stft_backward_kernel        d loss / d waveform from d loss / d stft (complex) or from d loss / d |stft|^p
 //                               (the spectrum is recomputed from the waveform instead of being saved: 164 MB at
 //                               config 2); one CTA per frame, any power-of-two n_fft, both through the Stockham
-//                               FFT of fft_stockham.cuh.  The frame's gradient is scattered with atomicAdd through
-//                               the same index map the forward pass gathers through (adjoint of the centre padding).
+//                               FFT of fft_stockham.cuh.  The windowed frame gradients go to a workspace
+//                               (frame-major, n_fft floats per frame);
+//   overlap_add_kernel          sums, for every waveform sample, the (up to n_fft / hop) frame entries that cover its
+//                               padded position plus those of the padded positions the forward pass filled from it
+//                               (adjoint of the reflect / replicate / circular / constant centre padding).  No atomics:
+//                               the gradient is deterministic, and a float atomic per frame sample (2048 per frame)
+//                               had cost more than the two FFTs.
 //   filterbank_backward_kernel  d loss / d spec[k, t] = sum_m d loss / d y[m, t] * fb[k, m]
 //   pointwise                   amplitude_to_db and complex_norm
 //
@@ -28,7 +33,7 @@ constexpr int kBwdThreads = 256;
 struct StftBwdParams {
   StftParams f;            // geometry of the forward call (x may be null in complex mode)
   const float* grad_out;   // complex mode: (n_seq, bins, frames, 2); power mode: (n_seq, bins, frames); contiguous
-  float* grad_x;           // (n_seq, n_samples) contiguous, zeroed before the launch
+  float* frames_out;       // workspace: (n_seq * frames, n_fft) windowed frame gradients
   int power_mode;          // -1: gradient of the complex spectrum; 2 / 1 / 0 as in the forward kernels
   float power;
 };
@@ -130,35 +135,115 @@ __global__ void __launch_bounds__(kBwdThreads) stft_backward_kernel(const StftBw
     }
     __syncthreads();
     const float2* r = stockham_forward<kBwdThreads>(buf_a, buf_b, tw_c, C, tid);   // z_n = conj(r_n)
-    float* grow = bp.grad_x + seq * p.n_samples;
-    const int n_samples = (int)p.n_samples;
+    float2* frow = reinterpret_cast<float2*>(bp.frames_out + (g - p.g0) * n_fft);
     for (int n = tid; n < C; n += kBwdThreads) {
       const float2 v = r[n];
-      const float y0 = v.x * win[2 * n], y1 = -v.y * win[2 * n + 1];
-      const int s0 = (int)start + 2 * n, s1 = s0 + 1;
-      const bool in0 = s0 >= 0 && s0 < n_samples, in1 = s1 >= 0 && s1 < n_samples;
-      if (in0 || p.pad_mode != 1) atomicAdd(grow + padded_index(s0, n_samples, p.pad_mode), y0);
-      if (in1 || p.pad_mode != 1) atomicAdd(grow + padded_index(s1, n_samples, p.pad_mode), y1);
+      frow[n] = make_float2(v.x * win[2 * n], -v.y * win[2 * n + 1]);
     }
     __syncthreads();
   }
 }
 
-static int launch_stft_backward(StftBwdParams& bp, cudaStream_t stream) {
+// P(q) = sum over the frames t covering padded position q of frames_out[t][q - t hop]
+__device__ __forceinline__ float ola_padded(const float* __restrict__ fr, int q, int frames, int n_fft, int hop) {
+  int t_lo = q - n_fft + 1;
+  t_lo = t_lo <= 0 ? 0 : (t_lo + hop - 1) / hop;
+  int t_hi = q / hop;
+  t_hi = t_hi > frames - 1 ? frames - 1 : t_hi;
+  float acc = 0.0f;
+  for (int t = t_lo; t <= t_hi; ++t) acc += __ldg(fr + (int64_t)t * n_fft + (q - t * hop));
+  return acc;
+}
+
+// grad_x[seq][j] = P(j + pad) + the padded positions that mirror / wrap onto j; `replicate` edges are finished by
+// overlap_add_edges_kernel (sample 0 and T - 1 collect `pad` positions each)
+__global__ void __launch_bounds__(256)
+overlap_add_kernel(const float* __restrict__ frames_ws, int64_t n_seq, int n_samples, int frames, int n_fft, int hop, int pad,
+                   int pad_mode, float* __restrict__ grad_x) {
+  const int64_t total = n_seq * n_samples;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t seq = i / n_samples;
+    const int j = (int)(i - seq * n_samples);
+    const float* fr = frames_ws + seq * frames * (int64_t)n_fft;
+    float acc = ola_padded(fr, j + pad, frames, n_fft, hop);
+    if (pad > 0) {
+      if (pad_mode == 0) {                                           // reflect: x[-k] = x[k], x[T-1+k] = x[T-1-k]
+        if (j >= 1 && j <= pad) acc += ola_padded(fr, pad - j, frames, n_fft, hop);
+        if (j >= n_samples - 1 - pad && j <= n_samples - 2) acc += ola_padded(fr, pad + 2 * (n_samples - 1) - j, frames, n_fft, hop);
+      } else if (pad_mode == 3) {                                    // circular
+        if (j >= n_samples - pad) acc += ola_padded(fr, j + pad - n_samples, frames, n_fft, hop);
+        if (j < pad) acc += ola_padded(fr, j + pad + n_samples, frames, n_fft, hop);
+      }
+    }
+    grad_x[i] = acc;
+  }
+}
+// replicate padding: sample 0 also receives padded positions [0, pad), sample T - 1 positions (pad + T - 1, T + 2 pad)
+__global__ void __launch_bounds__(256)
+overlap_add_edges_kernel(const float* __restrict__ frames_ws, int n_samples, int frames, int n_fft, int hop, int pad,
+                         float* __restrict__ grad_x) {
+  const int64_t seq = blockIdx.x >> 1;
+  const bool right = blockIdx.x & 1;
+  const float* fr = frames_ws + seq * frames * (int64_t)n_fft;
+  float acc = 0.0f;
+  for (int q = threadIdx.x; q < pad; q += blockDim.x) acc += ola_padded(fr, right ? pad + n_samples + q : q, frames, n_fft, hop);
+  __shared__ float part[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.0f;
+    for (int w = 0; w < 8; ++w) sum += part[w];
+    grad_x[seq * n_samples + (right ? n_samples - 1 : 0)] += sum;
+  }
+}
+
+static int64_t backward_workspace_bytes(const StftParams& p) { return p.n_seq * p.frames * (int64_t)p.n_fft * 4; }
+
+static int launch_overlap_add(const StftBwdParams& bp, float* grad_x, cudaStream_t stream) {
+  const StftParams& p = bp.f;
+  const int64_t total = p.n_seq * p.n_samples;
+  const int64_t want = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  {
+    LaunchProbe probe(KIND_POINTWISE, stream);
+    overlap_add_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(bp.frames_out, p.n_seq, (int)p.n_samples, (int)p.frames,
+                                                                        p.n_fft, p.hop, p.pad, p.pad_mode, grad_x);
+  }
+  TAC_CUDA_OK(cudaGetLastError());
+  if (p.pad > 0 && p.pad_mode == TAC_PAD_REPLICATE) {
+    LaunchProbe probe(KIND_POINTWISE, stream);
+    overlap_add_edges_kernel<<<(int)(2 * p.n_seq), 256, 0, stream>>>(bp.frames_out, (int)p.n_samples, (int)p.frames, p.n_fft,
+                                                                    p.hop, p.pad, grad_x);
+    TAC_CUDA_OK(cudaGetLastError());
+  }
+  return TAC_OK;
+}
+
+static int launch_stft_backward(StftBwdParams& bp, float* grad_x, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   const StftParams& p = bp.f;
   if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
-  TAC_CUDA_OK(cudaMemsetAsync(bp.grad_x, 0, (size_t)p.n_seq * p.n_samples * sizeof(float), stream));
   const int64_t n_frames = p.g1 - p.g0;
-  if (n_frames <= 0) return TAC_OK;
+  if (n_frames <= 0) {                                   // no frame covers anything: the gradient is zero
+    TAC_CUDA_OK(cudaMemsetAsync(grad_x, 0, (size_t)p.n_seq * p.n_samples * sizeof(float), stream));
+    return TAC_OK;
+  }
+  TAC_REQUIRE(workspace && workspace_bytes >= backward_workspace_bytes(p), TAC_ERR_WORKSPACE,
+              "stft backward: workspace of %lld bytes, %lld needed (tac_stft_backward_workspace_bytes)", (long long)workspace_bytes,
+              (long long)backward_workspace_bytes(p));
+  TAC_REQUIRE(p.n_seq * 2 < ((int64_t)1 << 31), TAC_ERR_UNSUPPORTED, "stft backward: too many sequences in one call");
+  bp.frames_out = static_cast<float*>(workspace);
   const size_t smem = bwd_smem_bytes(p.n_fft);
   TAC_CUDA_OK(cudaFuncSetAttribute(stft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = (int)((200 * 1024) / (smem + 1024));
   const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
   const int grid = (int)(n_frames < cap ? n_frames : cap);
-  LaunchProbe probe(KIND_STFT, stream);
-  stft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
+  {
+    LaunchProbe probe(KIND_STFT, stream);
+    stft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
+  }
   TAC_CUDA_OK(cudaGetLastError());
-  return TAC_OK;
+  return launch_overlap_add(bp, grad_x, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -253,9 +338,14 @@ static int pointwise_grid(int64_t n) {
 
 }  // namespace tac
 
+extern "C" int64_t tac_stft_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
+  if (n_fft <= 0 || hop <= 0 || n_seq <= 0) return 0;
+  return n_seq * tac_stft_num_frames(n_samples, n_fft, hop, center) * (int64_t)n_fft * 4;
+}
+
 extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_samples, const float* window, int n_fft,
                                      int hop, int center, int pad_mode, int normalized, int onesided, float* grad_x,
-                                     void* stream) {
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace tac;
   StftBwdParams bp;
   TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "stft_backward: null gradient pointer");
@@ -264,25 +354,24 @@ extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64
   if (rc != TAC_OK) return rc;
   bp.f.x = nullptr;
   bp.grad_out = grad_out;
-  bp.grad_x = grad_x;
   bp.power_mode = -1;
   bp.power = 1.0f;
-  return launch_stft_backward(bp, as_stream(stream));
+  return launch_stft_backward(bp, grad_x, workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                                             const float* window, int n_fft, int hop, int center, int pad_mode, int normalized,
-                                            int onesided, float power, const float* grad_out, float* grad_x, void* stream) {
+                                            int onesided, float power, const float* grad_out, float* grad_x, void* workspace,
+                                            int64_t workspace_bytes, void* stream) {
   using namespace tac;
   StftBwdParams bp;
   TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
   bp.grad_out = grad_out;
-  bp.grad_x = grad_x;
   bp.power = power;
   bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
-  return launch_stft_backward(bp, as_stream(stream));
+  return launch_stft_backward(bp, grad_x, workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,

@@ -490,16 +490,19 @@ def _stft_backward_call(x_or_none, grad_out, shape, fft_length, hop_length, win_
     g = _grad_f32(grad_out).contiguous()
     gx = torch.empty((n_seq, n_samples), dtype=torch.float32, device=device)
     lib = _cabi.lib()
+    ws_bytes = int(lib.tac_stft_backward_workspace_bytes(n_seq, n_samples, int(fft_length), hop, int(bool(center))))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)          # frame gradients before the overlap-add
     with torch.cuda.device(device):
         if power is None:
             _cabi.check(lib.tac_stft_backward_f32(
                 _cabi.ptr(g), n_seq, n_samples, _cabi.ptr(win), int(fft_length), hop, int(bool(center)),
-                _cabi.PAD_MODES[pad_mode], int(bool(normalized)), int(bool(onesided)), _cabi.ptr(gx), _cabi.stream_ptr(device)))
+                _cabi.PAD_MODES[pad_mode], int(bool(normalized)), int(bool(onesided)), _cabi.ptr(gx), _cabi.ptr(ws), ws_bytes,
+                _cabi.stream_ptr(device)))
         else:
             flat = x_or_none.reshape(-1, n_samples)
             _cabi.check(lib.tac_spectrogram_backward_f32(
                 *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized), int(bool(onesided)), float(power),
-                _cabi.ptr(g), _cabi.ptr(gx), _cabi.stream_ptr(device)))
+                _cabi.ptr(g), _cabi.ptr(gx), _cabi.ptr(ws), ws_bytes, _cabi.stream_ptr(device)))
     return gx.reshape(shape)
 
 

@@ -195,6 +195,18 @@ int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t
                                 int64_t stride_frame, const float* fb_dev, int64_t n_seq,
                                 int64_t frames, int n_bins, int n_bands, float* grad_spec,
                                 void* stream);
+/* Backward of the Melspectrogram chain in one call: filterbank adjoint, stft + |.|^power adjoint
+ * (spectrum recomputed from x) and overlap-add.  grad_y is addressed through element strides
+ * like tac_filterbank_backward_f32; fb_dev: (n_fft/2+1, n_bands) row-major; workspace:
+ * tac_melspec_backward_workspace_bytes(...) bytes.  n_fft = 2048 runs one warp per frame with the
+ * forward kernel's register FFT; other sizes use the generic kernels. */
+int64_t tac_melspec_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center);
+int tac_melspec_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                             const float* window, int n_fft, int hop, int center, int pad_mode,
+                             int normalized, float power, const float* fb_dev, int n_bands,
+                             const float* grad_y, int64_t stride_seq, int64_t stride_band,
+                             int64_t stride_frame, float* grad_x,
+                             void* workspace, int64_t workspace_bytes, void* stream);
 int tac_amplitude_to_db_backward_f32(const float* x, const float* grad_out, int64_t n, float amin,
                                      float* grad_x, void* stream);
 int tac_complex_norm_backward_f32(const float* z, const float* grad_out, int64_t n, float power,

@@ -39,12 +39,14 @@ print("forward only (no grad)            %.3f ms" % timed(lambda i: model(xs[i %
 print("forward + backward, mel           %.3f ms" % timed(fwd_bwd(model)))
 print("forward + backward, mel + dB      %.3f ms" % timed(fwd_bwd(model_db)))
 import ctypes
-lib.tac_profile_enable(1)
-fwd_bwd(model_db)(0)
-torch.cuda.synchronize()
-ms = (ctypes.c_double * 4)()
-n = (ctypes.c_int64 * 4)()
-lib.tac_profile_read(ms, n)
-lib.tac_profile_enable(0)
-print("one fwd+bwd (mel+dB) by kernel kind: stft-family %.3f ms (%d launches), filterbank %.3f ms (%d), pointwise %.3f ms (%d)"
-      % (ms[0], n[0], ms[1], n[1], ms[3], n[3]))
+for name, m in (("mel", model), ("mel+dB", model_db)):
+    lib.tac_profile_enable(1)
+    fwd_bwd(m)(0)
+    torch.cuda.synchronize()
+    ms = (ctypes.c_double * 4)()
+    n = (ctypes.c_int64 * 4)()
+    lib.tac_profile_read(ms, n)
+    lib.tac_profile_enable(0)
+    print("one fwd+bwd (%s) by kernel kind: stft-family %.3f ms (%d launches), filterbank %.3f ms (%d), pointwise %.3f ms (%d)"
+          % (name, ms[0], n[0], ms[1], n[1], ms[3], n[3]))
+print("upstream gradient strides (mel):", gy[0].stride())

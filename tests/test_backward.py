@@ -179,3 +179,55 @@ def test_no_grad_paths_still_refuse_silent_detach(tac):
         tac.phase_vocoder(z, 1.3, torch.linspace(0, 3.14159 * 128, 257, device="cuda")[..., None])
     with pytest.raises(RuntimeError):
         tac.mu_law_encoding(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("power", [2.0, 1.0, 0.7])
+@pytest.mark.parametrize("n_samples,pad_mode,normalized", [(2049, "reflect", False), (9000, "constant", True),
+                                                            (16001, "replicate", False), (12288, "circular", False)])
+def test_mel_2048_backward_options(tac, power, n_samples, pad_mode, normalized):
+    """The warp-per-frame adjoint kernel (n_fft 2048) against the oracle's autograd: exponents, padding modes, ragged
+    lengths (gather path), fewer frames than warps, a frame-major and a contiguous upstream gradient."""
+    torch.manual_seed(n_samples + int(10 * power))
+    x = torch.randn(2, 1, n_samples)
+    fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+
+    def ref(t):
+        spec = oc.spectrogram(t, 2048, 512, pad_mode=pad_mode, normalized=normalized, power=power)
+        return oc.apply_filterbank(spec, fb)
+
+    y0 = ref(x)
+    gy = torch.randn(y0.shape)
+    want = _oracle_grad(ref, x, gy)
+    # exponents below 1 make the gradient singular at small |X| (|X|^(p-2)): two float32 evaluations then differ by more
+    # than 1e-4 from each other, so both are judged against the float64 evaluation of the same chain
+    win64 = torch.hann_window(2048, dtype=torch.float64)
+
+    def ref64(t):
+        spec = oc.spectrogram(t, 2048, 512, window=win64, pad_mode=pad_mode, normalized=normalized, power=power)
+        return oc.apply_filterbank(spec, fb.double())
+
+    want64 = _oracle_grad(ref64, x.double(), gy.double())
+    tol = max(REL, 10.0 * rel_err(want, want64))            # p = 0.7: the fp32 reference itself is ~6e-5 off
+    for layout in ("reference", "contiguous"):
+        _, gx = _gpu_grad(lambda t: tac.functional.melspectrogram(t, fb.cuda(), 2048, 512, pad_mode=pad_mode, normalized=normalized,
+                                                                  power=power, layout=layout), x, gy)
+        assert rel_err(gx, want64) < tol, (layout, tol)
+
+
+@pytest.mark.gpu
+def test_backward_is_deterministic(tac):
+    """No atomics on the backward path: the same input and upstream gradient give the same bits."""
+    torch.manual_seed(2)
+    x = torch.randn(4, 1, 40000)
+    gy = None
+    outs = []
+    m = tac.Sequential(*tac.Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048, hop_length=512), tac.AmplitudeToDb()).cuda()
+    for _ in range(3):
+        xg = x.cuda().requires_grad_(True)
+        y = m(xg)
+        if gy is None:
+            gy = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, xg, gy)
+        outs.append(gx)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

@@ -57,6 +57,8 @@ SIGNATURES = {
     "tac_stft_backward_f32": (_int, [_ptr, _i64, _i64, _ptr, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _i64, _ptr]),
     "tac_spectrogram_backward_f32": (_int, _STFT_ARGS + [_int, _f32, _ptr, _ptr, _ptr, _i64, _ptr]),
     "tac_filterbank_backward_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _int, _ptr, _ptr]),
+    "tac_melspec_backward_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),
+    "tac_melspec_backward_f32": (_int, _STFT_ARGS + [_f32, _ptr, _int, _ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
     "tac_amplitude_to_db_backward_f32": (_int, [_ptr, _ptr, _i64, _f32, _ptr, _ptr]),
     "tac_complex_norm_backward_f32": (_int, [_ptr, _ptr, _i64, _f32, _ptr, _ptr]),
     "tac_mulaw_encode_f32_i64": (_int, [_ptr, _i64, _int, _ptr, _int, _int, _f32, _ptr, _ptr]),

@@ -502,6 +502,196 @@ __global__ void __launch_bounds__(kFastThreads, 1) stft2048_kernel(const StftPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of stft + |.|^p for n_fft = 2048: d loss / d (windowed frame) from d loss / d |X|^p, one warp
+// per frame with the machinery of the forward kernel.  `gspec` is frame-major, kpad floats per frame (the filterbank
+// adjoint writes it that way); the windowed frame gradient (2048 floats) goes to `frames_out`, which
+// overlap_add_kernel (stft_backward.cu) folds into the waveform gradient.
+//
+// With P = Zh[k], Q = conj(Zh[1024 - k]) (Zh = the half-scaled complex FFT the forward pass builds X from:
+// X_k = S + D, conj X_{1024-k} = S - D, S = P + Q, D = -i W^k (P - Q)), per-bin gains h_k (= g_k (p/2) |X_k|^(p-2)) and
+// sigma = h_k + h_{1024-k}, delta = h_k - h_{1024-k}, the spectrum whose inverse complex FFT carries the frame gradient
+// in (even, odd) sample pairs collapses to
+//     Zt_k = 2 [ (sigma + delta Im W^k) P + i delta Re W^k Q ]                 (k = 0: twice that, H_0 = G_0 not G_0 / 2)
+// i.e. untangling, gain and re-tangling are one two-term update per bin, in place.  The inverse FFT is
+// conj . FFT . conj with the same two register passes and one transposition through the slab.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft1024_mid(float2 (&u)[32], float2* slab, const float2* s_tw1, int lane) {
+  dit_fft_fma<32>(u);
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) slab[k2 * kSlabStride + lane] = u[bit_reverse<32>(k2)];
+  __syncwarp();
+#pragma unroll
+  for (int n1 = 0; n1 < 32; n1 += 2) {
+    const float4 a = *reinterpret_cast<const float4*>(slab + lane * kSlabStride + n1);
+    const float4 w = reinterpret_cast<const float4*>(s_tw1)[(n1 >> 1) * 32 + lane];
+    u[n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+    u[n1 + 1] = make_float2(fmaf(a.z, w.z, -a.w * w.w), fmaf(a.z, w.w, a.w * w.z));
+  }
+  __syncwarp();
+}
+
+// (p / 2) |X|^(p - 2) from |X|^2
+template <int PMODE>
+__device__ __forceinline__ float power_gain(float n2, float power) {
+  if constexpr (PMODE == 2) return 1.0f;
+  if constexpr (PMODE == 1) return n2 > 0.0f ? 0.5f * rsqrtf(n2) : 0.0f;
+  return n2 > 0.0f ? 0.5f * power * exp2f((0.5f * power - 1.0f) * __log2f(n2)) : 0.0f;
+}
+
+template <int PMODE>
+__global__ void __launch_bounds__(kFastThreads, 1)
+stft2048_backward_kernel(const StftParams p, const float* __restrict__ gspec, float* __restrict__ frames_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_win = reinterpret_cast<float2*>(smem_raw);
+  float2* s_tw1 = s_win + 1024;
+  float2* s_tw2 = s_tw1 + 1024;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + 1024);
+  float2* s_slab = reinterpret_cast<float2*>(s_bar + kFastWarps);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* bar = s_bar + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  float2* slab = s_slab + warp * kSlabComplex;
+  float* slab_f = reinterpret_cast<float*>(slab);
+  float* grow = reinterpret_cast<float*>(s_slab + kFastWarps * kSlabComplex) + warp * kStashFloats;   // this frame's gspec row
+  const uint64_t pol_stream = l2_policy_evict_first();
+  constexpr uint32_t kRowBytes = 1056 * sizeof(float);
+
+  const uint32_t n_all = (uint32_t)(p.g1 - p.g0);
+  const uint32_t per_cta = n_all / gridDim.x, extra = n_all % gridDim.x;
+  const uint32_t chunk0 = blockIdx.x * per_cta + (blockIdx.x < extra ? blockIdx.x : extra);
+  const uint32_t chunk1 = chunk0 + per_cta + (blockIdx.x < extra ? 1u : 0u);
+  const uint32_t frames_u = (uint32_t)p.frames;
+  uint32_t gi = chunk0 + warp;
+  const int64_t g_first = p.g0 + gi;
+  uint32_t seq = (uint32_t)(g_first / p.frames), t = (uint32_t)(g_first % p.frames);
+  FrameSpan span;
+  // samples (bulk part) and the gradient row land on the same barrier; samples the bulk copy cannot take are gathered
+  auto stage = [&](uint32_t g_idx, uint32_t sq, uint32_t tt) {
+    const int start = (int)tt * p.hop - p.pad;
+    span = frame_span<2048>(p, start);
+    __syncwarp();
+    if (elect_one()) {
+      fence_proxy_async();
+      const uint32_t bytes = span.bulk ? (uint32_t)(span.hi - span.lo) * sizeof(float) : 0u;
+      mbar_arrive_expect_tx(bar, bytes + kRowBytes);
+      if (span.bulk) bulk_g2s_hint(slab_f + span.lo, p.x + (int64_t)sq * p.seq_stride + (start + span.lo), bytes, bar, pol_stream);
+      bulk_g2s_hint(grow, gspec + (int64_t)g_idx * 1056, kRowBytes, bar, pol_stream);
+    }
+    if (!span.bulk) gather_padded<64, 32>(slab_f, p.x + (int64_t)sq * p.seq_stride, start, (int)p.n_samples, p.pad_mode, lane);
+  };
+  if (gi < chunk1) stage(gi, seq, t);
+  fft2048_tables(p, s_win, s_tw1, s_tw2, tid, kFastThreads);
+  __syncthreads();
+
+  uint32_t parity = 0;
+  const int partner = (32 - lane) & 31;
+#pragma unroll 1
+  for (; gi < chunk1; gi += kFastWarps) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    if (span.bulk) fill_padding<2048>(slab_f, span, p.pad_mode, lane, p.x + (int64_t)seq * p.seq_stride, (int)t * p.hop - p.pad);
+    else __syncwarp();
+
+    float2 v[32];
+    fft2048_front(v, slab, s_win, s_tw1, lane);
+    dit_fft_fma<32>(v);                            // v[bit_reverse(k1)] = Zh[32 k1 + lane]
+
+    // ---- in place: Zh -> conj(Zt).  Step (k1, 31 - k1) reads registers k1 and 31 - k1 of this lane and of lane
+    // 32 - lane; lane 0 pairs with its own registers 32 - k1 and k1 + 1 instead, the first of which the previous step
+    // has already overwritten: it travels in `carry`.
+    float2 carry = v[bit_reverse<32>(0)];          // lane 0, step 0: partner of bin 0 is bin 0 itself
+    auto update = [&](float2 z, float2 q, float gk, float gm, float2 w, bool first) -> float2 {
+      float hk = gk, hm = gm;
+      if constexpr (PMODE != 2) {
+        const float sx = z.x + q.x, sy = z.y - q.y, ax = z.x - q.x, ay = z.y + q.y;        // S, P - Q
+        const float dx = fmaf(w.x, ay, w.y * ax), dy = -fmaf(w.x, ax, -w.y * ay);          // D = -i W (P - Q)
+        const float xr = sx + dx, xi = sy + dy, mr = sx - dx, mi = sy - dy;
+        hk *= power_gain<PMODE>(fmaf(xr, xr, xi * xi), p.power);
+        hm *= power_gain<PMODE>(fmaf(mr, mr, mi * mi), p.power);
+      }
+      const float sigma = hk + hm, delta = hk - hm;
+      const float a = fmaf(delta, w.y, sigma), b = delta * w.x;
+      float zr = fmaf(a, z.x, b * q.y), zi = fmaf(a, z.y, b * q.x);
+      if (first) {
+        zr *= 2.0f;
+        zi *= 2.0f;
+      }
+      return make_float2(zr, -zi);                 // conj(Zt) / 2: the factor 2 (and the window's) rides on the gains
+    };
+    auto pair_step = [&](auto k1c) {
+      constexpr int k1 = decltype(k1c)::value;     // 0 .. 15, mirror register 31 - k1
+      constexpr int ra = bit_reverse<32>(k1), rb = bit_reverse<32>(31 - k1);
+      const float2 za = v[ra], zb = v[rb];
+      float2 qa, qb;
+      qa.x = __shfl_sync(0xffffffffu, zb.x, partner);
+      qa.y = __shfl_sync(0xffffffffu, zb.y, partner);
+      qb.x = __shfl_sync(0xffffffffu, za.x, partner);
+      qb.y = __shfl_sync(0xffffffffu, za.y, partner);
+      if (lane == 0) {
+        qa = carry;                                // register (32 - k1) & 31
+        qb = v[bit_reverse<32>(k1 + 1)];           // register 32 - (31 - k1)
+        carry = zb;                                // register 31 - k1 = 32 - (k1 + 1): the next step's partner
+      }
+      const int ka = 32 * k1 + lane, kb = 32 * (31 - k1) + lane;
+      const float ga = 4.0f * grow[ka], gam = 4.0f * grow[1024 - ka];
+      const float gb = 4.0f * grow[kb], gbm = 4.0f * grow[1024 - kb];
+      float4 tw_dummy;
+      const float2 wa = reinterpret_cast<const float2*>(s_tw2)[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];
+      const float2 wb = reinterpret_cast<const float2*>(s_tw2)[(((31 - k1) >> 1) * 32 + lane) * 2 + ((31 - k1) & 1)];
+      (void)tw_dummy;
+      v[ra] = update(za, qa, ga, gam, wa, k1 == 0 && lane == 0);
+      v[rb] = update(zb, qb, gb, gbm, wb, false);
+    };
+    static_for<16>(pair_step);
+    __syncwarp();                                  // gradient row consumed
+
+    float2 u[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) u[r] = v[bit_reverse<32>(r)];      // natural order for the next pass (renaming only)
+    fft1024_mid(u, slab, s_tw1, lane);             // slab and row buffer free: fetch the next frame
+    uint32_t seq_next = seq, t_next = t + kFastWarps;
+    while (t_next >= frames_u) {
+      t_next -= frames_u;
+      ++seq_next;
+    }
+    const bool has_next = gi + kFastWarps < chunk1;
+    if (has_next) stage(gi + kFastWarps, seq_next, t_next);
+    dit_fft_fma<32>(u);                            // u[bit_reverse(m1)] = Y[32 m1 + lane], frame samples = conj(Y) pairs
+
+    float2* frow = reinterpret_cast<float2*>(frames_out + (int64_t)gi * 2048) + lane;
+#pragma unroll
+    for (int m1 = 0; m1 < 32; m1 += 2) {
+      const float4 w = reinterpret_cast<const float4*>(s_win)[(m1 >> 1) * 32 + lane];       // window * scale / 2
+      const float2 y0 = u[bit_reverse<32>(m1)], y1 = u[bit_reverse<32>(m1 + 1)];
+      __stcs(frow + 32 * m1, make_float2(y0.x * w.x, -y0.y * w.y));
+      __stcs(frow + 32 * (m1 + 1), make_float2(y1.x * w.z, -y1.y * w.w));
+    }
+    seq = seq_next;
+    t = t_next;
+  }
+}
+
+int launch_stft2048_backward(const StftParams& p, const float* gspec_fm, float* frames_out, cudaStream_t stream) {
+  const int64_t n_frames = p.g1 - p.g0;
+  if (n_frames <= 0) return TAC_OK;
+  TAC_REQUIRE(p.n_fft == 2048 && p.onesided, TAC_ERR_UNSUPPORTED, "stft2048_backward: n_fft = 2048, onesided only");
+  TAC_REQUIRE((reinterpret_cast<uintptr_t>(gspec_fm) & 15) == 0, TAC_ERR_INVALID, "stft2048_backward: gradient rows must be 16-byte aligned");
+  int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
+  const int grid = (int)(want < sm_count() ? want : sm_count());
+  using Kernel = void (*)(const StftParams, const float*, float*);
+  Kernel k = p.power_mode == 2 ? stft2048_backward_kernel<2> : (p.power_mode == 1 ? stft2048_backward_kernel<1> : stft2048_backward_kernel<0>);
+  TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
+  LaunchProbe probe(KIND_STFT, stream);
+  k<<<grid, kFastThreads, kFusedSmemBytes, stream>>>(p, gspec_fm, frames_out);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
 // n_fft = 2048 with the reference's public output layouts, (n_seq, 1025, frames[, 2]) with time innermost.
 // A frame's bins are 4 * frames bytes apart there, so per-frame stores would scatter 4-byte writes over 1025
 // rows.  Instead the CTA works on tiles of 16 consecutive frames of one sequence (warp w = frame t0 + w), the

@@ -220,6 +220,10 @@ static int launch_overlap_add(const StftBwdParams& bp, float* grad_x, cudaStream
   return TAC_OK;
 }
 
+static int launch_filterbank_backward(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,
+                                      const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands, float* grad_spec,
+                                      int frame_major_kpad, void* table_scratch, cudaStream_t stream);
+
 static int launch_stft_backward(StftBwdParams& bp, float* grad_x, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   const StftParams& p = bp.f;
   if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
@@ -306,6 +310,90 @@ filterbank_backward_kernel(const float* __restrict__ grad_y, int64_t sy_seq, int
   }
 }
 
+// The same contraction with a FRAME-MAJOR result, grad_spec[(s frames + t) kpad + k] (kpad = 1056 for 1025 bins,
+// padding bins zero): the row layout stft2048_backward_kernel bulk-copies.  A warp takes a frame of the tile, lanes walk
+// the bins, so the stores are coalesced; each bin's non-zero weights (at most four, true for every triangular
+// filterbank) sit in a shared-memory table built once per CTA; wider rows fall back to reading the matrix.
+// per-bin table of the matrix: non-zero column range and the first four weights of it.  One warp per bin, all bins in
+// parallel (built by every CTA of the contraction kernel, one bin after the other, it cost 80 us of load latency).
+__global__ void __launch_bounds__(kFbThreads)
+filterbank_table_kernel(const float* __restrict__ fb, int n_bins, int n_bands, int kpad, float4* __restrict__ w_out,
+                        int2* __restrict__ rg_out) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (kFbThreads / 32) + (threadIdx.x >> 5);
+  if (k >= kpad) return;
+  int lo = n_bands, hi = 0;
+  if (k < n_bins)
+    for (int m = lane; m < n_bands; m += 32)
+      if (__ldg(fb + (int64_t)k * n_bands + m) != 0.0f) {
+        lo = m < lo ? m : lo;
+        hi = m + 1;
+      }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (hi <= lo) lo = hi = 0;
+  float wv = 0.0f;
+  if (lane < 4 && lo + lane < hi) wv = __ldg(fb + (int64_t)k * n_bands + lo + lane);
+  const float w0 = __shfl_sync(0xffffffffu, wv, 0), w1 = __shfl_sync(0xffffffffu, wv, 1);
+  const float w2 = __shfl_sync(0xffffffffu, wv, 2), w3 = __shfl_sync(0xffffffffu, wv, 3);
+  if (lane == 0) {
+    w_out[k] = make_float4(w0, w1, w2, w3);
+    rg_out[k] = make_int2(lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(kFbThreads)
+filterbank_backward_fm_kernel(const float* __restrict__ grad_y, int64_t sy_seq, int64_t sy_band, int64_t sy_frame,
+                              const float* __restrict__ fb, int n_bins, int n_bands, int64_t frames, int tiles_per_seq,
+                              int64_t n_jobs, int kpad, const float4* __restrict__ g_w, const int2* __restrict__ g_rg,
+                              float* __restrict__ grad_spec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_w = reinterpret_cast<float4*>(smem_raw);                      // [kpad] weights of columns lo .. lo + 3
+  int2* s_rg = reinterpret_cast<int2*>(s_w + kpad);                       // [kpad] (lo, hi)
+  float* tile = reinterpret_cast<float*>(s_rg + kpad);                    // [n_bands + 3][kFbTileT + 1], last 3 rows zero
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kRow = kFbTileT + 1;
+  for (int k = tid; k < kpad; k += kFbThreads) {
+    s_w[k] = __ldg(g_w + k);
+    s_rg[k] = __ldg(g_rg + k);
+  }
+  for (int i = tid; i < 3 * kRow; i += kFbThreads) tile[n_bands * kRow + i] = 0.0f;
+  for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int64_t seq = job / tiles_per_seq;
+    const int64_t t0 = (job - seq * tiles_per_seq) * kFbTileT;
+    __syncthreads();
+    const float* gy = grad_y + seq * sy_seq;
+    if (sy_band == 1) {
+      for (int i = tid; i < n_bands * kFbTileT; i += kFbThreads) {
+        const int tt = i / n_bands, m = i - tt * n_bands;
+        tile[m * kRow + tt] = (t0 + tt < frames) ? __ldg(gy + (t0 + tt) * sy_frame + m) : 0.0f;
+      }
+    } else {
+      for (int i = tid; i < n_bands * kFbTileT; i += kFbThreads) {
+        const int m = i / kFbTileT, tt = i - m * kFbTileT;
+        tile[m * kRow + tt] = (t0 + tt < frames) ? __ldg(gy + (int64_t)m * sy_band + (t0 + tt) * sy_frame) : 0.0f;
+      }
+    }
+    __syncthreads();
+    for (int tt = warp; tt < kFbTileT && t0 + tt < frames; tt += kFbThreads / 32) {
+      float* out = grad_spec + (seq * frames + t0 + tt) * (int64_t)kpad;
+      for (int k = lane; k < kpad; k += 32) {
+        const int2 rg = s_rg[k];
+        float acc;
+        if (rg.y - rg.x <= 4) {
+          const float4 w = s_w[k];
+          const float* col = tile + rg.x * kRow + tt;
+          acc = fmaf(w.w, col[3 * kRow], fmaf(w.z, col[2 * kRow], fmaf(w.y, col[kRow], w.x * col[0])));
+        } else {
+          acc = 0.0f;
+          for (int m = rg.x; m < rg.y; ++m) acc = fmaf(__ldg(fb + (int64_t)k * n_bands + m), tile[m * kRow + tt], acc);
+        }
+        out[k] = acc;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pointwise backward
 // ---------------------------------------------------------------------------------------------------------------
@@ -374,26 +462,111 @@ extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64
   return launch_stft_backward(bp, grad_x, workspace, workspace_bytes, as_stream(stream));
 }
 
-extern "C" int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,
-                                           const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands,
-                                           float* grad_spec, void* stream) {
-  using namespace tac;
+namespace tac {
+static int launch_filterbank_backward(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,
+                                      const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands, float* grad_spec,
+                                      int frame_major_kpad, void* table_scratch, cudaStream_t stream) {
   TAC_REQUIRE(n_seq >= 0 && frames >= 0 && n_bins > 0 && n_bands > 0, TAC_ERR_INVALID, "filterbank_backward: bad shape");
   if (n_seq == 0 || frames == 0) return TAC_OK;
   TAC_REQUIRE(grad_y && fb_dev && grad_spec, TAC_ERR_INVALID, "filterbank_backward: null pointer");
-  const size_t smem = sizeof(float) * (size_t)n_bands * (kFbTileT + 1) + sizeof(int2) * (size_t)n_bins;
-  TAC_REQUIRE(smem <= 200 * 1024, TAC_ERR_UNSUPPORTED, "filterbank_backward: %d bands x %d bins exceed one CTA's shared memory",
-              n_bands, n_bins);
-  TAC_CUDA_OK(cudaFuncSetAttribute(filterbank_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles_per_seq = (int)((frames + kFbTileT - 1) / kFbTileT);
   const int64_t jobs = n_seq * tiles_per_seq;
   const int64_t cap = (int64_t)sm_count() * 4;
   const int grid = (int)(jobs < cap ? jobs : cap);
-  LaunchProbe probe(KIND_MELBANK, as_stream(stream));
-  filterbank_backward_kernel<<<grid, kFbThreads, smem, as_stream(stream)>>>(grad_y, stride_seq, stride_band, stride_frame, fb_dev,
-                                                                           n_bins, n_bands, frames, tiles_per_seq, jobs, grad_spec);
+  if (frame_major_kpad > 0) {
+    const size_t smem = (sizeof(float4) + sizeof(int2)) * (size_t)frame_major_kpad + sizeof(float) * (size_t)(n_bands + 3) * (kFbTileT + 1);
+    TAC_REQUIRE(smem <= 200 * 1024, TAC_ERR_UNSUPPORTED, "filterbank_backward: %d bands x %d bins exceed one CTA's shared memory",
+                n_bands, n_bins);
+    TAC_REQUIRE(table_scratch && (reinterpret_cast<uintptr_t>(table_scratch) & 15) == 0, TAC_ERR_INVALID,
+                "filterbank_backward: missing scratch for the per-bin table");
+    float4* g_w = static_cast<float4*>(table_scratch);                    // 24 bytes per bin, in the caller's workspace
+    int2* g_rg = reinterpret_cast<int2*>(g_w + frame_major_kpad);
+    TAC_CUDA_OK(cudaFuncSetAttribute(filterbank_backward_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      LaunchProbe probe(KIND_MELBANK, stream);
+      filterbank_table_kernel<<<(frame_major_kpad + 7) / 8, kFbThreads, 0, stream>>>(fb_dev, n_bins, n_bands, frame_major_kpad, g_w, g_rg);
+    }
+    LaunchProbe probe(KIND_MELBANK, stream);
+    filterbank_backward_fm_kernel<<<grid, kFbThreads, smem, stream>>>(grad_y, stride_seq, stride_band, stride_frame, fb_dev, n_bins,
+                                                                     n_bands, frames, tiles_per_seq, jobs, frame_major_kpad, g_w, g_rg,
+                                                                     grad_spec);
+  } else {
+    LaunchProbe probe(KIND_MELBANK, stream);
+    const size_t smem = sizeof(float) * (size_t)n_bands * (kFbTileT + 1) + sizeof(int2) * (size_t)n_bins;
+    TAC_REQUIRE(smem <= 200 * 1024, TAC_ERR_UNSUPPORTED, "filterbank_backward: %d bands x %d bins exceed one CTA's shared memory",
+                n_bands, n_bins);
+    TAC_CUDA_OK(cudaFuncSetAttribute(filterbank_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    filterbank_backward_kernel<<<grid, kFbThreads, smem, stream>>>(grad_y, stride_seq, stride_band, stride_frame, fb_dev, n_bins,
+                                                                  n_bands, frames, tiles_per_seq, jobs, grad_spec);
+  }
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
+}
+}  // namespace tac
+
+extern "C" int tac_filterbank_backward_f32(const float* grad_y, int64_t stride_seq, int64_t stride_band, int64_t stride_frame,
+                                           const float* fb_dev, int64_t n_seq, int64_t frames, int n_bins, int n_bands,
+                                           float* grad_spec, void* stream) {
+  return tac::launch_filterbank_backward(grad_y, stride_seq, stride_band, stride_frame, fb_dev, n_seq, frames, n_bins, n_bands,
+                                         grad_spec, 0, nullptr, tac::as_stream(stream));
+}
+
+// Backward of the whole Melspectrogram chain (stft -> |.|^power -> filterbank), d loss / d waveform from d loss / d mel.
+// Workspace = [filterbank-adjoint result | windowed frame gradients].  n_fft = 2048: frame-major filterbank adjoint ->
+// stft2048_backward_kernel (one warp per frame, stft.cu) -> overlap-add; other sizes: the generic kernels above.
+static int64_t melspec_backward_split(int64_t n_seq, int64_t frames, int n_fft, int n_bins, int64_t* spec_bytes) {
+  const int64_t rows = n_seq * frames;
+  int64_t a = (n_fft == 2048 ? rows * 1056 : rows * (int64_t)n_bins) * 4;
+  a = (a + 255) & ~(int64_t)255;
+  if (spec_bytes) *spec_bytes = a;
+  return a + rows * (int64_t)n_fft * 4 + 32768;          // + the per-bin table of the frame-major filterbank adjoint
+}
+
+extern "C" int64_t tac_melspec_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
+  if (n_fft <= 0 || hop <= 0 || n_seq <= 0) return 0;
+  return melspec_backward_split(n_seq, tac_stft_num_frames(n_samples, n_fft, hop, center), n_fft, n_fft / 2 + 1, nullptr);
+}
+
+extern "C" int tac_melspec_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
+                                        int n_fft, int hop, int center, int pad_mode, int normalized, float power,
+                                        const float* fb_dev, int n_bands, const float* grad_y, int64_t stride_seq,
+                                        int64_t stride_band, int64_t stride_frame, float* grad_x, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+  using namespace tac;
+  StftBwdParams bp;
+  const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
+  if (rc != TAC_OK) return rc;
+  StftParams& p = bp.f;
+  if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
+  TAC_REQUIRE(grad_x, TAC_ERR_INVALID, "melspec_backward: null gradient pointer");
+  cudaStream_t st = as_stream(stream);
+  if (p.g1 <= 0) {
+    TAC_CUDA_OK(cudaMemsetAsync(grad_x, 0, (size_t)p.n_seq * p.n_samples * sizeof(float), st));
+    return TAC_OK;
+  }
+  int64_t spec_bytes = 0;
+  const int64_t need = melspec_backward_split(p.n_seq, p.frames, n_fft, p.bins, &spec_bytes);
+  TAC_REQUIRE(workspace && workspace_bytes >= need, TAC_ERR_WORKSPACE,
+              "melspec_backward: workspace of %lld bytes, %lld needed (tac_melspec_backward_workspace_bytes)",
+              (long long)workspace_bytes, (long long)need);
+  float* gspec = static_cast<float*>(workspace);
+  bp.frames_out = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + spec_bytes);
+  bp.grad_out = gspec;
+  bp.power = power;
+  bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  p.power = power;
+  p.power_mode = bp.power_mode;
+  const bool fast = n_fft == 2048;
+  void* table = bp.frames_out + p.n_seq * p.frames * (int64_t)n_fft;     // the last 32 KB of the workspace
+  int rc2 = launch_filterbank_backward(grad_y, stride_seq, stride_band, stride_frame, fb_dev, p.n_seq, p.frames, p.bins, n_bands,
+                                       gspec, fast ? 1056 : 0, table, st);
+  if (rc2 != TAC_OK) return rc2;
+  if (fast) {
+    rc2 = launch_stft2048_backward(p, gspec, bp.frames_out, st);
+    if (rc2 != TAC_OK) return rc2;
+    return launch_overlap_add(bp, grad_x, st);
+  }
+  return launch_stft_backward(bp, grad_x, bp.frames_out, workspace_bytes - spec_bytes - 32768, st);
 }
 
 extern "C" int tac_amplitude_to_db_backward_f32(const float* x, const float* grad_out, int64_t n, float amin, float* grad_x,

@@ -78,3 +78,36 @@ def test_peer_gather_two_gpus(layout, to_db):
     assert not alive, "peer-gather worker hung"
     results = sorted(q.get(timeout=5) for _ in range(2))
     assert results == [(0, True), (1, True)]
+
+
+def test_peer_gather_single_rank():
+    """world_size 1 on one GPU: the peer allocation, the PEERS variant of the mel kernel and the flag barrier run
+    (this is what a single-GPU box can exercise of the N > 1 path); result identical to the plain call."""
+    import torch.distributed as dist
+    import torchaudio_contrib_b200 as tac
+    from torchaudio_contrib_b200.distributed import PeerGatheredOutput
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        torch.manual_seed(11)
+        dev = torch.device("cuda", 0)
+        x = torch.randn(3, 2, 20000, device=dev)
+        fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+        for layout in ("reference", "contiguous"):
+            prep = tac.PreparedMelspectrogram(x.shape, dev, fb, 2048, 512, to_db=True, layout=layout)
+            buf = PeerGatheredOutput(prep.out_shape, dev)
+            lib = tac._cabi.lib()
+            n0 = lib.tac_launch_count()
+            got = prep.gather_into(x, buf)
+            buf.barrier()
+            buf.check()
+            assert lib.tac_launch_count() - n0 == 2                 # the mel kernel + the barrier kernel
+            want = prep(x, prep.empty_output())
+            assert got.shape == want.shape and got.stride() == want.stride()
+            assert torch.equal(got, want)
+            with pytest.raises(RuntimeError):
+                prep.gather_into(x, buf, item_offset=1)              # would run past the gathered batch
+            buf.close()
+    finally:
+        dist.destroy_process_group()

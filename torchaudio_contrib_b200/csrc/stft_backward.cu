@@ -155,27 +155,55 @@ __device__ __forceinline__ float ola_padded(const float* __restrict__ fr, int q,
   return acc;
 }
 
-// grad_x[seq][j] = P(j + pad) + the padded positions that mirror / wrap onto j; `replicate` edges are finished by
-// overlap_add_edges_kernel (sample 0 and T - 1 collect `pad` positions each)
+// the padded positions that mirror / wrap onto waveform sample j (reflect / circular; replicate edges: see below)
+__device__ __forceinline__ float ola_folded(const float* __restrict__ fr, int j, int n_samples, int frames, int n_fft, int hop,
+                                            int pad, int pad_mode) {
+  float acc = 0.0f;
+  if (pad_mode == 0) {                                             // reflect: x[-k] = x[k], x[T-1+k] = x[T-1-k]
+    if (j >= 1 && j <= pad) acc += ola_padded(fr, pad - j, frames, n_fft, hop);
+    if (j >= n_samples - 1 - pad && j <= n_samples - 2) acc += ola_padded(fr, pad + 2 * (n_samples - 1) - j, frames, n_fft, hop);
+  } else if (pad_mode == 3) {                                      // circular
+    if (j >= n_samples - pad) acc += ola_padded(fr, j + pad - n_samples, frames, n_fft, hop);
+    if (j < pad) acc += ola_padded(fr, j + pad + n_samples, frames, n_fft, hop);
+  }
+  return acc;
+}
+
+// grad_x[seq][j] = P(j + pad) + folded positions.  VEC: four consecutive samples per thread with 16-byte loads (hop, pad,
+// n_fft and the row length multiples of 4: the four samples then sit in the same frames at the same offsets).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 overlap_add_kernel(const float* __restrict__ frames_ws, int64_t n_seq, int n_samples, int frames, int n_fft, int hop, int pad,
                    int pad_mode, float* __restrict__ grad_x) {
-  const int64_t total = n_seq * n_samples;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t seq = i / n_samples;
-    const int j = (int)(i - seq * n_samples);
+  constexpr int kPer = VEC ? 4 : 1;
+  const int j0 = (blockIdx.x * 256 + threadIdx.x) * kPer;
+  if (j0 >= n_samples) return;
+  for (int64_t seq = blockIdx.y; seq < n_seq; seq += gridDim.y) {
     const float* fr = frames_ws + seq * frames * (int64_t)n_fft;
-    float acc = ola_padded(fr, j + pad, frames, n_fft, hop);
-    if (pad > 0) {
-      if (pad_mode == 0) {                                           // reflect: x[-k] = x[k], x[T-1+k] = x[T-1-k]
-        if (j >= 1 && j <= pad) acc += ola_padded(fr, pad - j, frames, n_fft, hop);
-        if (j >= n_samples - 1 - pad && j <= n_samples - 2) acc += ola_padded(fr, pad + 2 * (n_samples - 1) - j, frames, n_fft, hop);
-      } else if (pad_mode == 3) {                                    // circular
-        if (j >= n_samples - pad) acc += ola_padded(fr, j + pad - n_samples, frames, n_fft, hop);
-        if (j < pad) acc += ola_padded(fr, j + pad + n_samples, frames, n_fft, hop);
+    float* out = grad_x + seq * n_samples + j0;
+    if constexpr (VEC) {
+      const int q = j0 + pad;
+      int t_lo = q + 3 - n_fft + 1;
+      t_lo = t_lo <= 0 ? 0 : (t_lo + hop - 1) / hop;
+      int t_hi = q / hop;
+      t_hi = t_hi > frames - 1 ? frames - 1 : t_hi;
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (int t = t_lo; t <= t_hi; ++t) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(fr + (int64_t)t * n_fft + (q - t * hop)));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
+      if (pad > 0 && (j0 <= pad || j0 + 3 >= n_samples - 1 - pad)) {
+        acc.x += ola_folded(fr, j0, n_samples, frames, n_fft, hop, pad, pad_mode);
+        acc.y += ola_folded(fr, j0 + 1, n_samples, frames, n_fft, hop, pad, pad_mode);
+        acc.z += ola_folded(fr, j0 + 2, n_samples, frames, n_fft, hop, pad, pad_mode);
+        acc.w += ola_folded(fr, j0 + 3, n_samples, frames, n_fft, hop, pad, pad_mode);
+      }
+      *reinterpret_cast<float4*>(out) = acc;
+    } else {
+      float acc = ola_padded(fr, j0 + pad, frames, n_fft, hop);
+      if (pad > 0) acc += ola_folded(fr, j0, n_samples, frames, n_fft, hop, pad, pad_mode);
+      *out = acc;
     }
-    grad_x[i] = acc;
   }
 }
 // replicate padding: sample 0 also receives padded positions [0, pad), sample T - 1 positions (pad + T - 1, T + 2 pad)
@@ -202,13 +230,18 @@ static int64_t backward_workspace_bytes(const StftParams& p) { return p.n_seq * 
 
 static int launch_overlap_add(const StftBwdParams& bp, float* grad_x, cudaStream_t stream) {
   const StftParams& p = bp.f;
-  const int64_t total = p.n_seq * p.n_samples;
-  const int64_t want = (total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
+  const bool vec = (p.hop & 3) == 0 && (p.pad & 3) == 0 && (p.n_fft & 3) == 0 && (p.n_samples & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(bp.frames_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_x) & 15) == 0;
+  const int per_block = 256 * (vec ? 4 : 1);
+  dim3 grid((unsigned)((p.n_samples + per_block - 1) / per_block), (unsigned)(p.n_seq < 32768 ? p.n_seq : 32768), 1);
   {
     LaunchProbe probe(KIND_POINTWISE, stream);
-    overlap_add_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(bp.frames_out, p.n_seq, (int)p.n_samples, (int)p.frames,
-                                                                        p.n_fft, p.hop, p.pad, p.pad_mode, grad_x);
+    if (vec)
+      overlap_add_kernel<true><<<grid, 256, 0, stream>>>(bp.frames_out, p.n_seq, (int)p.n_samples, (int)p.frames, p.n_fft, p.hop,
+                                                          p.pad, p.pad_mode, grad_x);
+    else
+      overlap_add_kernel<false><<<grid, 256, 0, stream>>>(bp.frames_out, p.n_seq, (int)p.n_samples, (int)p.frames, p.n_fft, p.hop,
+                                                           p.pad, p.pad_mode, grad_x);
   }
   TAC_CUDA_OK(cudaGetLastError());
   if (p.pad > 0 && p.pad_mode == TAC_PAD_REPLICATE) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- mel-spectrogram frames/sec (fft 2048 / hop 512) on N B200s, with roofline evidence.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|mulaw]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|mulaw]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of `Melspectrogram(num_mels=128, sample_rate=16000, fft_length=2048,
@@ -35,7 +35,17 @@ WORKLOADS = {
     # name: (batch, channels, samples, sample_rate, to_db)
     "cfg2": (64, 1, 160000, 16000, False),
     "cfg3": (256, 2, 480000, 48000, True),
+    # BASELINE config 4: batch 8192 split over the ranks (strong scaling: 8192 // world sequences per GPU)
+    "cfg4": (8192, 1, 160000, 16000, False),
 }
+
+
+def workload_of(name, world):
+    """(batch per rank, channels, samples, sample_rate, to_db, scaling)."""
+    batch, channels, samples, sr, to_db = WORKLOADS[name]
+    if name == "cfg4":
+        return batch // world, channels, samples, sr, to_db, "strong"
+    return batch, channels, samples, sr, to_db, "weak"
 N_FFT, HOP, N_MELS = 2048, 512, 128
 L2_BYTES = 126 << 20
 
@@ -240,7 +250,7 @@ def run_reference_arm(args, rank, world):
     """`--impl reference`: the reference's own CPU implementation, rank 0 only."""
     if rank != 0:
         return
-    batch, channels, samples, sr, to_db = WORKLOADS[args.workload]
+    batch, channels, samples, sr, to_db, _ = workload_of(args.workload, 1)
     run, kind = load_cpu_chain()
     nb = cpu_sample_batch(batch, channels, samples)
     x = torch.randn(nb, channels, samples, generator=torch.Generator().manual_seed(1234))
@@ -290,7 +300,7 @@ def run_ours(args, rank, world, local):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    batch, channels, samples, sr, to_db = WORKLOADS[args.workload]
+    batch, channels, samples, sr, to_db, scaling = workload_of(args.workload, world)
     frames = frames_of(samples)
     frames_per_step = batch * channels * frames
     in_bytes = 4 * batch * channels * samples
@@ -479,7 +489,7 @@ def run_ours(args, rank, world, local):
         line = {
             "metric": "mel-spectrogram frames/sec (fft=2048/hop=512)",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "%s: Melspectrogram(num_mels=128, sample_rate=%d, fft_length=2048, hop_length=512)%s on "

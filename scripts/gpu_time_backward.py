@@ -38,6 +38,15 @@ lib = tac._cabi.lib()
 print("forward only (no grad)            %.3f ms" % timed(lambda i: model(xs[i % 4].detach())))
 print("forward + backward, mel           %.3f ms" % timed(fwd_bwd(model)))
 print("forward + backward, mel + dB      %.3f ms" % timed(fwd_bwd(model_db)))
+spec = tac.Spectrogram(fft_length=2048, hop_length=512, power=2.0).to(dev)
+with torch.no_grad():
+    s0 = spec(xs[0])
+gy.append(torch.randn_like(s0))
+def spec_run(i):
+    x = xs[i % 4]
+    x.grad = None
+    spec(x).backward(gy[1])
+print("forward + backward, Spectrogram   %.3f ms" % timed(spec_run))
 import ctypes
 for name, m in (("mel", model), ("mel+dB", model_db)):
     lib.tac_profile_enable(1)

@@ -231,3 +231,27 @@ def test_backward_is_deterministic(tac):
         (gx,) = torch.autograd.grad(y, xg, gy)
         outs.append(gx)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("power,n_samples,pad_mode", [(2.0, 20000, "reflect"), (1.0, 7001, "reflect"), (2.0, 4096, "constant"),
+                                                      (0.7, 12288, "replicate")])
+def test_spectrogram_2048_backward(tac, power, n_samples, pad_mode):
+    """Spectrogram at n_fft 2048: the public-layout gradient is transposed to frame-major and takes the warp-per-frame
+    adjoint kernel."""
+    torch.manual_seed(int(n_samples + 10 * power))
+    x = torch.randn(3, 2, n_samples)
+    win64 = torch.hann_window(2048, dtype=torch.float64)
+
+    def ref(t):
+        return oc.spectrogram(t, 2048, 512, pad_mode=pad_mode, power=power)
+
+    gy = torch.randn(ref(x).shape)
+    want = _oracle_grad(ref, x, gy)
+    want64 = _oracle_grad(lambda t: oc.spectrogram(t, 2048, 512, window=win64, pad_mode=pad_mode, power=power), x.double(), gy.double())
+    # p <= 1: d|X|^p / dX ~ X / |X|^(2-p) is ill-conditioned at bins that vanish in exact arithmetic (the reflected edge
+    # frames are symmetric, so whole sets of bins do): any fp32 evaluation is off by O(rounding / |X|) there
+    tol = max(REL if power > 1.0 else 3e-4, 10.0 * rel_err(want, want64))
+    model = tac.Spectrogram(fft_length=2048, hop_length=512, pad_mode=pad_mode, power=power).cuda()
+    _, gx = _gpu_grad(model, x, gy)
+    assert rel_err(gx, want64) < tol

@@ -427,6 +427,28 @@ filterbank_backward_fm_kernel(const float* __restrict__ grad_y, int64_t sy_seq, 
   }
 }
 
+// (n_seq, n_bins, frames) -> frame-major (n_seq * frames, kpad) with zero padding bins: what stft2048_backward_kernel
+// bulk-copies, for a gradient that arrives in the reference's public Spectrogram layout.  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+spec_to_frame_major_kernel(const float* __restrict__ src, int n_bins, int64_t frames, int kpad, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int64_t seq = blockIdx.z;
+  const int k0 = blockIdx.y * 32;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                  // 32 x 8
+  const float* s = src + seq * n_bins * frames;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r;
+    tile[r][tx] = (k < n_bins && t0 + tx < frames) ? __ldg(s + (int64_t)k * frames + t0 + tx) : 0.0f;
+  }
+  __syncthreads();
+  float* d = dst + seq * frames * kpad;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t t = t0 + r;
+    if (t < frames && k0 + tx < kpad) d[t * kpad + k0 + tx] = tile[tx][r];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pointwise backward
 // ---------------------------------------------------------------------------------------------------------------
@@ -461,7 +483,9 @@ static int pointwise_grid(int64_t n) {
 
 extern "C" int64_t tac_stft_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
   if (n_fft <= 0 || hop <= 0 || n_seq <= 0) return 0;
-  return n_seq * tac_stft_num_frames(n_samples, n_fft, hop, center) * (int64_t)n_fft * 4;
+  const int64_t rows = n_seq * tac_stft_num_frames(n_samples, n_fft, hop, center);
+  // frame gradients; n_fft = 2048 adds the frame-major copy of a Spectrogram gradient (1056 floats per frame)
+  return rows * (int64_t)n_fft * 4 + (n_fft == 2048 ? rows * 1056 * 4 : 0);
 }
 
 extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_samples, const float* window, int n_fft,
@@ -492,6 +516,29 @@ extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64
   bp.grad_out = grad_out;
   bp.power = power;
   bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+  StftParams& p = bp.f;
+  const int64_t rows = p.n_seq * p.frames;
+  if (n_fft == 2048 && onesided && rows > 0 && p.n_samples > 0 && p.n_seq < 65536) {
+    // warp-per-frame kernel of stft.cu: it wants the gradient frame-major
+    const int64_t frames_bytes = rows * 2048 * 4, need = frames_bytes + rows * 1056 * 4;
+    TAC_REQUIRE(workspace && workspace_bytes >= need, TAC_ERR_WORKSPACE,
+                "spectrogram_backward: workspace of %lld bytes, %lld needed (tac_stft_backward_workspace_bytes)",
+                (long long)workspace_bytes, (long long)need);
+    bp.frames_out = static_cast<float*>(workspace);
+    float* gspec = bp.frames_out + rows * 2048;
+    cudaStream_t st = as_stream(stream);
+    {
+      LaunchProbe probe(KIND_POINTWISE, st);
+      dim3 grid((unsigned)((p.frames + 31) / 32), (unsigned)(1056 / 32), (unsigned)p.n_seq);
+      spec_to_frame_major_kernel<<<grid, 256, 0, st>>>(grad_out, p.bins, p.frames, 1056, gspec);
+    }
+    TAC_CUDA_OK(cudaGetLastError());
+    p.power = power;
+    p.power_mode = bp.power_mode;
+    const int rc2 = launch_stft2048_backward(p, gspec, bp.frames_out, st);
+    if (rc2 != TAC_OK) return rc2;
+    return launch_overlap_add(bp, grad_x, st);
+  }
   return launch_stft_backward(bp, grad_x, workspace, workspace_bytes, as_stream(stream));
 }
 

@@ -640,10 +640,8 @@ stft2048_backward_kernel(const StftParams p, const float* __restrict__ gspec, fl
       const int ka = 32 * k1 + lane, kb = 32 * (31 - k1) + lane;
       const float ga = 4.0f * grow[ka], gam = 4.0f * grow[1024 - ka];
       const float gb = 4.0f * grow[kb], gbm = 4.0f * grow[1024 - kb];
-      float4 tw_dummy;
-      const float2 wa = reinterpret_cast<const float2*>(s_tw2)[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];
-      const float2 wb = reinterpret_cast<const float2*>(s_tw2)[(((31 - k1) >> 1) * 32 + lane) * 2 + ((31 - k1) & 1)];
-      (void)tw_dummy;
+      const float2 wa = s_tw2[((k1 >> 1) * 32 + lane) * 2 + (k1 & 1)];                      // W_2048^ka (pair-interleaved table)
+      const float2 wb = s_tw2[(((31 - k1) >> 1) * 32 + lane) * 2 + ((31 - k1) & 1)];        // W_2048^kb
       v[ra] = update(za, qa, ga, gam, wa, k1 == 0 && lane == 0);
       v[rb] = update(zb, qb, gb, gbm, wb, false);
     };

@@ -255,3 +255,21 @@ def test_spectrogram_2048_backward(tac, power, n_samples, pad_mode):
     model = tac.Spectrogram(fft_length=2048, hop_length=512, pad_mode=pad_mode, power=power).cuda()
     _, gx = _gpu_grad(model, x, gy)
     assert rel_err(gx, want64) < tol
+
+
+@pytest.mark.gpu
+def test_mel_2048_backward_dense_filterbank(tac):
+    """A dense (random) filterbank at n_fft 2048: forward on the tensor-core path, backward through the wide-row branch
+    of the frame-major filterbank adjoint and the warp-per-frame kernel."""
+    torch.manual_seed(8)
+    x = torch.randn(2, 1, 14000)
+    fb = torch.randn(1025, 24).abs()
+
+    def ref(t):
+        return oc.apply_filterbank(oc.spectrogram(t, 2048, 512, power=2.0), fb)
+
+    gy = torch.randn(ref(x).shape)
+    want = _oracle_grad(ref, x, gy)
+    y, gx = _gpu_grad(lambda t: tac.functional.melspectrogram(t, fb.cuda(), 2048, 512), x, gy)
+    assert rel_err(y, ref(x)) < REL
+    assert rel_err(gx, want) < REL

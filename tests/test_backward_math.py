@@ -1,0 +1,89 @@
+"""CPU checks of the mathematics behind the adjoint kernels (csrc/stft.cu `stft2048_backward_kernel`,
+csrc/stft_backward.cu `overlap_add_kernel`): numpy float64 models that follow the kernels' formulas, against torch
+autograd through the reference's operators (torch.stft's framing / padding, rfft, |.|^p).  No GPU, no library call."""
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.mark.parametrize("power", [2.0, 1.0, 0.7])
+def test_collapsed_untangle_gain_retangle(power):
+    """Zt_k = 2[(sigma + delta Im W^k) Zh_k + i delta Re W^k conj Zh_{C-k}] (k = 0 doubled), then an inverse complex FFT of
+    size C = N/2 whose (Re, Im) pairs are the (even, odd) samples: equals d/dx sum_k g_k |rfft(x w)_k|^p."""
+    rng = np.random.default_rng(int(10 * power))
+    N, C = 2048, 1024
+    x, g = rng.standard_normal(N), rng.standard_normal(C + 1)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)
+
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    X = torch.fft.rfft(xt * torch.tensor(w))
+    mag2 = X.real ** 2 + X.imag ** 2
+    (torch.tensor(g) * (mag2 if power == 2.0 else mag2 ** (power / 2))).sum().backward()
+    want = xt.grad.numpy()
+
+    xw = 0.5 * x * w                                         # the kernels' window table carries the 1/2
+    zh = np.fft.fft(xw[0::2] + 1j * xw[1::2])                # Zh: what both register passes of the forward kernel produce
+    k = np.arange(C)
+    wk = np.exp(-2j * np.pi * k / N)
+    q = zh[(C - k) % C]
+    p_, q_ = zh, np.conj(q)
+    s_, d_ = p_ + q_, -1j * wk * (p_ - q_)                   # X_k = S + D, conj X_{C-k} = S - D
+
+    def gain(n2):                                            # (p / 2) |X|^(p - 2)
+        return np.ones_like(n2) if power == 2.0 else 0.5 * power * n2 ** (0.5 * power - 1.0)
+
+    hk = g[k] * gain(np.abs(s_ + d_) ** 2)
+    hm = g[C - k] * gain(np.abs(s_ - d_) ** 2)
+    sigma, delta = hk + hm, hk - hm
+    zt = 2 * ((sigma + delta * wk.imag) * p_ + 1j * delta * wk.real * q_)
+    zt[0] *= 2                                               # H_0 = G_0, not G_0 / 2
+    y = np.fft.ifft(zt) * C                                  # unnormalised inverse
+    grad = np.empty(N)
+    grad[0::2], grad[1::2] = y.real, y.imag
+    grad *= w
+    assert np.abs(grad - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def _ola_model(frames_ws, n_samples, n_fft, hop, pad, pad_mode):
+    """overlap_add_kernel (+ overlap_add_edges_kernel) statement for statement."""
+    n_frames = frames_ws.shape[0]
+
+    def padded(qpos):
+        t_lo = qpos - n_fft + 1
+        t_lo = 0 if t_lo <= 0 else (t_lo + hop - 1) // hop
+        t_hi = min(qpos // hop, n_frames - 1)
+        return sum(frames_ws[t, qpos - t * hop] for t in range(t_lo, t_hi + 1))
+
+    out = np.zeros(n_samples)
+    for j in range(n_samples):
+        acc = padded(j + pad)
+        if pad > 0:
+            if pad_mode == "reflect":
+                if 1 <= j <= pad:
+                    acc += padded(pad - j)
+                if n_samples - 1 - pad <= j <= n_samples - 2:
+                    acc += padded(pad + 2 * (n_samples - 1) - j)
+            elif pad_mode == "circular":
+                if j >= n_samples - pad:
+                    acc += padded(j + pad - n_samples)
+                if j < pad:
+                    acc += padded(j + pad + n_samples)
+        out[j] = acc
+    if pad > 0 and pad_mode == "replicate":
+        out[0] += sum(padded(qpos) for qpos in range(pad))
+        out[n_samples - 1] += sum(padded(pad + n_samples + qpos) for qpos in range(pad))
+    return out
+
+
+@pytest.mark.parametrize("pad_mode", ["reflect", "constant", "replicate", "circular"])
+@pytest.mark.parametrize("n_samples,n_fft,hop,center", [(100, 32, 8, True), (77, 32, 12, True), (64, 16, 16, True), (90, 32, 8, False)])
+def test_overlap_add_is_the_adjoint_of_padding_and_framing(pad_mode, n_samples, n_fft, hop, center):
+    rng = np.random.default_rng(n_samples + hop)
+    pad = n_fft // 2 if center else 0
+    x = torch.tensor(rng.standard_normal(n_samples), dtype=torch.float64, requires_grad=True)
+    xp = torch.nn.functional.pad(x.view(1, 1, -1), (pad, pad), mode=pad_mode).view(-1) if pad else x
+    fr = xp.unfold(0, n_fft, hop)                            # torch.stft's framing of the padded signal
+    gfr = torch.tensor(rng.standard_normal(tuple(fr.shape)))
+    (fr * gfr).sum().backward()
+    got = _ola_model(gfr.numpy(), n_samples, n_fft, hop, pad, pad_mode)
+    assert np.abs(got - x.grad.numpy()).max() < 1e-12

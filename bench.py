@@ -388,12 +388,15 @@ def run_ours(args, rank, world, local):
         e2e_steps = max(3, min(args.steps, 20))
         for i in range(3):
             hp(host_in[i % 2], out=host_out)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            hp(host_in[i % 2], out=host_out)
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
+        e2e_s = None
+        for _ in range(3):                                  # wall-clock timing: keep the best of three passes
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                hp(host_in[i % 2], out=host_out)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            e2e_s = dt if e2e_s is None else min(e2e_s, dt)
         barrier()
 
     # optional output all-gather (BASELINE config 4): every rank ends up with the (world*batch, C, M, frames)

@@ -249,3 +249,54 @@ def test_missing_library_fails_loudly(tac, tmp_path):
             tac._cabi.load(str(tmp_path / "absent.so"))
         finally:
             tac._cabi._lib = saved
+
+
+# ---------------------------------------------------------------------------------------- backward / multi-GPU host logic
+def test_backward_workspace_sizes_and_argument_checks(tac):
+    """Workspace formulas of the adjoint entry points, and that a too-small workspace is refused before any launch."""
+    lib = tac._cabi.lib()
+    frames = lib.tac_stft_num_frames(160000, 2048, 512, 1)
+    assert frames == 313
+    rows = 64 * frames
+    assert lib.tac_stft_backward_workspace_bytes(64, 160000, 2048, 512, 1) == rows * 2048 * 4 + rows * 1056 * 4
+    assert lib.tac_stft_backward_workspace_bytes(64, 160000, 512, 128, 1) == 64 * lib.tac_stft_num_frames(160000, 512, 128, 1) * 512 * 4
+    assert lib.tac_stft_backward_workspace_bytes(0, 160000, 512, 128, 1) == 0
+    a = (rows * 1056 * 4 + 255) // 256 * 256
+    assert lib.tac_melspec_backward_workspace_bytes(64, 160000, 2048, 512, 1) == a + rows * 2048 * 4 + 32768
+    f1k = lib.tac_stft_num_frames(160000, 1024, 256, 1)
+    a = (64 * f1k * 513 * 4 + 255) // 256 * 256
+    assert lib.tac_melspec_backward_workspace_bytes(64, 160000, 1024, 256, 1) == a + 64 * f1k * 1024 * 4 + 32768
+    # argument validation happens on the host, before any CUDA call: fake non-null pointers are never dereferenced
+    fake = ctypes.c_void_p(4096)
+    rc = lib.tac_melspec_backward_f32(fake, 2, 8000, 8000, fake, 2048, 512, 1, 0, 0, 2.0, fake, 128, fake, 128 * 16, 16, 1,
+                                      fake, fake, 1024, None)
+    assert rc == tac._cabi.TAC_ERR_WORKSPACE
+    assert b"tac_melspec_backward_workspace_bytes" in lib.tac_last_error()
+    rc = lib.tac_melspec_backward_f32(fake, 2, 900, 900, fake, 2048, 512, 1, 0, 0, 2.0, fake, 128, fake, 128, 1, 1, fake, fake, 1 << 30, None)
+    assert rc == tac._cabi.TAC_ERR_INVALID and b"Padding size" in lib.tac_last_error()       # reflect pad >= length, like the forward
+
+
+def test_one_kernel_path_predicate(tac, monkeypatch):
+    """`_mel_frame_major`: which calls write the frame-major buffer (one-kernel path, reference layout)."""
+    F = tac.functional
+    tri = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+    dense = torch.rand(1025, 24) + 0.1
+    cpu = torch.device("cpu")
+    assert F._mel_frame_major(tri, 2048, "reference", cpu, None) is True
+    assert F._mel_frame_major(tri, 2048, "contiguous", cpu, None) is False
+    assert F._mel_frame_major(dense, 2048, "reference", cpu, None) is False                 # tensor-core path
+    tri_small = tac.MelFilterbank(num_freqs=513, num_mels=64, sample_rate=16000).get_filterbank()
+    assert F._mel_frame_major(tri_small, 1024, "reference", cpu, None) is False
+    monkeypatch.setenv("TAC_MELSPEC_FUSED", "0")
+    assert F._mel_frame_major(tri, 2048, "reference", cpu, None) is False
+
+
+def test_gradient_dispatch_helpers(tac):
+    F = tac.functional
+    x = torch.zeros(4, requires_grad=True)
+    assert F._wants_grad(x) and not F._wants_grad(x.detach()) and not F._wants_grad(None)
+    with torch.no_grad():
+        assert not F._wants_grad(x)
+    F._no_param_grad(torch.zeros(3), "window")                                             # constants without grad are fine
+    with pytest.raises(RuntimeError, match="signal only"):
+        F._no_param_grad(x, "filterbank")

@@ -719,8 +719,9 @@ class PreparedMelspectrogram(object):
                 or out.device != self.device):
             raise RuntimeError("PreparedMelspectrogram: expected contiguous float32 x %s and out %s on %s"
                                % (self.shape, self.out_shape, self.device))
-        _cabi.check(self._fn(_cabi.ptr(x), *self._head, _cabi.ptr(out), *self._tail,
-                             ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        with torch.cuda.device(self.device):
+            _cabi.check(self._fn(_cabi.ptr(x), *self._head, _cabi.ptr(out), *self._tail,
+                                 ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out.transpose(-2, -1) if self.frame_major else out
 
     def gather_into(self, x, gathered, item_offset=None):
@@ -745,10 +746,11 @@ class PreparedMelspectrogram(object):
             raise RuntimeError("gather_into: items [%d, %d) outside the gathered batch of %d"
                                % (item_offset, item_offset + self.shape[0], full[0]))
         seq_per_item = self.n_seq // max(self.shape[0], 1)
-        _cabi.check(_cabi.lib().tac_melspec_banded_peers_f32(
-            _cabi.ptr(x), *self._head, ctypes.cast(gathered.payload_array, ctypes.c_void_p), gathered.world,
-            int(item_offset) * seq_per_item, int(self.frame_major),
-            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().tac_melspec_banded_peers_f32(
+                _cabi.ptr(x), *self._head, ctypes.cast(gathered.payload_array, ctypes.c_void_p), gathered.world,
+                int(item_offset) * seq_per_item, int(self.frame_major),
+                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return gathered.tensor.transpose(-2, -1) if self.frame_major else gathered.tensor
 
 

@@ -3,7 +3,7 @@
 This is what a caller holding host memory binds -- the reference's CPU-runnable configuration
 (`Spectrogram(fft_length=512, hop_length=128)` on a CPU tensor) goes through here.  It is not a
 CPU fallback: the library copies the batch to the device in slices, runs the same kernels and
-copies the result back, overlapping both copy directions with compute on two streams.
+copies the result back, overlapping both copy directions with compute (one stream each for H2D, kernels, D2H).
 """
 import ctypes
 
@@ -59,7 +59,8 @@ class HostPipeline(object):
             out = torch.empty(shape, dtype=torch.float32)
         elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype != torch.float32:
             raise RuntimeError("HostPipeline: `out` must be a contiguous float32 tensor of shape %s" % (shape,))
-        _cabi.check(_cabi.lib().tac_pipeline_run_host(self._handle, _cabi.ptr(x), n_seq, n_samples, _cabi.ptr(out)))
+        with torch.cuda.device(self.device):               # the library selects its device; restore the caller's afterwards
+            _cabi.check(_cabi.lib().tac_pipeline_run_host(self._handle, _cabi.ptr(x), n_seq, n_samples, _cabi.ptr(out)))
         return out
 
     def close(self):

@@ -162,3 +162,41 @@ def test_skipped_bands_are_rejected_or_exact():
         power = np.abs(np.random.default_rng(1).standard_normal((1, 1025))).astype(np.float32)
         np.testing.assert_allclose(kernel_model(blob, handle, power, 700), power.astype(np.float64) @ fb, rtol=2e-6,
                                    atol=1e-30)
+
+
+# ------------------------------------------------------------------------------- index logic of stft2048_kernel, modelled
+def test_contiguous_chunks_partition_the_frames():
+    """csrc/stft.cu: CTA b takes frames [chunk0, chunk1) with chunk sizes differing by at most one."""
+    for n_all, grid in [(20032, 148), (480256, 148), (7, 148), (148, 148), (149, 148), (2368, 148), (1, 1), (33, 3)]:
+        per, extra = divmod(n_all, grid)
+        covered = []
+        for b in range(grid):
+            c0 = b * per + min(b, extra)
+            c1 = c0 + per + (1 if b < extra else 0)
+            covered.extend(range(c0, c1))
+            assert c1 - c0 in (per, per + 1)
+        assert covered == list(range(n_all))
+
+
+def test_stash_stores_are_bank_conflict_free():
+    """The two store instructions of one untangling step (csrc/stft.cu emit2): `dst` = (row k1, column lane) and the
+    mirror = (row 31 - k1, column 32 - lane), lane 0's mirror at (row 32 - k1, column 0) moved one float down
+    (bandplan.cuh kStashShiftRow).  Every lane must hit its own bank, and every bin its own float."""
+    owner = {}
+    for k1 in range(16):
+        dst = [k1 * STRIDE + lane for lane in range(32)]
+        mir = [(STRIDE - 1 if lane == 0 else 32 - lane) + (31 - k1) * STRIDE for lane in range(32)]
+        for addrs in (dst, mir):
+            assert len({a % 32 for a in addrs}) == 32
+        for lane in range(32):
+            k = 32 * k1 + lane
+            owner[dst[lane]] = k
+            owner[mir[lane]] = 1024 - k
+    owner[16 * STRIDE] = 512                                  # lane 0, step k1 = 16 (its own mirror)
+    assert len(owner) == 1025 and sorted(owner.values()) == list(range(1025))
+    # the consumer's view: lane l reads bins 32 l + i at l * 33 + i, column 0 of rows >= 17 one float lower
+    for lane in range(32):
+        for i in range(32):
+            addr = lane * STRIDE + i - (1 if (i == 0 and lane >= SHIFT_ROW) else 0)
+            assert owner[addr] == 32 * lane + i
+    assert owner[NYQ] == 1024

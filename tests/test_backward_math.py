@@ -87,3 +87,27 @@ def test_overlap_add_is_the_adjoint_of_padding_and_framing(pad_mode, n_samples, 
     (fr * gfr).sum().backward()
     got = _ola_model(gfr.numpy(), n_samples, n_fft, hop, pad, pad_mode)
     assert np.abs(got - x.grad.numpy()).max() < 1e-12
+
+
+def test_in_place_pairing_of_the_backward_kernel():
+    """stft2048_backward_kernel's combine loop (csrc/stft.cu): step (k1, 31 - k1) overwrites registers k1 and 31 - k1 of
+    every lane; partners come by shuffle from lane 32 - l (registers 31 - k1 and k1), except lane 0, which pairs with its
+    own registers 32 - k1 (carried from the previous step, already overwritten) and k1 + 1.  Model: registers hold the
+    bin index they were loaded with, or -1 once overwritten; every bin k must meet bin (1024 - k) mod 1024, untouched."""
+    reg = [[32 * k1 + lane for k1 in range(32)] for lane in range(32)]        # reg[lane][k1]
+    met = {}
+    carry = reg[0][0]
+    for k1 in range(16):
+        za = [reg[lane][k1] for lane in range(32)]
+        zb = [reg[lane][31 - k1] for lane in range(32)]
+        qa = [zb[(32 - lane) & 31] for lane in range(32)]                     # shuffles read before anything is written
+        qb = [za[(32 - lane) & 31] for lane in range(32)]
+        qa[0], qb[0] = carry, reg[0][k1 + 1]
+        carry = zb[0]
+        for lane in range(32):
+            met[za[lane]] = qa[lane]
+            met[zb[lane]] = qb[lane]
+            reg[lane][k1] = reg[lane][31 - k1] = -1
+    assert sorted(met) == list(range(1024))
+    for k, partner in met.items():
+        assert partner == (1024 - k) % 1024, (k, partner)

@@ -257,6 +257,11 @@ int tac_pipeline_destroy(tac_pipeline* p);
 int64_t tac_launch_count(void);
 int tac_profile_enable(int on);
 int tac_profile_read(double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
+/* Which kernel serves the one-kernel mel path (tac_melspec_banded_f32 and everything built on it):
+ * 0 (default) = two frames per warp in packed fp32 pairs (csrc/stft_pair.cu), 1 = one frame per warp
+ * (csrc/stft.cu, round 1).  The two agree bit for bit; the switch exists for A/B timing and that test.
+ * Returns the previous value; a negative argument only queries.  Environment: TAC_MEL_SINGLE=1. */
+int tac_mel_kernel_variant(int variant);
 
 #ifdef __cplusplus
 }

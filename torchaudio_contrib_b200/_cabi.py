@@ -70,6 +70,7 @@ SIGNATURES = {
     "tac_launch_count": (_i64, []),
     "tac_profile_enable": (_int, [_int]),
     "tac_profile_read": (_int, [_c.POINTER(_c.c_double), _c.POINTER(_i64)]),
+    "tac_mel_kernel_variant": (_int, [_int]),
 }
 
 

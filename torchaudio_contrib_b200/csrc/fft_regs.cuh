@@ -8,6 +8,8 @@
 
 #include <cuda_runtime.h>
 
+#include "f32x2.cuh"
+
 namespace tac {
 
 // cos(2*pi*q/64), q = 0..16 (first quadrant); rounded once from the double value
@@ -152,6 +154,60 @@ template <int N>
 __device__ __forceinline__ void dit_fft_fma(float2 (&v)[N]) {
   static_assert(N >= 2 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two in [2, 64]");
   dit_stages<N, 2>(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same FMA-form DIT network over a generic real type R (float, or the packed pair `pk` of f32x2.cuh: two
+// frames per warp, every butterfly one FADD2 / FFMA2 per component for both).  cx<R> v[N]; contract as above.
+// The packed instructions have no negated addend, so the cotangent form keeps -pi and flips the sign of g.
+// ---------------------------------------------------------------------------------------------
+template <int J, int M, class R>
+__device__ __forceinline__ void dit_butterfly_r(cx<R>& u, cx<R>& b) {
+  static_assert(M <= 64 && 64 % M == 0 && J >= 0 && 2 * J < M, "twiddle out of range");
+  if constexpr (J == 0) {
+    const R ur = u.x, ui = u.y;
+    u.x = ur + b.x; u.y = ui + b.y;
+    b.x = ur - b.x; b.y = ui - b.y;
+  } else if constexpr (4 * J == M) {               // w = -i
+    const R ur = u.x, ui = u.y, br = b.x, bi = b.y;
+    u.x = ur + bi; u.y = ui - br;
+    b.x = ur - bi; b.y = ui + br;
+  } else {
+    constexpr double c = (double)cos64(J * (64 / M)), sn = (double)sin64(J * (64 / M));
+    const R ur = u.x, ui = u.y;
+    if constexpr ((c >= 0 ? c : -c) >= (sn >= 0 ? sn : -sn)) {
+      constexpr float t = (float)(sn / c), g = (float)c;
+      const R pr = pfma(t, b.y, b.x);              // w b = g (pr + i pi)
+      const R pi = pfma(-t, b.x, b.y);
+      u.x = pfma(g, pr, ur); u.y = pfma(g, pi, ui);
+      b.x = pfma(-g, pr, ur); b.y = pfma(-g, pi, ui);
+    } else {
+      constexpr float ct = (float)(c / sn), g = (float)sn;
+      const R pr = pfma(ct, b.x, b.y);             // w b = g (pr - i npi)
+      const R npi = pfma(-ct, b.y, b.x);
+      u.x = pfma(g, pr, ur); u.y = pfma(-g, npi, ui);
+      b.x = pfma(-g, pr, ur); b.y = pfma(g, npi, ui);
+    }
+  }
+}
+
+template <int N, int M, int K, int J, class R>
+__device__ __forceinline__ void dit_stage_walk_r(cx<R> (&v)[N]) {
+  dit_butterfly_r<J, M, R>(v[bit_reverse<N>(K + J)], v[bit_reverse<N>(K + J + M / 2)]);
+  if constexpr (J + 1 < M / 2) dit_stage_walk_r<N, M, K, J + 1, R>(v);
+  else if constexpr (K + M < N) dit_stage_walk_r<N, M, K + M, 0, R>(v);
+}
+
+template <int N, int M, class R>
+__device__ __forceinline__ void dit_stages_r(cx<R> (&v)[N]) {
+  dit_stage_walk_r<N, M, 0, 0, R>(v);
+  if constexpr (2 * M <= N) dit_stages_r<N, 2 * M, R>(v);
+}
+
+template <int N, class R>
+__device__ __forceinline__ void dit_fft_fma_r(cx<R> (&v)[N]) {
+  static_assert(N >= 2 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two in [2, 64]");
+  dit_stages_r<N, 2, R>(v);
 }
 
 }  // namespace tac

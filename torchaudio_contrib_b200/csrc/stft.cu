@@ -891,10 +891,21 @@ int dump_k1_trace() {
   return TAC_OK;
 }
 
+static int g_mel_variant = -1;
+static int mel_kernel_variant() {
+  if (g_mel_variant < 0) g_mel_variant = getenv("TAC_MEL_SINGLE") ? 1 : 0;
+  return g_mel_variant;
+}
+
 int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
   if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024)) return launch_stft_warp(p, stream);
+  if (p.n_fft == 2048 && p.onesided && (p.out_mode == OUT_MEL_FUSED || p.out_mode == OUT_MEL_FUSED_PEERS)) {
+    // two frames per warp in packed fp32 pairs (stft_pair.cu); TAC_MEL_SINGLE=1 keeps the one-frame-per-warp kernel
+    // below (A/B timing and the bit-equality test of the two)
+    if (mel_kernel_variant() == 0 && stft2048_pair_applies(p)) return launch_stft2048_pair(p, stream);
+  }
   if (p.n_fft == 2048 && p.onesided) {
     const bool whole = p.g0 == 0 && p.g1 == p.n_seq * p.frames;       // the tiled public kernel walks whole sequences
     int64_t want = (n_frames + kFastWarps - 1) / kFastWarps;
@@ -993,6 +1004,12 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
 }
 
 }  // namespace tac
+
+extern "C" int tac_mel_kernel_variant(int variant) {
+  const int prev = tac::mel_kernel_variant();
+  if (variant >= 0) tac::g_mel_variant = variant ? 1 : 0;
+  return prev;
+}
 
 extern "C" int tac_debug_dump_k1_trace(void) { return tac::dump_k1_trace(); }
 

@@ -161,6 +161,9 @@ int launch_stft_warp(const StftParams& p, cudaStream_t stream);   // stft_multi.
 int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                      const float* window, int n_fft, int hop, int center, int pad_mode, int normalized, int onesided);
 int launch_stft(const StftParams& p, cudaStream_t stream);
+// stft_pair.cu: the one-kernel mel path (OUT_MEL_FUSED / OUT_MEL_FUSED_PEERS, n_fft = 2048) with two frames per warp
+bool stft2048_pair_applies(const StftParams& p);    // hop <= 512 and even, whole sequences
+int launch_stft2048_pair(const StftParams& p, cudaStream_t stream);
 // stft.cu: backward of stft + |.|^p for n_fft = 2048; gspec_fm: (frames of the launch, 1056) frame-major gradient of
 // |X|^p, frames_out: (frames of the launch, 2048) windowed frame gradients (p.power / p.power_mode as in the forward pass)
 int launch_stft2048_backward(const StftParams& p, const float* gspec_fm, float* frames_out, cudaStream_t stream);

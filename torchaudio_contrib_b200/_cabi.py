@@ -91,11 +91,14 @@ class TacError(RuntimeError):
 _lib = None
 
 
-def load(path=LIB_PATH):
-    """dlopen the library and declare every prototype of include/tac_b200.h."""
+def load(path=None):
+    """dlopen the library and declare every prototype of include/tac_b200.h.
+    TAC_B200_LIB names another build of the same library (kernel experiments, scripts/build_variant.sh)."""
     global _lib
     if _lib is not None:
         return _lib
+    if path is None:
+        path = os.environ.get("TAC_B200_LIB", LIB_PATH)
     if not os.path.exists(path):
         raise ImportError(
             "torchaudio_contrib_b200 needs its CUDA library %s (build it with "

@@ -33,8 +33,12 @@
 
 namespace tac {
 
-constexpr int kPairWarps = 12;
+#ifndef PAIR_WARPS
+#define PAIR_WARPS 8
+#endif
+constexpr int kPairWarps = PAIR_WARPS;                           // experiments: scripts/build_variant.sh -DPAIR_WARPS=8
 constexpr int kPairThreads = kPairWarps * 32;
+static_assert(kPairWarps % 4 == 0, "whole lane quadrants of tensor memory");
 constexpr int kPairMaxHop = 512;
 constexpr int kRegionFloats = 2048 + kPairMaxHop;               // samples of frames A and B
 constexpr int kXStride = 33;                                    // transposition row stride, float4 elements
@@ -42,7 +46,12 @@ constexpr int kXBufBytes = 32 * kXStride * 16;                  // 16 896 B
 constexpr int kStashOffBytes = kRegionFloats * 4;               // 10 240: behind the sample region
 constexpr int kWarpBytes = kStashOffBytes + kStashFloats * 8;   // 18 752
 static_assert(kWarpBytes >= kXBufBytes && kWarpBytes % 16 == 0, "transposition buffer inside the warp's block");
-constexpr size_t kPairSmemBytes = 32 * sizeof(float2)           // W_2048^lane
+#ifdef PAIR_TABLES_SMEM
+constexpr size_t kPairTabBytes = 12 * 4 * 32 * sizeof(float4);
+#else
+constexpr size_t kPairTabBytes = 0;
+#endif
+constexpr size_t kPairSmemBytes = kPairTabBytes + 32 * sizeof(float2)           // W_2048^lane
                                   + 16 * sizeof(uint64_t)       // mbarriers (12 used) + tmem base slot
                                   + (size_t)kPairWarps * kWarpBytes;
 static_assert(kPairSmemBytes <= 227 * 1024, "pair kernel exceeds the shared memory of one CTA");
@@ -80,6 +89,19 @@ __device__ __forceinline__ pk pair_shfl(pk x, int src) {
 
 // 16 columns of this thread's tensor-memory lane
 __device__ __forceinline__ void tmem_table16(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+#ifdef PAIR_TABLES_SMEM
+// experiment (scripts/build_variant.sh -DPAIR_TABLES_SMEM): the same tables in shared memory, [chunk][quarter][lane] float4
+__device__ __forceinline__ void smem_table16(const float4* tab, int chunk, int lane, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = tab[(chunk * 4 + q) * 32 + lane];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+#define PAIR_TABLE16(kindcol, c, v) smem_table16(s_tab, ((kindcol) / 64) * 4 + (c), lane, v)
+#else
+#define PAIR_TABLE16(kindcol, c, v) tmem_table16(t_lane + (kindcol) + 16 * (c), v)
+#endif
 
 // Everything about a pair's sample region that is not the plain interior bulk copy, out of line (inlined, the
 // unrolled gather and padding loops made the kernel 10 k instructions and ptxas cloned half the frame loop).
@@ -141,7 +163,7 @@ __device__ __noinline__ void pair_fixup_region(float* region, const float* __res
 // Band contraction of both frames' power spectra (stash of float2 pairs) with the two-band plan, dB epilogue, stores.
 // Same walk as band_contract (stft.cu); weights (from tensor memory), masks and list offsets are shared by the frames.
 template <bool PEERS>
-__device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* stash, uint32_t t_band, int lane, int64_t off_a,
+__device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* stash, uint32_t t_lane, const float4* s_tab, int lane, int64_t off_a,
                                                    int64_t off_b, bool store_b) {
   __syncwarp();
   uint4 ci[4];
@@ -175,7 +197,7 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float w[16];                                   // (w0, w1) of bins 8 q .. 8 q + 7 of this lane
-    tmem_table16(t_band + 16 * q, w);
+    PAIR_TABLE16(kColBand, q, w);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int bin = 8 * q + i;
@@ -243,10 +265,13 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
   __syncwarp();
 }
 
-template <bool PEERS, int PMODE>
+// SHIFT: hop / 64 when hop is a multiple of 64 (frame B's register r is then frame A's register r + SHIFT: the two
+// frames share their sample loads), 0 for any other even hop (separate loads).
+template <bool PEERS, int PMODE, int SHIFT>
 __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* s_twb = reinterpret_cast<float2*>(smem_raw);        // W_2048^lane
+  const float4* s_tab = reinterpret_cast<const float4*>(smem_raw);   // PAIR_TABLES_SMEM only (0 bytes otherwise)
+  float2* s_twb = reinterpret_cast<float2*>(smem_raw + kPairTabBytes);        // W_2048^lane
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_twb + 32);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 15);
   uint32_t* s_next = s_tmem + 1;                              // next pair of this CTA's chunk nobody has taken yet
@@ -316,13 +341,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
   const uint32_t tmem_base = *s_tmem;
   const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   {
-    // 12 chunks of 16 columns (4 window, 4 twiddle, 4 band weights) per lane quadrant; the three warps of a quadrant
-    // (warp, warp + 4, warp + 8) take four each
+    // 12 chunks of 16 columns (4 window, 4 twiddle, 4 band weights) per lane quadrant, dealt to the warps of the
+    // quadrant (warp, warp + 4, ...)
     const float g = 0.5f * p.scale;
     const float4* wtab = reinterpret_cast<const float4*>(p.band_plan + kBandOffW) + lane;
     const int third = warp >> 2;
 #pragma unroll 1
-    for (int chunk = third; chunk < 12; chunk += 3) {
+    for (int chunk = third; chunk < 12; chunk += kPairWarps / 4) {
       const int kind = chunk >> 2, c = chunk & 3;
       float w[16];
       if (kind == 0) {
@@ -347,6 +372,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
           w[4 * i] = b.x; w[4 * i + 1] = b.y; w[4 * i + 2] = b.z; w[4 * i + 3] = b.w;
         }
       }
+#ifdef PAIR_TABLES_SMEM
+      if ((warp & 3) == 0) {                                  // one quadrant's warps fill the (quadrant-independent) table
+        float4* tab = const_cast<float4*>(s_tab);
+        for (int q = 0; q < 4; ++q) tab[(chunk * 4 + q) * 32 + lane] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      }
+#endif
       tmem_st16(t_lane + (kind == 0 ? kColWin : (kind == 1 ? kColTw1 : kColBand)) + 16 * c, w);
     }
     tc_wait_st();
@@ -374,17 +405,36 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
     cx<pk> v[32];
     {
       const float2* sa2 = reinterpret_cast<const float2*>(region);
-      const float2* sb2 = reinterpret_cast<const float2*>(region + hop);
+      if constexpr (SHIFT > 0) {
+        // z_B[n] = z_A[n + 32 SHIFT]: element r of frame B is element r + SHIFT of frame A, same lane -- 32 + SHIFT
+        // loads serve both frames (40 instead of 64 LDS.64 per pair at hop 512)
+        float2 e[32 + SHIFT];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float w[16];
-        tmem_table16(t_lane + kColWin + 16 * c, w);
+        for (int r = 0; r < 32 + SHIFT; ++r) e[r] = sa2[lane + 32 * r];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 8 * c + i;
-          const float2 a = sa2[lane + 32 * r], b = sb2[lane + 32 * r];
-          v[r].x = mk2(a.x * w[2 * i], b.x * w[2 * i]);
-          v[r].y = mk2(a.y * w[2 * i + 1], b.y * w[2 * i + 1]);
+        for (int c = 0; c < 4; ++c) {
+          float w[16];
+          PAIR_TABLE16(kColWin, c, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 8 * c + i;
+            v[r].x = mk2(e[r].x * w[2 * i], e[r + SHIFT].x * w[2 * i]);
+            v[r].y = mk2(e[r].y * w[2 * i + 1], e[r + SHIFT].y * w[2 * i + 1]);
+          }
+        }
+      } else {
+        const float2* sb2 = reinterpret_cast<const float2*>(region + hop);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float w[16];
+          PAIR_TABLE16(kColWin, c, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 8 * c + i;
+            const float2 a = sa2[lane + 32 * r], b = sb2[lane + 32 * r];
+            v[r].x = mk2(a.x * w[2 * i], b.x * w[2 * i]);
+            v[r].y = mk2(a.y * w[2 * i + 1], b.y * w[2 * i + 1]);
+          }
         }
       }
     }
@@ -399,7 +449,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float w[16];                                   // W_1024^(n1 k2), k2 = lane, n1 = 8 c .. 8 c + 7
-      tmem_table16(t_lane + kColTw1 + 16 * c, w);
+      PAIR_TABLE16(kColTw1, c, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int n1 = 8 * c + i;
@@ -417,7 +467,15 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
     const uint32_t seq_next = pj_next / pairs_per_seq, j_next = pj_next % pairs_per_seq;
     if (pj_next < chunk1) stage_bulk(seq_next, j_next);
 
+#ifdef PAIR_STOP_AFTER_TW1                           // cost-breakdown builds (scripts/build_variant.sh): stop here, keep the values live
+    { pk acc = v[0].x; for (int i = 0; i < 32; ++i) acc = acc + v[i].x + v[i].y; if (lo(acc) + hi(acc) == 12345.678f) p.out[lane] = lo(acc); }
+    pj = pj_next; seq = seq_next; j = j_next; continue;
+#endif
     dit_fft_fma_r<32, pk>(v);                        // pass 2 over n1: v[bit_reverse(k1)] = Z[32 k1 + lane] / 2
+#ifdef PAIR_STOP_AFTER_PASS2
+    { pk acc = v[0].x; for (int i = 0; i < 32; ++i) acc = acc + v[i].x + v[i].y; if (lo(acc) + hi(acc) == 12345.678f) p.out[lane] = lo(acc); }
+    pj = pj_next; seq = seq_next; j = j_next; continue;
+#endif
 
     // ---- untangling + |X|^p of bins 32 k1 + lane and their mirrors 1024 - k, as in stft.cu (emit2) ------------
     {
@@ -452,10 +510,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
         if (lane == 0) dst[16 * kStashStride] = make_float2(lo(pc), hi(pc));
       }
     }
+#ifdef PAIR_STOP_AFTER_UNTANGLE
+    __syncwarp();
+    { const float2 t = stash[lane * kStashStride + 3]; if (t.x + t.y == 12345.678f) p.out[lane] = t.x; }
+    __syncwarp();
+    pj = pj_next; seq = seq_next; j = j_next; continue;
+#endif
     {
       const int64_t seq0 = PEERS ? p.peer_seq0 : 0;
       const int64_t off_a = ((int64_t)seq + seq0) * p.out_seq_stride + (int64_t)t_a * p.out_t_stride;
-      band_contract_pair<PEERS>(p, stash, t_lane + kColBand, lane, off_a, off_a + p.out_t_stride, has_b);
+      band_contract_pair<PEERS>(p, stash, t_lane, s_tab, lane, off_a, off_a + p.out_t_stride, has_b);
     }
     pj = pj_next;
     seq = seq_next;
@@ -481,10 +545,14 @@ int launch_stft2048_pair(const StftParams& p, cudaStream_t stream) {
   const int grid = (int)(want < sm_count() ? want : sm_count());
   using Kernel = void (*)(const StftParams);
   Kernel k;
-  if (p.out_mode == OUT_MEL_FUSED_PEERS)
-    k = p.power_mode == 2 ? stft2048_pair_kernel<true, 2> : (p.power_mode == 1 ? stft2048_pair_kernel<true, 1> : stft2048_pair_kernel<true, 0>);
-  else
-    k = p.power_mode == 2 ? stft2048_pair_kernel<false, 2> : (p.power_mode == 1 ? stft2048_pair_kernel<false, 1> : stft2048_pair_kernel<false, 0>);
+  const bool peers = p.out_mode == OUT_MEL_FUSED_PEERS;
+  if (p.hop == 512) {                                          // the headline hop: shared sample loads
+    if (peers) k = p.power_mode == 2 ? stft2048_pair_kernel<true, 2, 8> : (p.power_mode == 1 ? stft2048_pair_kernel<true, 1, 8> : stft2048_pair_kernel<true, 0, 8>);
+    else k = p.power_mode == 2 ? stft2048_pair_kernel<false, 2, 8> : (p.power_mode == 1 ? stft2048_pair_kernel<false, 1, 8> : stft2048_pair_kernel<false, 0, 8>);
+  } else {
+    if (peers) k = p.power_mode == 2 ? stft2048_pair_kernel<true, 2, 0> : (p.power_mode == 1 ? stft2048_pair_kernel<true, 1, 0> : stft2048_pair_kernel<true, 0, 0>);
+    else k = p.power_mode == 2 ? stft2048_pair_kernel<false, 2, 0> : (p.power_mode == 1 ? stft2048_pair_kernel<false, 1, 0> : stft2048_pair_kernel<false, 0, 0>);
+  }
   TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
   LaunchProbe probe(KIND_STFT, stream);
   k<<<grid, kPairThreads, kPairSmemBytes, stream>>>(p);

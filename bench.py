@@ -29,7 +29,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("TAC_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout: one JSON line only
+# NCCL's log level is the caller's (the driver reads NCCL's INFO lines to count ranks); quiet only when nobody asked
+os.environ.setdefault("NCCL_DEBUG", os.environ.get("TAC_NCCL_DEBUG", "WARN"))
 
 WORKLOADS = {
     # name: (batch, channels, samples, sample_rate, to_db)
@@ -288,6 +289,229 @@ def run_reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+KERNEL_NAME = "stft2048_pair_kernel"      # csrc/stft_pair.cu; stft2048_kernel<OUT_MEL_FUSED> with TAC_MEL_SINGLE=1
+
+
+def source_fingerprint():
+    """Hash of the kernel sources the loaded library was built from (build_native._fingerprint): a measured DRAM
+    traffic figure under profiles/ is only quoted when it was taken from the same sources."""
+    try:
+        import build_native
+        return build_native._fingerprint()[:16]
+    except Exception:
+        return None
+
+
+def measured_traffic(fused):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the latest ncu launch list
+    (scripts/summarize_profiles.py), or (None, why) when the kernels have changed since it was taken."""
+    import glob
+    names = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_dram_bytes.json" % ("melfused" if fused else "stft2048"))))
+    if not names:
+        return None, "no ncu launch list under profiles/"
+    with open(names[-1]) as fh:
+        rec = json.load(fh)
+    fp = source_fingerprint()
+    if rec.get("source_fingerprint") and fp and rec["source_fingerprint"] != fp:
+        return None, "%s was measured on other kernel sources (%s, now %s)" % (os.path.basename(names[-1]), rec["source_fingerprint"], fp)
+    return rec.get("dram_bytes_per_launch"), os.path.basename(names[-1])
+
+
+class MelWorkload(object):
+    """One named BASELINE workload on this rank: modules, prepared call, rotating device-resident inputs."""
+
+    def __init__(self, tac, name, world, rank, dev, n_sets=None):
+        self.name = name
+        self.batch, self.channels, self.samples, self.sr, self.to_db, self.scaling = workload_of(name, world)
+        self.frames = frames_of(self.samples)
+        self.frames_per_step = self.batch * self.channels * self.frames
+        self.in_bytes = 4 * self.batch * self.channels * self.samples
+        self.out_bytes = 4 * self.batch * self.channels * N_MELS * self.frames
+        self.mods = list(tac.Melspectrogram(num_mels=N_MELS, sample_rate=self.sr, fft_length=N_FFT, hop_length=HOP))
+        if self.to_db:
+            self.mods.append(tac.AmplitudeToDb())
+        self.model = tac.Sequential(*self.mods).to(dev)
+        # inputs larger than L2: rotate over enough distinct batches that each step reads its input from HBM
+        if n_sets is None:
+            n_sets = max(2, -(-2 * L2_BYTES // self.in_bytes)) if self.in_bytes < 2 * L2_BYTES else 2
+        self.n_sets = n_sets
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.inputs = [torch.randn(self.batch, self.channels, self.samples, device=dev, generator=gen) for _ in range(n_sets)]
+        self.prepared = tac.PreparedMelspectrogram((self.batch, self.channels, self.samples), dev, self.mods[2].filterbank,
+                                                   N_FFT, HOP, window=self.mods[0].window, power=2.0, to_db=self.to_db)
+        self.outs = [self.prepared.empty_output() for _ in range(2)]
+
+    def describe(self):
+        return "%s: Melspectrogram(num_mels=128, sample_rate=%d, fft_length=2048, hop_length=512)%s on (%d,%d,%d) fp32 per GPU" % (
+            self.name, self.sr, "+AmplitudeToDb" if self.to_db else "", self.batch, self.channels, self.samples)
+
+    def step(self, i):
+        self.prepared(self.inputs[i % self.n_sets], self.outs[i % 2])
+
+    def timed(self, steps, warmup, barrier):
+        """ms for `steps` steps (CUDA events on the launching stream, barrier + synchronize on both sides)."""
+        with torch.no_grad():
+            for i in range(max(warmup, 3)):
+                self.step(i)
+            barrier()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for i in range(steps):
+                self.step(i)
+            stop.record()
+            barrier()
+        return start.elapsed_time(stop)
+
+
+def time_gathers(w, world, dev, steps, barrier):
+    """(ms with one NCCL all_gather_into_tensor of the output per step on a side stream, ms with the kernel-side gather,
+    error string or None): BASELINE config 4's optional all-gather, both ways."""
+    import torch.distributed as dist
+    from torchaudio_contrib_b200.distributed import PeerGatheredOutput
+    full = torch.empty((world * w.batch, w.channels, N_MELS, w.frames), dtype=torch.float32, device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty((w.batch, w.channels, N_MELS, w.frames), dtype=torch.float32, device=dev) for _ in range(2)]
+    with torch.no_grad():
+        def step(i):
+            y = w.model(w.inputs[i % w.n_sets])
+            buf = bufs[i % 2]
+            buf.copy_(y)
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                dist.all_gather_into_tensor(full, buf)
+        for i in range(3):
+            step(i)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(steps):
+            step(i)
+        torch.cuda.current_stream(dev).wait_stream(comm)
+        g1.record()
+        barrier()
+    gather_ms = g0.elapsed_time(g1)
+    del full, bufs
+
+    # the same gather done by the mel kernel itself: every frame's bands stored into all ranks' full outputs over
+    # NVLink from the epilogue (tac_melspec_banded_peers_f32), one flag barrier per step instead of the collective
+    peer_ms, peer_err = 0.0, None
+    if w.prepared.fused:
+        try:
+            fulls = [PeerGatheredOutput((world * w.batch,) + w.prepared.out_shape[1:], dev) for _ in range(2)]
+            with torch.no_grad():
+                def peer_step(i):
+                    w.prepared.gather_into(w.inputs[i % w.n_sets], fulls[i % 2])
+                    fulls[i % 2].barrier(timeout_s=2.0)
+                for i in range(4):
+                    peer_step(i)
+                barrier()
+                for f in fulls:
+                    f.check()                                   # a barrier that timed out (dead peer) ends the leg here
+                g0.record()
+                for i in range(steps):
+                    peer_step(i)
+                g1.record()
+                barrier()
+            peer_ms = g0.elapsed_time(g1)
+            for f in fulls:
+                f.check()
+            # the gathered tensor equals an NCCL all-gather of what the plain call returns on every rank
+            last = (steps - 1) % w.n_sets
+            local = w.prepared.empty_output()
+            w.prepared(w.inputs[last], local)
+            want = torch.empty_like(fulls[0].tensor)
+            dist.all_gather_into_tensor(want, local)
+            if not torch.equal(want, fulls[(steps - 1) % 2].tensor):
+                peer_err = "gathered tensor differs from the all-gather of the single-GPU calls"
+            del want, local
+            for f in fulls:
+                f.close()
+        except Exception as exc:                                # report, do not lose the whole bench line
+            peer_err = "%s: %s" % (type(exc).__name__, exc)
+    return gather_ms, peer_ms, peer_err
+
+
+def bare_copy_bound(dev, host_in, host_out, steps, barrier):
+    """The ceiling of the end-to-end number: the same pinned buffers copied in and out with nothing in between
+    (H2D of the input and D2H of an output-sized buffer on two streams, back to back), wall clock, best of three."""
+    d_in = torch.empty(host_in.shape, dtype=torch.float32, device=dev)
+    d_out = torch.empty(host_out.shape, dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                host_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 1e3 * best / steps
+
+
+def max_over_ranks(values, world, dev):
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def sub_record(tac, lib, name, world, rank, dev, steps, barrier, hbm_peak, gathers):
+    """Short device-resident record of another BASELINE workload for the default line."""
+    w = MelWorkload(tac, name, world, rank, dev, n_sets=2 if name != "cfg2" else None)
+    ms = w.timed(steps, 3, barrier)
+    vals = [ms, 0.0, 0.0]
+    peer_err = None
+    if gathers and world > 1:
+        g_ms, p_ms, peer_err = time_gathers(w, world, dev, steps, barrier)
+        vals = [ms, g_ms, p_ms]
+    ms, g_ms, p_ms = max_over_ranks(vals, world, dev)
+    per_step = ms / steps
+    rec = {"workload": w.describe(), "scaling": w.scaling, "steps": steps, "ms_per_step": per_step,
+           "value": world * w.frames_per_step / (per_step * 1e-3), "unit": "frames/s",
+           "hbm_roofline_frac": (algorithmic_bytes(w.batch, w.channels, w.samples) / (per_step * 1e-3) / 1e9) / hbm_peak,
+           "call": "tac_melspec_banded_f32" if w.prepared.fused else "tac_melspec_f32"}
+    if gathers and world > 1:
+        rec["with_allgather"] = {"ms_per_step": g_ms / steps, "value": world * w.frames_per_step / (g_ms / steps * 1e-3)}
+        rec["with_peer_gather"] = ({"error": peer_err} if peer_err is not None else
+                                   {"ms_per_step": p_ms / steps, "value": world * w.frames_per_step / (p_ms / steps * 1e-3)})
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
+def mulaw_record(tac, lib, rank, dev, steps, hbm_peak):
+    """BASELINE config 5 on this rank: encode and decode of (4096,1,240000), 12 B per sample each way."""
+    shape = (4096, 1, 240000)
+    n = shape[0] * shape[2]
+    x = torch.rand(shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1234 + rank)) * 2 - 1
+    out, codes = {}, None
+    for name, fn in (("encode", tac.mu_law_encoding), ("decode", tac.mu_law_decoding)):
+        arg = x if name == "encode" else codes
+        for _ in range(3):
+            res = fn(arg, 256)
+        torch.cuda.synchronize(dev)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            res = fn(arg, 256)
+        stop.record()
+        torch.cuda.synchronize(dev)
+        ms = start.elapsed_time(stop) / steps
+        gbs = 12.0 * n / (ms * 1e-3) / 1e9
+        out[name] = {"ms_per_step": ms, "samples_per_s": n / (ms * 1e-3), "gbs": gbs, "hbm_roofline_frac": gbs / hbm_peak}
+        if name == "encode":
+            codes = res
+    del x, codes, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local):
     import torchaudio_contrib_b200 as tac
     from torchaudio_contrib_b200 import _cabi
@@ -299,37 +523,25 @@ def run_ours(args, rank, world, local):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-
-    batch, channels, samples, sr, to_db, scaling = workload_of(args.workload, world)
-    frames = frames_of(samples)
-    frames_per_step = batch * channels * frames
-    in_bytes = 4 * batch * channels * samples
-    out_bytes = 4 * batch * channels * N_MELS * frames
     lib = _cabi.lib()
-
-    mods = list(tac.Melspectrogram(num_mels=N_MELS, sample_rate=sr, fft_length=N_FFT, hop_length=HOP))
-    if to_db:
-        mods.append(tac.AmplitudeToDb())
-    model = tac.Sequential(*mods).to(dev)
-
-    # inputs larger than L2: rotate over enough distinct batches that each step reads its input from HBM
-    n_sets = max(2, -(-2 * L2_BYTES // in_bytes)) if in_bytes < 2 * L2_BYTES else 2
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    inputs = [torch.randn(batch, channels, samples, device=dev, generator=gen) for _ in range(n_sets)]
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks["hbm_gbs"])
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    w = MelWorkload(tac, args.workload, world, rank, dev)
+    prepared, inputs, n_sets, model = w.prepared, w.inputs, w.n_sets, w.model
+    batch, channels, samples, sr, to_db, scaling = w.batch, w.channels, w.samples, w.sr, w.to_db, w.scaling
+    frames, frames_per_step, in_bytes, out_bytes = w.frames, w.frames_per_step, w.in_bytes, w.out_bytes
+
     # the timed step: ONE C-ABI call per batch into a pre-allocated output (output allocation excluded);
     # the nn.Module call of the same chain is timed next to it (`module_ms_per_step`)
-    prepared = tac.PreparedMelspectrogram((batch, channels, samples), dev, mods[2].filterbank, N_FFT, HOP,
-                                          window=mods[0].window, power=2.0, to_db=to_db)
-    outs = [prepared.empty_output() for _ in range(2)]
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
-            prepared(inputs[i % n_sets], outs[i % 2])
+            w.step(i)
         barrier()
         launches0 = int(lib.tac_launch_count())
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,7 +549,7 @@ def run_ours(args, rank, world, local):
             barrier()
             start.record()
             for i in range(args.steps):
-                prepared(inputs[i % n_sets], outs[i % 2])
+                w.step(i)
             stop.record()
             barrier()
         ms = start.elapsed_time(stop)
@@ -352,13 +564,13 @@ def run_ours(args, rank, world, local):
         stop.record()
         barrier()
         module_ms = start.elapsed_time(stop) / args.steps
-        same = bool(torch.equal(out, prepared(inputs[(args.steps - 1) % n_sets], outs[0])))
+        same = bool(torch.equal(out, prepared(inputs[(args.steps - 1) % n_sets], w.outs[0])))
 
         # same call, contiguous (n_seq, bands, frames) output instead of the reference's frame-major memory order
         contiguous_ms = None
         if prepared.fused:
-            alt = tac.PreparedMelspectrogram((batch, channels, samples), dev, mods[2].filterbank, N_FFT, HOP,
-                                             window=mods[0].window, power=2.0, to_db=to_db, layout="contiguous")
+            alt = tac.PreparedMelspectrogram((batch, channels, samples), dev, w.mods[2].filterbank, N_FFT, HOP,
+                                             window=w.mods[0].window, power=2.0, to_db=to_db, layout="contiguous")
             alt_out = alt.empty_output()
             for i in range(3):
                 alt(inputs[i % n_sets], alt_out)
@@ -369,11 +581,12 @@ def run_ours(args, rank, world, local):
             stop.record()
             barrier()
             contiguous_ms = start.elapsed_time(stop) / args.steps
+            del alt, alt_out
 
         # per-kernel durations: same loop again with every launch bracketed by events on its stream
         lib.tac_profile_enable(1)
         for i in range(args.steps):
-            prepared(inputs[i % n_sets], outs[i % 2])
+            w.step(i)
         torch.cuda.synchronize(dev)
         kind_ms = (ctypes.c_double * 4)()
         kind_n = (ctypes.c_int64 * 4)()
@@ -381,96 +594,35 @@ def run_ours(args, rank, world, local):
         lib.tac_profile_enable(0)
 
         # e2e: host buffers through the C-ABI host entry (H2D + kernels + D2H inside the timed region)
-        fb = mods[2].filterbank
+        fb = w.mods[2].filterbank
         hp = tac.HostPipeline(N_FFT, HOP, power=2.0, filterbank=fb, to_db=to_db, device=dev)
         host_in = [torch.randn(batch, channels, samples).pin_memory() for _ in range(2)]
         host_out = torch.empty(batch, channels, N_MELS, frames).pin_memory()
         e2e_steps = max(3, min(args.steps, 20))
         for i in range(3):
             hp(host_in[i % 2], out=host_out)
-        e2e_s = None
-        for _ in range(3):                                  # wall-clock timing: keep the best of three passes
+        passes = []
+        for _ in range(5):                                  # wall-clock timing: best and median of five passes
             barrier()
             t0 = time.perf_counter()
             for i in range(e2e_steps):
                 hp(host_in[i % 2], out=host_out)
             torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
-            e2e_s = dt if e2e_s is None else min(e2e_s, dt)
+            passes.append(time.perf_counter() - t0)
         barrier()
+        e2e_s, e2e_median_s = min(passes), sorted(passes)[len(passes) // 2]
+        bound_ms = bare_copy_bound(dev, host_in[0], host_out, e2e_steps, barrier)
+        hp.close()
+        del host_in, host_out
 
-    # optional output all-gather (BASELINE config 4): every rank ends up with the (world*batch, C, M, frames)
-    # tensor.  One NCCL all_gather_into_tensor per step, issued on a side stream so it overlaps the next step.
-    gather_ms = 0.0
+    # optional output all-gather (BASELINE config 4), NCCL and kernel-side
+    gather_ms = peer_ms = 0.0
+    peer_err = None
     if world > 1:
-        import torch.distributed as dist
-        full = torch.empty((world * batch, channels, N_MELS, frames), dtype=torch.float32, device=dev)
-        comm = torch.cuda.Stream(device=dev)
-        outs = [torch.empty((batch, channels, N_MELS, frames), dtype=torch.float32, device=dev) for _ in range(2)]
-        with torch.no_grad():
-            def step(i):
-                y = model(inputs[i % n_sets])
-                buf = outs[i % 2]
-                buf.copy_(y)
-                done = torch.cuda.Event()
-                done.record()
-                with torch.cuda.stream(comm):
-                    comm.wait_event(done)
-                    dist.all_gather_into_tensor(full, buf)
-            for i in range(3):
-                step(i)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for i in range(args.steps):
-                step(i)
-            torch.cuda.current_stream(dev).wait_stream(comm)
-            g1.record()
-            barrier()
-        gather_ms = g0.elapsed_time(g1)
+        gather_ms, peer_ms, peer_err = time_gathers(w, world, dev, args.steps, barrier)
 
-    # the same gather done by the mel kernel itself: every frame's bands stored into all ranks' full outputs over
-    # NVLink from the epilogue (tac_melspec_banded_peers_f32), one flag barrier per step instead of the collective
-    peer_ms, peer_err = 0.0, None
-    if world > 1 and prepared.fused:
-        from torchaudio_contrib_b200.distributed import PeerGatheredOutput
-        try:
-            fulls = [PeerGatheredOutput((world * batch,) + prepared.out_shape[1:], dev) for _ in range(2)]
-            with torch.no_grad():
-                def peer_step(i):
-                    prepared.gather_into(inputs[i % n_sets], fulls[i % 2])
-                    fulls[i % 2].barrier(timeout_s=2.0)
-                for i in range(4):
-                    peer_step(i)
-                barrier()
-                for f in fulls:
-                    f.check()                                   # a barrier that timed out (dead peer) ends the leg here
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record()
-                for i in range(args.steps):
-                    peer_step(i)
-                g1.record()
-                barrier()
-            peer_ms = g0.elapsed_time(g1)
-            for f in fulls:
-                f.check()
-            # the gathered tensor equals an NCCL all-gather of what the plain call returns on every rank
-            last = (args.steps - 1) % n_sets
-            local = prepared.empty_output()
-            prepared(inputs[last], local)
-            want = torch.empty_like(fulls[0].tensor)
-            torch.distributed.all_gather_into_tensor(want, local)
-            if not torch.equal(want, fulls[(args.steps - 1) % 2].tensor):
-                peer_err = "gathered tensor differs from the all-gather of the single-GPU calls"
-            for f in fulls:
-                f.close()
-        except Exception as exc:                                # report, do not lose the whole bench line
-            peer_err = "%s: %s" % (type(exc).__name__, exc)
-
-    t = torch.tensor([ms, e2e_s * 1e3, gather_ms, peer_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms, gather_ms, peer_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms, e2e_ms, e2e_median_ms, gather_ms, peer_ms, bound_ms = max_over_ranks(
+        [ms, e2e_s * 1e3, e2e_median_s * 1e3, gather_ms, peer_ms, bound_ms], world, dev)
 
     ref_gpu = None
     if rank == 0 and world == 1:
@@ -478,49 +630,65 @@ def run_ours(args, rank, world, local):
             ref_gpu = time_reference_on_gpu(inputs, sr, to_db, frames_per_step)
         except Exception as exc:                                # informational only
             ref_gpu = {"error": "%s: %s" % (type(exc).__name__, exc)}
-        torch.cuda.empty_cache()
+    fused, frame_major = prepared.fused, prepared.frame_major
+    workload_text = w.describe()
+    del w, prepared, inputs, model
+    torch.cuda.empty_cache()
+
+    # the other BASELINE configurations, short: every rank takes part (barriers, collectives), rank 0 reports
+    extras = {}
+    if args.workload == "cfg2" and not args.skip_extras:
+        try:
+            extras["cfg3"] = sub_record(tac, lib, "cfg3", world, rank, dev, 10, barrier, hbm_peak, gathers=False)
+            extras["cfg4"] = sub_record(tac, lib, "cfg4", world, rank, dev, 5, barrier, hbm_peak, gathers=True)
+            extras["mulaw"] = mulaw_record(tac, lib, rank, dev, 5, hbm_peak)
+        except Exception as exc:                                # a failed extra must not take the headline line with it
+            extras["error"] = "%s: %s" % (type(exc).__name__, exc)
 
     if rank == 0:
-        peaks, peak_kind = measured_peaks()
-        hbm_peak = float(peaks["hbm_gbs"])
         stft_ms = kind_ms[0] / max(kind_n[0], 1)               # average launch duration
         frames_per_stft_launch = args.steps * frames_per_step / max(kind_n[0], 1)
         alg_per_frame = algorithmic_bytes(batch, channels, samples) / frames_per_step
         achieved = alg_per_frame * frames_per_stft_launch / (stft_ms * 1e-3) / 1e9 if stft_ms > 0 else 0.0
         value = world * args.steps * frames_per_step / (ms * 1e-3)
         cpu = time_cpu_chain(batch, channels, samples, sr, to_db, budget_s=args.cpu_seconds)
+        traffic, traffic_src = measured_traffic(fused)
+        kernel = (KERNEL_NAME if lib.tac_mel_kernel_variant(-1) == 0 else "stft2048_kernel<OUT_MEL_FUSED>") if fused else "stft2048_kernel"
         line = {
             "metric": "mel-spectrogram frames/sec (fft=2048/hop=512)",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s: Melspectrogram(num_mels=128, sample_rate=%d, fft_length=2048, hop_length=512)%s on "
-                            "(%d,%d,%d) fp32 per GPU" % (args.workload, sr, "+AmplitudeToDb" if to_db else "", batch, channels, samples),
+                "workload": workload_text,
                 "parallelism": "batch split, %d rank(s), no data-path collective" % world,
                 "l2_policy": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (n_sets, n_sets * in_bytes / 1e6),
-                "precision": ("fp32 FFT + fp32 two-band filterbank in one kernel (stft2048_kernel<OUT_MEL_FUSED>)" if prepared.fused
+                "precision": ("fp32 FFT (two frames per warp, packed FFMA2) + fp32 two-band filterbank in one kernel (%s)" % kernel if fused
                               else "fp32 FFT on CUDA cores; filterbank 3xTF32 on tcgen05 (fp32 accumulate)"),
-                "call": "tac_melspec_banded_f32" if prepared.fused else "tac_melspec_f32",
+                "call": "tac_melspec_banded_f32" if fused else "tac_melspec_f32",
             },
             "module_ms_per_step": module_ms, "module_matches_call": same,
             "output_layout": ("reference: (batch, channel, bands, frames) view of frame-major memory, strides (..., 1, bands) "
-                              "as the reference's matmul(...).transpose(-2, -1) returns" if prepared.frame_major else "contiguous"),
+                              "as the reference's matmul(...).transpose(-2, -1) returns" if frame_major else "contiguous"),
             "contiguous_layout_ms_per_step": contiguous_ms,
             "hbm_roofline_frac_step": (algorithmic_bytes(batch, channels, samples) / (ms / args.steps * 1e-3) / 1e9) / hbm_peak,
-            "roofline": {"bound": "hbm", "kernel": "stft2048_kernel<OUT_MEL_FUSED>" if prepared.fused else "stft2048_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                          "avg_launch_ms": stft_ms, "launches_timed": int(kind_n[0]),
                          "algorithmic_bytes_per_frame": alg_per_frame},
-            "kernel_ms_per_step": {"stft2048_kernel": kind_ms[0] / args.steps, "melbank_kernel": kind_ms[1] / args.steps},
+            "kernel_ms_per_step": {"stft": kind_ms[0] / args.steps, "melbank_kernel": kind_ms[1] / args.steps},
             "cpu_baseline": cpu,
             "e2e": {"value": world * e2e_steps * frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / e2e_steps,
+                    "median_ms_per_step": e2e_median_ms / e2e_steps, "passes": 5,
+                    "bound_ms": bound_ms, "bound": "bare pinned H2D of the input + D2H of an output-sized buffer on two "
+                                                   "streams, all ranks at once, max over ranks",
                     "api": "tac_pipeline_run_host (HostPipeline), pinned host buffers"},
             "reference_on_gpu": ref_gpu,
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
+        line.update(extras)
         if world > 1:
             line["with_allgather"] = {
                 "value": world * args.steps * frames_per_step / (gather_ms * 1e-3), "unit": "frames/s",
@@ -536,11 +704,7 @@ def run_ours(args, rank, world, local):
                     "bytes_sent_per_rank_per_step": (world - 1) * out_bytes}
             elif peer_err is not None:
                 line["with_peer_gather"] = {"error": peer_err}
-        traffic_file = os.path.join(ROOT, "profiles", "r01_melfused_dram_bytes.json" if prepared.fused else "r01_stft2048_dram_bytes.json")
-        if os.path.exists(traffic_file):
-            with open(traffic_file) as fh:
-                line["roofline"]["traffic"] = json.load(fh).get("dram_bytes_per_launch")
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -617,6 +781,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["mulaw"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the in-run CPU baseline")
+    ap.add_argument("--skip-extras", action="store_true", help="only the named workload (no cfg3 / cfg4 / mulaw sub-records)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.workload == "mulaw":

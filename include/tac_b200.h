@@ -249,6 +249,14 @@ int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64_t n_seq, i
                           float* out_host);
 int tac_pipeline_destroy(tac_pipeline* p);
 
+/* Adjoints of the pointwise operators the reference differentiates through torch:
+ *   op 0  db_to_amplitude  (functional.py:299-314): a = forward output y, g1 = dL/dy        -> out = dL/dx      (n)
+ *   op 1  magphase / angle (functional.py:187-201): a = z (n x 2), g1 = dL/d|z|^p0 or NULL,
+ *                                                   g2 = dL/dphase or NULL                   -> out = dL/dz      (n x 2)
+ *   op 2  mu_law_decoding of float codes (functional.py:349-354): a = codes, g1 = dL/dy, p0 = mu -> out = dL/dcodes (n) */
+int tac_pointwise_backward_f32(int op, const float* a, const float* g1, const float* g2, int64_t n, float p0,
+                               float* out, void* stream);
+
 /* ---- instrumentation (used by bench.py; off by default) -----------------------------------
  * tac_launch_count: kernels launched by this library in this process so far.
  * tac_profile_enable(1): bracket every kernel launch with CUDA events on its own stream;

@@ -191,6 +191,67 @@ def grads(ref, oc):
     print("gradient fixtures reproduce under oracle.ref_chain autograd")
 
 
+def grads_more(ref, oc):
+    """Round-2 gradient fixtures: the pointwise operators of SURVEY 8f N4 (db_to_amplitude, angle, magphase, float
+    mu_law_decoding) and the gradient w.r.t. a learnable filterbank (apply_filterbank, Melspectrogram chain), from the
+    UNMODIFIED reference under torch autograd.  Own seed, own file: `python oracle/gen_golden.py grads_more` writes
+    tests/golden/grads_more.npz only."""
+    g = torch.Generator().manual_seed(20261017)
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g)
+
+    blob = {}
+
+    def record(tag, inputs, run_ref, run_oc):
+        """inputs: dict name -> tensor (all differentiated); outputs may be a tensor or a tuple of tensors."""
+        def run(fn):
+            leaves = {k: v.clone().requires_grad_(True) for k, v in inputs.items()}
+            out = fn(**leaves)
+            return leaves, (out if isinstance(out, tuple) else (out,))
+        with _shimmed(ref):
+            lr, yr = run(run_ref)
+        gys = [randn(*y.shape) for y in yr]
+        gr = torch.autograd.grad(yr, list(lr.values()), gys)
+        lo, yo = run(run_oc)
+        go = torch.autograd.grad(yo, list(lo.values()), gys)
+        for a, b in zip(yr, yo):
+            _same(a.detach(), b.detach(), "grads_more/%s forward" % tag)
+        for a, b in zip(gr, go):
+            _same(a, b, "grads_more/%s backward" % tag)
+        for k, v in inputs.items():
+            blob["%s_in_%s" % (tag, k)] = v.numpy()
+        for i, gy in enumerate(gys):
+            blob["%s_gy%d" % (tag, i)] = gy.numpy()
+        for k, gk in zip(inputs, gr):
+            blob["%s_g_%s" % (tag, k)] = gk.numpy()
+
+    db = randn(3, 40, 50) * 20.0
+    record("fromdb", dict(x=db), lambda x: ref.db_to_amplitude(x, ref=2.0), lambda x: oc.db_to_amplitude(x, 2.0))
+    z = randn(2, 33, 40, 2)
+    record("angle", dict(z=z), lambda z: ref.angle(z), lambda z: oc.angle(z))
+    record("magphase_p1", dict(z=z), lambda z: ref.magphase(z, 1.0), lambda z: oc.magphase(z, 1.0))
+    record("magphase_p2", dict(z=z), lambda z: ref.magphase(z, 2.0), lambda z: oc.magphase(z, 2.0))
+    codes = torch.rand(4, 1000, generator=g) * 255.0
+    record("mudec", dict(c=codes), lambda c: ref.mu_law_decoding(c, 256), lambda c: oc.mu_law_decoding(c, 256))
+    spec = randn(3, 2, 65, 50).abs()
+    fb = randn(65, 20)
+    record("fbank_param", dict(s=spec, fb=fb), lambda s, fb: ref.apply_filterbank(s, fb), lambda s, fb: oc.apply_filterbank(s, fb))
+    x = randn(2, 1, 9000)
+    mel_fb = oc.mel_filterbank_for(64, 16000, fft_length=2048)
+    amp = ref.AmplitudeToDb()
+
+    def chain_ref(x, fb):
+        return amp(ref.apply_filterbank(ref.Spectrogram(fft_length=2048, hop_length=512, power=2.0)(x), fb))
+
+    def chain_oc(x, fb):
+        return oc.amplitude_to_db(oc.apply_filterbank(oc.spectrogram(x, 2048, 512, power=2.0), fb), 1.0, 1e-7)
+
+    record("melchain_param", dict(x=x, fb=mel_fb), chain_ref, chain_oc)
+    _save("grads_more.npz", **blob)
+    print("round-2 gradient fixtures reproduce under oracle.ref_chain autograd")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
@@ -201,6 +262,11 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         grads(ref, oc)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "grads_more":
+        grads_more(ref, oc)
+        return
+    if len(sys.argv) > 1:
+        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more]   (no argument: the forward fixtures)")
     g = torch.Generator().manual_seed(20260925)
 
     def randn(*shape):

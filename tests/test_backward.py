@@ -44,8 +44,32 @@ def test_oracle_autograd_reproduces_reference_gradients():
 def test_requires_grad_on_constants_is_refused_without_a_gpu_call():
     import torchaudio_contrib_b200.functional as F
     w = torch.hann_window(512).requires_grad_(True)
-    with pytest.raises(RuntimeError, match="w.r.t. the signal only"):
+    with pytest.raises(RuntimeError, match="the window is a constant"):
         F._no_param_grad(w, "stft: window")
+    x = torch.zeros(1, 1, 4096)                         # the check comes first: signal without grad, CPU tensor, no library call
+    for fn in (lambda: F.stft(x, 512, window=w), lambda: F.spectrogram(x, 512, window=w),
+               lambda: F.melspectrogram(x, torch.zeros(257, 8), 512, window=w)):
+        with pytest.raises(RuntimeError, match="the window is a constant"):
+            fn()
+
+
+def test_oracle_autograd_reproduces_round2_gradients():
+    """tests/golden/grads_more.npz (oracle/gen_golden.py grads_more): pointwise operators and the filterbank gradient."""
+    g = golden("grads_more.npz")
+
+    def grads(fn, names, tag, n_out=1):
+        leaves = [g["%s_in_%s" % (tag, k)].clone().requires_grad_(True) for k in names]
+        out = fn(*leaves)
+        out = out if isinstance(out, tuple) else (out,)
+        return torch.autograd.grad(out, leaves, [g["%s_gy%d" % (tag, i)] for i in range(n_out)])
+
+    cases = [("fromdb", ["x"], lambda x: oc.db_to_amplitude(x, 2.0), 1), ("angle", ["z"], oc.angle, 1),
+             ("magphase_p1", ["z"], lambda z: oc.magphase(z, 1.0), 2), ("magphase_p2", ["z"], lambda z: oc.magphase(z, 2.0), 2),
+             ("mudec", ["c"], lambda c: oc.mu_law_decoding(c, 256), 1),
+             ("fbank_param", ["s", "fb"], oc.apply_filterbank, 1)]
+    for tag, names, fn, n_out in cases:
+        for k, got in zip(names, grads(fn, names, tag, n_out)):
+            assert rel_err(got, g["%s_g_%s" % (tag, k)]) < 1e-5, (tag, k)
 
 
 # --------------------------------------------------------------------------------------------- GPU: kernels vs fixtures
@@ -273,3 +297,57 @@ def test_mel_2048_backward_dense_filterbank(tac):
     y, gx = _gpu_grad(lambda t: tac.functional.melspectrogram(t, fb.cuda(), 2048, 512), x, gy)
     assert rel_err(y, ref(x)) < REL
     assert rel_err(gx, want) < REL
+
+
+# --------------------------------------------------------------------------------------------- round 2: N4 pointwise + filterbank
+@pytest.mark.gpu
+def test_pointwise_gradients_round2(tac):
+    """db_to_amplitude, angle, magphase, float mu_law_decoding: gradients of the unmodified reference (grads_more.npz)."""
+    g = golden("grads_more.npz")
+
+    def check(tag, fn, n_out=1, tol=REL):
+        name = [k for k in g if k.startswith(tag + "_in_")][0].split("_in_")[1]
+        leaf = g["%s_in_%s" % (tag, name)].cuda().requires_grad_(True)
+        out = fn(leaf)
+        out = out if isinstance(out, tuple) else (out,)
+        (gx,) = torch.autograd.grad(out, [leaf], [g["%s_gy%d" % (tag, i)].cuda() for i in range(n_out)])
+        assert rel_err(gx.cpu(), g["%s_g_%s" % (tag, name)]) < tol, tag
+
+    check("fromdb", lambda x: tac.db_to_amplitude(x, ref=2.0))
+    check("angle", tac.angle)
+    check("magphase_p1", lambda z: tac.magphase(z, 1.0), 2)
+    check("magphase_p2", lambda z: tac.magphase(z, 2.0), 2)
+    check("mudec", lambda c: tac.mu_law_decoding(c, 256))
+    # only one of magphase's outputs used: the other gradient is absent, not zero-filled garbage
+    z = g["angle_in_z"].cuda().requires_grad_(True)
+    mag, _ = tac.magphase(z, 1.0)
+    (gz,) = torch.autograd.grad(mag.sum(), z)
+    zr = g["angle_in_z"].clone().requires_grad_(True)
+    (want,) = torch.autograd.grad(oc.magphase(zr, 1.0)[0].sum(), zr)
+    assert rel_err(gz.cpu(), want) < REL
+
+
+@pytest.mark.gpu
+def test_filterbank_parameter_gradient(tac):
+    """A learnable filterbank (requires_grad) gets the reference's gradient -- with or without a gradient for the signal,
+    through apply_filterbank and through the Melspectrogram chain (+ dB), one-kernel and two-kernel paths."""
+    g = golden("grads_more.npz")
+    s = g["fbank_param_in_s"].cuda().requires_grad_(True)
+    fb = g["fbank_param_in_fb"].cuda().requires_grad_(True)
+    gy = g["fbank_param_gy0"].cuda()
+    gs, gfb = torch.autograd.grad(tac.apply_filterbank(s, fb), [s, fb], gy)
+    assert rel_err(gs.cpu(), g["fbank_param_g_s"]) < REL and rel_err(gfb.cpu(), g["fbank_param_g_fb"]) < REL
+    (gfb_only,) = torch.autograd.grad(tac.apply_filterbank(s.detach(), fb), [fb], gy)       # signal without grad
+    assert rel_err(gfb_only.cpu(), g["fbank_param_g_fb"]) < REL
+
+    x = g["melchain_param_in_x"].cuda().requires_grad_(True)
+    fb = g["melchain_param_in_fb"].cuda().requires_grad_(True)
+    gy = g["melchain_param_gy0"].cuda()
+    y = tac.functional.melspectrogram(x, fb, 2048, 512, to_db=True)
+    gx, gfb = torch.autograd.grad(y, [x, fb], gy)
+    assert rel_err(gx.cpu(), g["melchain_param_g_x"]) < REL
+    assert rel_err(gfb.cpu(), g["melchain_param_g_fb"]) < REL
+    y = tac.functional.melspectrogram(x.detach(), fb, 2048, 512, to_db=True)                # parameter only
+    assert y.requires_grad
+    (gfb2,) = torch.autograd.grad(y, [fb], gy)
+    assert rel_err(gfb2.cpu(), g["melchain_param_g_fb"]) < REL

@@ -71,6 +71,7 @@ SIGNATURES = {
     "tac_profile_enable": (_int, [_int]),
     "tac_profile_read": (_int, [_c.POINTER(_c.c_double), _c.POINTER(_i64)]),
     "tac_mel_kernel_variant": (_int, [_int]),
+    "tac_pointwise_backward_f32": (_int, [_int, _ptr, _ptr, _ptr, _i64, _f32, _ptr, _ptr]),
 }
 
 

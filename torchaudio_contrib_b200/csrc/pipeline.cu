@@ -194,45 +194,38 @@ struct tac_pipeline {
   float* d_x[kHostSlots];
   float* d_out[kHostSlots];
   float* d_ws[kHostSlots];
-  int64_t cap_x, cap_out, cap_ws;       // bytes per slot
+  int64_t cap_x[kHostSlots], cap_out[kHostSlots], cap_ws[kHostSlots];       // bytes each slot's buffers hold
 };
+
+// Grow one device buffer; on failure the slot is left empty with capacity 0, so the next call allocates it again
+// (capacities used to be per pipeline: a failed cudaMalloc left a null slot that the next call at the old size used).
+static int grow_buffer(float** buf, int64_t* cap, int64_t bytes) {
+  using namespace tac;
+  if (bytes <= *cap) return TAC_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  TAC_CUDA_OK(cudaMalloc(buf, (size_t)bytes));
+  *cap = bytes;
+  return TAC_OK;
+}
 
 static int pipeline_reserve(tac_pipeline* p, int64_t x_bytes, int64_t out_bytes, int64_t ws_bytes) {
   using namespace tac;
   for (int i = 0; i < kHostSlots; ++i) {
-    if (x_bytes > p->cap_x) {
-      if (p->d_x[i]) TAC_CUDA_OK(cudaFree(p->d_x[i]));
-      p->d_x[i] = nullptr;
-      TAC_CUDA_OK(cudaMalloc(&p->d_x[i], (size_t)x_bytes));
-    }
-    if (out_bytes > p->cap_out) {
-      if (p->d_out[i]) TAC_CUDA_OK(cudaFree(p->d_out[i]));
-      p->d_out[i] = nullptr;
-      TAC_CUDA_OK(cudaMalloc(&p->d_out[i], (size_t)out_bytes));
-    }
-    if (ws_bytes > p->cap_ws) {
-      if (p->d_ws[i]) TAC_CUDA_OK(cudaFree(p->d_ws[i]));
-      p->d_ws[i] = nullptr;
-      TAC_CUDA_OK(cudaMalloc(&p->d_ws[i], (size_t)ws_bytes));
-    }
+    int rc = grow_buffer(&p->d_x[i], &p->cap_x[i], x_bytes);
+    if (rc == TAC_OK) rc = grow_buffer(&p->d_out[i], &p->cap_out[i], out_bytes);
+    if (rc == TAC_OK) rc = grow_buffer(&p->d_ws[i], &p->cap_ws[i], ws_bytes);
+    if (rc != TAC_OK) return rc;
   }
-  if (x_bytes > p->cap_x) p->cap_x = x_bytes;
-  if (out_bytes > p->cap_out) p->cap_out = out_bytes;
-  if (ws_bytes > p->cap_ws) p->cap_ws = ws_bytes;
   return TAC_OK;
 }
 
-extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* window_host, const float* fb_host,
-                                   tac_pipeline** out) {
+extern "C" int tac_pipeline_destroy(tac_pipeline* p);
+
+// everything that can fail after the handle exists; the caller destroys the half-built handle on any error
+static int pipeline_build(tac_pipeline* p, const tac_pipeline_config* cfg, const float* window_host, const float* fb_host) {
   using namespace tac;
-  TAC_REQUIRE(cfg && window_host && out, TAC_ERR_INVALID, "pipeline_create: null pointer");
-  TAC_REQUIRE(is_pow2(cfg->n_fft) && cfg->n_fft >= 32 && cfg->n_fft <= 8192, TAC_ERR_UNSUPPORTED,
-              "pipeline_create: n_fft=%d is not a power of two in [32, 8192]", cfg->n_fft);
-  TAC_REQUIRE(cfg->n_bands == 0 || (fb_host && cfg->n_bins == cfg->n_fft / 2 + 1), TAC_ERR_INVALID,
-              "pipeline_create: filterbank must have n_fft/2+1 = %d rows (got %d)", cfg->n_fft / 2 + 1, cfg->n_bins);
-  tac_pipeline* p = static_cast<tac_pipeline*>(calloc(1, sizeof(tac_pipeline)));
-  TAC_REQUIRE(p, TAC_ERR_INVALID, "pipeline_create: out of host memory");
-  p->cfg = *cfg;
   TAC_CUDA_OK(cudaGetDevice(&p->device));
   TAC_CUDA_OK(cudaMalloc(&p->d_window, sizeof(float) * cfg->n_fft));
   TAC_CUDA_OK(cudaMemcpy(p->d_window, window_host, sizeof(float) * cfg->n_fft, cudaMemcpyHostToDevice));
@@ -258,6 +251,30 @@ extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* 
     TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
     TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming));
     TAC_CUDA_OK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+  }
+  return TAC_OK;
+}
+
+extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* window_host, const float* fb_host,
+                                   tac_pipeline** out) {
+  using namespace tac;
+  TAC_REQUIRE(cfg && window_host && out, TAC_ERR_INVALID, "pipeline_create: null pointer");
+  *out = nullptr;
+  TAC_REQUIRE(is_pow2(cfg->n_fft) && cfg->n_fft >= 32 && cfg->n_fft <= 8192, TAC_ERR_UNSUPPORTED,
+              "pipeline_create: n_fft=%d is not a power of two in [32, 8192]", cfg->n_fft);
+  TAC_REQUIRE(cfg->n_bands == 0 || (fb_host && cfg->n_bins == cfg->n_fft / 2 + 1), TAC_ERR_INVALID,
+              "pipeline_create: filterbank must have n_fft/2+1 = %d rows (got %d)", cfg->n_fft / 2 + 1, cfg->n_bins);
+  tac_pipeline* p = static_cast<tac_pipeline*>(calloc(1, sizeof(tac_pipeline)));
+  TAC_REQUIRE(p, TAC_ERR_INVALID, "pipeline_create: out of host memory");
+  p->cfg = *cfg;
+  const int rc = pipeline_build(p, cfg, window_host, fb_host);
+  if (rc != TAC_OK) {
+    char saved[512];                                         // destroy must not overwrite the reason
+    strncpy(saved, last_error_buffer(), sizeof(saved) - 1);
+    saved[sizeof(saved) - 1] = 0;
+    tac_pipeline_destroy(p);
+    strncpy(last_error_buffer(), saved, 511);
+    return rc;
   }
   *out = p;
   return TAC_OK;
@@ -316,7 +333,7 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
     if (c.n_bands > 0 && p->band_handle) {
       rc = run_melspec_banded(sp, c.power, p->d_plan, p->band_handle, c.n_bands, c.to_db, c.ref, c.amin, p->d_out[slot], 0, st);
     } else if (c.n_bands > 0) {
-      rc = run_melspec(sp, c.power, p->d_plan, c.n_bands, c.to_db, c.ref, c.amin, p->d_ws[slot], p->cap_ws, p->d_out[slot], st);
+      rc = run_melspec(sp, c.power, p->d_plan, c.n_bands, c.to_db, c.ref, c.amin, p->d_ws[slot], p->cap_ws[slot], p->d_out[slot], st);
     } else {
       sp.out = p->d_out[slot];
       sp.out_mode = OUT_POWER_PUBLIC;

@@ -138,6 +138,44 @@ magphase_kernel(const float2* __restrict__ z, int64_t n, float power, int mode, 
   }
 }
 
+// Adjoints of the remaining pointwise operators (the reference differentiates them through torch).
+//   op 0  db_to_amplitude (functional.py:299-314): y = sqrt(ref 10^(x/10)) -> dy/dx = y ln(10) / 20;   a = y, g1 = dL/dy
+//   op 1  magphase / angle (functional.py:187-201): a = z (n x 2), g1 = dL/d|z|^p or null, g2 = dL/dphase or null;
+//         d|z|^p/dz = p |z|^(p-2) z (0 at z = 0, torch.norm's subgradient), dphase/dz = (-im, re) / |z|^2;  out = dL/dz (n x 2)
+//   op 2  mu_law_decoding of float codes (functional.py:349-354): x = 2 c / mu - 1, y = sign(x) (exp(|x| L) - 1) / mu,
+//         L = log1p(mu) -> dy/dc = 2 L exp(|x| L) / mu^2;   a = c, g1 = dL/dy, p0 = mu
+__global__ void __launch_bounds__(kPwThreads)
+pointwise_backward_kernel(int op, const float* __restrict__ a, const float* __restrict__ g1, const float* __restrict__ g2,
+                          int64_t n, float p0, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kPwThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += stride) {
+    if (op == 0) {
+      out[i] = g1[i] * a[i] * 0.11512925464970229f;                     // ln(10) / 20
+    } else if (op == 1) {
+      const float2 z = reinterpret_cast<const float2*>(a)[i];
+      const float n2 = fmaf(z.x, z.x, z.y * z.y);
+      float gr = 0.0f, gi = 0.0f;
+      if (n2 > 0.0f) {
+        if (g1) {
+          const float k = g1[i] * (p0 == 1.0f ? rsqrtf(n2) : (p0 == 2.0f ? 2.0f : p0 * powf(n2, 0.5f * p0 - 1.0f)));
+          gr = k * z.x;
+          gi = k * z.y;
+        }
+        if (g2) {
+          const float k = g2[i] / n2;
+          gr = fmaf(-k, z.y, gr);
+          gi = fmaf(k, z.x, gi);
+        }
+      }
+      reinterpret_cast<float2*>(out)[i] = make_float2(gr, gi);
+    } else {
+      const float mu = p0, l1p = log1pf(mu);
+      const float x = (a[i] / mu) * 2.0f - 1.0f;
+      out[i] = g1[i] * (2.0f * l1p / (mu * mu)) * expf(fabsf(x) * l1p);
+    }
+  }
+}
+
 static int pw_grid(int64_t n_vec) {
   const int64_t want = (n_vec + kPwThreads - 1) / kPwThreads;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -188,6 +226,18 @@ extern "C" int tac_magphase_f32(const float* z, int64_t n, float power, float* m
   LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
   magphase_kernel<<<pw_grid((n + 1) / 2), kPwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(z), n, power,
                                                                               power_mode(power), mag, phase);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
+extern "C" int tac_pointwise_backward_f32(int op, const float* a, const float* g1, const float* g2, int64_t n, float p0,
+                                          float* out, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(n >= 0 && op >= 0 && op <= 2, TAC_ERR_INVALID, "pointwise_backward: op=%d n=%lld", op, (long long)n);
+  if (n == 0) return TAC_OK;
+  TAC_REQUIRE(a && out && (g1 || (op == 1 && g2)), TAC_ERR_INVALID, "pointwise_backward: null pointer");
+  LaunchProbe probe(KIND_POINTWISE, as_stream(stream));
+  pointwise_backward_kernel<<<pw_grid(n), kPwThreads, 0, as_stream(stream)>>>(op, a, g1, g2, n, p0, out);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
 }

@@ -137,6 +137,8 @@ class PeerGatheredOutput(object):
         dist.all_gather_object(failures, failure, group=group)   # also: every rank has mapped every buffer
         failures = [f for f in failures if f]
         if failures:
+            self._unmap()                                      # whatever this rank did map before a peer failed
+            self._own = None
             raise RuntimeError("PeerGatheredOutput: mapping peer memory failed (%s)" % "; ".join(failures))
         self.base_array = (ctypes.c_void_p * self.world)(*self._bases)
         self.payload_array = (ctypes.c_void_p * self.world)(*[b + 128 for b in self._bases])
@@ -150,8 +152,36 @@ class PeerGatheredOutput(object):
             _cabi.check(_cabi.lib().tac_peer_barrier(ctypes.cast(self.base_array, ctypes.c_void_p), self.world, self.rank,
                                                      self.epoch, float(timeout_s), _cabi.stream_ptr(self.device)))
 
+    def wait(self, timeout_s=20.0):
+        """`barrier()`, then block the host until it has run and raise if it gave up on a peer: the call to use when the
+        gathered tensor is about to be consumed on the host or handed on (a timed-out barrier otherwise leaves a
+        partially filled `tensor` with nothing but `check()` to say so)."""
+        self.barrier(timeout_s)
+        self.check()
+        return self.tensor
+
+    def _unmap(self):
+        """Unmap the peers' buffers this rank has opened (no collective)."""
+        bases, self._bases = self._bases, None
+        if not bases:
+            return
+        lib = _cabi.lib()
+        with torch.cuda.device(self.device):
+            for r, b in enumerate(bases):
+                if r != self.rank and b:
+                    lib.tac_peer_close(ctypes.c_void_p(b))
+
+    def __del__(self):
+        try:                                                   # a buffer dropped without close(): at least unmap the peers
+            if getattr(self, "_bases", None):
+                torch.cuda.synchronize(self.device)
+                self._unmap()
+        except Exception:                                      # interpreter shutdown
+            pass
+
     def check(self):
-        """Synchronise and raise if a barrier gave up waiting for a peer."""
+        """Synchronise and raise if a barrier gave up waiting for a peer (mandatory after `barrier()` before the result
+        is trusted; `wait()` does both)."""
         flag = ctypes.c_int(0)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().tac_peer_timed_out(ctypes.c_void_p(self._own.base.value), ctypes.byref(flag)))

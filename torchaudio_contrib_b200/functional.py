@@ -3,8 +3,13 @@ hand-written sm_100a kernels.
 
 Same names, argument meaning and shapes as the reference; every function documents the reference
 lines it stands in for.  Tensors must live on a CUDA device and be float32 (mu-law codes int64):
-each call enqueues kernels of libtac_b200.so on the current stream.  There is no CPU path.  The
-kernels are forward-only; an input that requires grad raises instead of silently detaching.
+each call enqueues kernels of libtac_b200.so on the current stream.  There is no CPU path.
+
+Autograd: the signal path (stft, complex_norm, apply_filterbank, amplitude_to_db, spectrogram, melspectrogram,
+db_to_amplitude, magphase / angle, float-input mu_law_decoding) is differentiated by hand-written adjoint kernels,
+and the `filterbank` argument gets its gradient too (a learnable filterbank).  What is not differentiated raises
+instead of silently detaching: a `window` that requires grad (whether or not the signal does), `phase_vocoder`
+and `mu_law_encoding` inputs that require grad.
 """
 import ctypes
 import math
@@ -30,8 +35,8 @@ def _wants_grad(t):
 
 def _no_param_grad(t, name):
     if isinstance(t, torch.Tensor) and torch.is_grad_enabled() and t.requires_grad:
-        raise RuntimeError("%s requires grad: the B200 backward kernels differentiate w.r.t. the signal only "
-                           "(window and filterbank are constants, as the reference's buffers are)" % name)
+        raise RuntimeError("%s requires grad: the B200 backward kernels differentiate w.r.t. the signal and the "
+                           "filterbank; the window is a constant (a buffer in the reference's layers)" % name)
 
 
 def _forward_only(t, name):
@@ -110,8 +115,8 @@ def stft(waveforms, fft_length, hop_length=None, win_length=None, window=None,
     of two in [32, 8192].  Unlike the reference, a missing `window` is created on the input's
     device.  The result is a contiguous tensor of the reference's logical shape.
     """
+    _no_param_grad(window, "stft: window")
     if _wants_grad(waveforms):
-        _no_param_grad(window, "stft: window")
         return _StftFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided))
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
@@ -129,8 +134,8 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
                 pad_mode='reflect', normalized=False, onesided=True, power=1.):
     """`Spectrogram(...)(x)` in one kernel: stft then `|.|^power` (layers.py:294-304), the complex
     spectrum never reaches HBM.  Returns `(*, channel, num_freqs, frames)`."""
+    _no_param_grad(window, "spectrogram: window")
     if _wants_grad(waveforms):
-        _no_param_grad(window, "spectrogram: window")
         return _SpectrogramFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized,
                                                 onesided, power))
     x = _as_f32_cuda(waveforms, "waveforms")
@@ -275,8 +280,7 @@ def apply_filterbank(mag_specgrams, filterbank, _cache=None):
     """`(*, num_freqs, time) x (num_freqs, num_bands) -> (*, num_bands, time)`: contraction over
     the frequency axis (functional.py:172-184) on the tcgen05 tensor cores with 3xTF32 split
     accumulation (csrc/melbank.cu).  Any dense matrix is accepted; zero blocks are skipped."""
-    if _wants_grad(mag_specgrams):
-        _no_param_grad(filterbank, "apply_filterbank: filterbank")
+    if _wants_grad(mag_specgrams) or _wants_grad(filterbank):
         return _ApplyFilterbankFn.apply(mag_specgrams, filterbank, _cache)
     spec = _as_f32_cuda(mag_specgrams, "mag_specgrams")
     plan = _plan_for(filterbank, spec.device, _cache)
@@ -300,7 +304,8 @@ def amplitude_to_db(x, ref=1.0, amin=1e-7):
 
 def db_to_amplitude(x, ref=1.0):
     """`sqrt(10 ** (x / 10 + log10(ref)))` (functional.py:299-314): the inverse of `amplitude_to_db`."""
-    _forward_only(x, "db_to_amplitude")
+    if _wants_grad(x):
+        return _DbToAmplitudeFn.apply(x, float(ref))
     a = _as_f32_cuda(x, "x")
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):
@@ -313,7 +318,9 @@ def db_to_amplitude(x, ref=1.0):
 # N4: angle / magphase
 # ------------------------------------------------------------------------------------------------
 def _magphase(complex_tensor, power, want_mag, name):
-    _forward_only(complex_tensor, name)
+    if _wants_grad(complex_tensor):
+        mag, phase = _MagphaseFn.apply(complex_tensor, float(power), want_mag, name)
+        return (mag if want_mag else None), phase
     z = _as_f32_cuda(complex_tensor, "complex_tensor")
     if z.dim() < 1 or z.size(-1) != 2:
         raise RuntimeError("%s: expected a (*, 2) tensor, got %s" % (name, tuple(z.shape)))
@@ -396,16 +403,10 @@ def phase_vocoder(complex_specgrams, rate, phase_advance):
 # ------------------------------------------------------------------------------------------------
 # a6: fused Melspectrogram pipeline
 # ------------------------------------------------------------------------------------------------
-_workspaces = {}
-
-
 def _workspace(device, nbytes):
-    """Per-device scratch for the frame-major power rows (sized to stay L2 resident)."""
-    buf = _workspaces.get(str(device))
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        _workspaces[str(device)] = buf
-    return buf
+    """Scratch for the power tiles of the two-kernel path, allocated per call: torch's caching allocator recycles it
+    stream-safely (a process-wide buffer was shared by concurrent streams / threads on one device)."""
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
 
 
 def _mel_frame_major(filterbank, fft_length, layout, device, cache):
@@ -432,9 +433,8 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     `matmul(...).transpose(-2, -1)` (functional.py:183-184; a frame's bands are one 512-byte store);
     `layout="contiguous"` returns a contiguous `(*, num_bands, frames)` tensor (4-byte stores, ~9 % slower
     at BASELINE config 2).  The two-kernel path always returns a contiguous tensor."""
-    if _wants_grad(waveforms):
-        _no_param_grad(window, "melspectrogram: window")
-        _no_param_grad(filterbank, "melspectrogram: filterbank")
+    _no_param_grad(window, "melspectrogram: window")
+    if _wants_grad(waveforms) or _wants_grad(filterbank):
         # The Function returns the buffer as it lies in memory; the reference-layout view is taken out here, where
         # autograd sees an ordinary transpose (a view created inside Function.forward costs an as_strided replay:
         # measured 0.46 ms per backward call at BASELINE config 2).
@@ -587,15 +587,36 @@ def _filterbank_backward(grad_y, filterbank):
     return out.reshape(lead + (int(fb.size(0)), frames))
 
 
+def _filterbank_param_grad(spec, grad_y, like):
+    """d loss / d filterbank[k, m] = sum over sequences and frames of spec[.., k, t] * grad_y[.., m, t]: a plain
+    (num_freqs x frames) . (frames x num_bands) GEMM per sequence, summed -- a library GEMM (torch.matmul), off the
+    hot path; the reference gets the same gradient from its matmul (functional.py:183)."""
+    g = _grad_f32(grad_y)
+    s3 = spec.reshape((-1,) + tuple(spec.shape[-2:]))
+    g3 = g.reshape((-1,) + tuple(g.shape[-2:]))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gfb = torch.matmul(s3, g3.transpose(-2, -1)).sum(0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return gfb.to(dtype=like.dtype, device=like.device)
+
+
 class _ApplyFilterbankFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mag_specgrams, filterbank, cache):
         ctx.filterbank = filterbank
-        return apply_filterbank(mag_specgrams.detach(), filterbank, cache)
+        spec = _as_f32_cuda(mag_specgrams.detach(), "mag_specgrams")
+        ctx.save_for_backward(spec if filterbank.requires_grad else spec.new_empty(0))
+        return apply_filterbank(spec, filterbank.detach(), cache)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return _filterbank_backward(grad_out, ctx.filterbank), None, None
+        (spec,) = ctx.saved_tensors
+        gspec = _filterbank_backward(grad_out, ctx.filterbank) if ctx.needs_input_grad[0] else None
+        gfb = _filterbank_param_grad(spec, grad_out, ctx.filterbank) if ctx.needs_input_grad[1] else None
+        return gspec, gfb, None
 
 
 def _amplitude_to_db_backward(x, grad_out, amin):
@@ -631,7 +652,7 @@ class _MelspectrogramFn(torch.autograd.Function):
         x = _as_f32_cuda(waveforms.detach(), "waveforms")
         ctx.save_for_backward(x)
         ctx.filterbank, ctx.kw, ctx.cache, ctx.shape, ctx.frame_major = filterbank, kw, cache, tuple(waveforms.shape), frame_major
-        return melspectrogram(x, filterbank, _cache=cache, _raw_buffer=True, **kw)     # the buffer, not the view
+        return melspectrogram(x, filterbank.detach(), _cache=cache, _raw_buffer=True, **kw)     # the buffer, not the view
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -640,8 +661,16 @@ class _MelspectrogramFn(torch.autograd.Function):
         g = grad_out.transpose(-2, -1) if ctx.frame_major else grad_out                # logical (*, bands, frames)
         if kw["to_db"]:
             plain = dict(kw, to_db=False, layout="contiguous")
-            mel = melspectrogram(x, ctx.filterbank, _cache=ctx.cache, **plain)           # (*, bands, frames) contiguous
+            mel = melspectrogram(x, ctx.filterbank.detach(), _cache=ctx.cache, **plain)  # (*, bands, frames) contiguous
             g = _amplitude_to_db_backward(mel, g, kw["amin"])
+        gfb = None
+        if ctx.needs_input_grad[1]:                          # learnable filterbank: |X|^p recomputed, one GEMM
+            spec = spectrogram(x, kw["fft_length"], kw["hop_length"], kw["win_length"], kw["window"], kw["center"],
+                               kw["pad_mode"], kw["normalized"], True, kw["power"])
+            gfb = _filterbank_param_grad(spec, g, ctx.filterbank)
+            del spec
+        if not ctx.needs_input_grad[0]:
+            return None, gfb, None, None, None
         # filterbank adjoint -> stft + |.|^p adjoint -> overlap-add in one C-ABI call (tac_melspec_backward_f32)
         g = _grad_f32(g)
         n_bands, frames = int(g.size(-2)), int(g.size(-1))
@@ -660,7 +689,72 @@ class _MelspectrogramFn(torch.autograd.Function):
                 *_stft_args(flat, win, fft_length, hop, kw["center"], kw["pad_mode"], kw["normalized"]), float(kw["power"]),
                 _cabi.ptr(fb), n_bands, _cabi.ptr(g3), g3.stride(0) if g3.size(0) > 1 else n_bands * frames, g3.stride(1),
                 g3.stride(2), _cabi.ptr(gx), _cabi.ptr(ws), ws_bytes, _cabi.stream_ptr(x.device)))
-        return gx.reshape(ctx.shape), None, None, None, None
+        return gx.reshape(ctx.shape), gfb, None, None, None
+
+
+def _pointwise_backward(op, a, g1, g2, n, p0, out):
+    with torch.cuda.device(a.device):
+        _cabi.check(_cabi.lib().tac_pointwise_backward_f32(op, _cabi.ptr(a), _cabi.ptr(g1) if g1 is not None else None,
+                                                           _cabi.ptr(g2) if g2 is not None else None, n, float(p0),
+                                                           _cabi.ptr(out), _cabi.stream_ptr(a.device)))
+    return out
+
+
+class _DbToAmplitudeFn(torch.autograd.Function):
+    """functional.py:299-314 differentiates through torch.pow; here dy/dx = y ln(10) / 20 from the saved output."""
+
+    @staticmethod
+    def forward(ctx, x, ref):
+        y = db_to_amplitude(x.detach(), ref)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (y,) = ctx.saved_tensors
+        g = _grad_f32(grad_out).contiguous()
+        return _pointwise_backward(0, y, g, None, y.numel(), 0.0, torch.empty_like(y)), None
+
+
+class _MagphaseFn(torch.autograd.Function):
+    """magphase / angle (functional.py:187-201): both outputs' gradients fold into one dL/dz pass."""
+
+    @staticmethod
+    def forward(ctx, complex_tensor, power, want_mag, name):
+        z = _as_f32_cuda(complex_tensor.detach(), "complex_tensor")
+        ctx.save_for_backward(z)
+        ctx.power, ctx.want_mag = power, want_mag
+        mag, phase = _magphase(z, power, want_mag, name)
+        if not want_mag:
+            mag = phase.new_empty(0)
+            ctx.mark_non_differentiable(mag)
+        return mag, phase
+
+    @staticmethod
+    def backward(ctx, grad_mag, grad_phase):
+        (z,) = ctx.saved_tensors
+        gm = _grad_f32(grad_mag).contiguous() if (ctx.want_mag and grad_mag is not None) else None
+        gp = _grad_f32(grad_phase).contiguous() if grad_phase is not None else None
+        if gm is None and gp is None:
+            return torch.zeros_like(z), None, None, None
+        return _pointwise_backward(1, z, gm, gp, z.numel() // 2, ctx.power, torch.empty_like(z)), None, None, None
+
+
+class _MuLawDecodingFn(torch.autograd.Function):
+    """Float codes are differentiable in the reference (functional.py:349-354, no rounding on that path)."""
+
+    @staticmethod
+    def forward(ctx, x_mu, n_quantize):
+        c = _as_f32_cuda(x_mu.detach(), "x_mu")
+        ctx.save_for_backward(c)
+        ctx.mu = float(n_quantize - 1)
+        return mu_law_decoding(c, n_quantize)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (c,) = ctx.saved_tensors
+        g = _grad_f32(grad_out).contiguous()
+        return _pointwise_backward(2, c, g, None, c.numel(), ctx.mu, torch.empty_like(c)), None
 
 
 class PreparedMelspectrogram(object):
@@ -782,7 +876,8 @@ def mu_law_decoding(x_mu, n_quantize=256, dtype=torch.float32):
     (lut,) = _mulaw_tables.on_device("dec", n_quantize, x_mu.device)
     lib = _cabi.lib()
     if x_mu.dtype.is_floating_point:
-        _forward_only(x_mu, "mu_law_decoding")
+        if _wants_grad(x_mu):
+            return _MuLawDecodingFn.apply(x_mu, int(n_quantize))
         codes = _as_f32_cuda(x_mu, "x_mu")
         fn = lib.tac_mulaw_decode_f32_f32
     else:

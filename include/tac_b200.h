@@ -100,6 +100,9 @@ int tac_fbplan_build_host(const float* fb_host, int n_bins, int n_bands,
  * e.g. create_mel_filter functional.py:131-169, n_bins = 1025).  The opaque handle is what
  * tac_melspec_banded_f32 takes; 0 means only the tensor-core path applies. */
 int64_t tac_fbplan_band_handle(const void* plan_host);
+/* Handle to pass to tac_melspec_banded_f32 for this plan at this fft length, 0 when the one-kernel path does not apply
+ * (dense matrix, other fft length): n_fft = 2048 -> the band plan's handle, 256 / 512 / 1024 -> the range plan's. */
+int64_t tac_fbplan_fused_handle(const void* plan_host, int n_fft);
 
 /* spec: (n_seq, n_bins, frames) real, or (n_seq, n_bins, frames, 2) complex when is_complex.
  * Computes |.|^power first when is_complex (a2), contracts over bins with the plan (a3) and,

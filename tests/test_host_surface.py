@@ -47,10 +47,10 @@ def test_num_frames_formula(tac):
 def _unpack_plan(blob, n_bins, n_bands):
     """Rebuild the dense matrix from the operand images; also returns the per-slice (band_lo, n)."""
     raw = blob.numpy().tobytes()
-    hdr = np.frombuffer(raw, dtype=np.int32, count=8)
+    hdr = np.frombuffer(raw, dtype=np.int32, count=12)                      # FbPlanHeader, 48 bytes
     assert hdr[1] == n_bins and hdr[2] == n_bands
     n_chunks, n_bblocks, max_n = int(hdr[3]), int(hdr[4]), int(hdr[5])
-    table = np.frombuffer(raw, dtype=np.int32, count=4 * n_chunks * n_bblocks, offset=32).reshape(n_bblocks, n_chunks, 4)
+    table = np.frombuffer(raw, dtype=np.int32, count=4 * n_chunks * n_bblocks, offset=48).reshape(n_bblocks, n_chunks, 4)
     fb = np.zeros((n_chunks * 32, n_bblocks * 128), dtype=np.float64)
     hi_only = np.zeros_like(fb)
     spans = []
@@ -97,6 +97,60 @@ def test_filterbank_plan_images(tac, which):
     # too-small buffer is refused, not overrun
     assert lib.tac_fbplan_build_host(fbc.data_ptr(), fb.size(0), fb.size(1), buf.data_ptr(), 64, ctypes.byref(used)) == -4
     assert b"too small" in lib.tac_last_error()
+
+
+def _unpack_range_plan(blob):
+    """(dense matrix rebuilt from the range plan, sum of range lengths), or None when the blob carries none."""
+    raw = blob.numpy().tobytes()
+    hdr = np.frombuffer(raw, dtype=np.int32, count=12)
+    off, nbytes = int(hdr[8]), int(hdr[9])
+    if off == 0:
+        return None
+    rh = np.frombuffer(raw, dtype=np.int32, count=8, offset=off)
+    n_bins, n_bands, pad, nnz_pad, max_len = (int(v) for v in rh[1:6])
+    assert nbytes == 32 + pad * 8 + nnz_pad * 4 and off % 16 == 0 and nbytes % 16 == 0
+    meta = np.frombuffer(raw, dtype=np.int32, count=2 * pad, offset=off + 32).reshape(pad, 2)
+    w = np.frombuffer(raw, dtype=np.float32, count=nnz_pad, offset=off + 32 + pad * 8)
+    fb = np.zeros((n_bins, n_bands), dtype=np.float32)
+    total = 0
+    for b in range(pad):
+        lo, ln, o = int(meta[b, 0]) & 0xffff, int(meta[b, 0]) >> 16, int(meta[b, 1])
+        assert ln <= max_len and (b < n_bands or ln == 0)
+        if ln:
+            fb[lo:lo + ln, b] = w[o:o + ln]
+            total += ln
+    return fb, total
+
+
+@pytest.mark.parametrize("name,fft", [("fb_16k_1025x128", 2048), ("fb_16k_513x128", 1024), ("fb_16k_129x128", 256)])
+def test_range_plan_describes_the_matrix(tac, name, fft):
+    """The per-band bin ranges of the fused epilogue for n_fft != 2048 (csrc/bandplan.cu build_range_plan) rebuild the
+    filterbank exactly; a dense matrix gets no range plan and no fused handle."""
+    g = golden("filterbanks.npz")
+    if name not in g:
+        fb = tac.MelFilterbank(num_freqs=fft // 2 + 1, num_mels=128, sample_rate=16000).get_filterbank()
+    else:
+        fb = g[name]
+    lib = tac._cabi.lib()
+
+    def build(m):
+        cap = lib.tac_fbplan_bytes(m.size(0), m.size(1))
+        buf = torch.zeros(cap, dtype=torch.uint8)
+        used = ctypes.c_int64()
+        mc = m.contiguous()
+        assert lib.tac_fbplan_build_host(mc.data_ptr(), m.size(0), m.size(1), buf.data_ptr(), cap, ctypes.byref(used)) == 0
+        return buf[:used.value]
+
+    blob = build(fb)
+    rebuilt, total = _unpack_range_plan(blob)
+    assert np.array_equal(rebuilt, fb.numpy())
+    assert total <= 2 * fb.size(0) + 2 * 128                             # a triangular bank: ~2 non-zeros per bin
+    handle = lib.tac_fbplan_fused_handle(blob.data_ptr(), fft)
+    assert handle != 0
+    assert lib.tac_fbplan_fused_handle(blob.data_ptr(), fft * 2) == 0      # wrong fft length for this matrix
+    dense = torch.randn(fft // 2 + 1, 40, generator=torch.Generator().manual_seed(9))
+    dblob = build(dense)
+    assert _unpack_range_plan(dblob) is None and lib.tac_fbplan_fused_handle(dblob.data_ptr(), fft) == 0
 
 
 # ---------------------------------------------------------------------------------------- mu-law tables
@@ -286,7 +340,12 @@ def test_one_kernel_path_predicate(tac, monkeypatch):
     assert F._mel_frame_major(tri, 2048, "contiguous", cpu, None) is False
     assert F._mel_frame_major(dense, 2048, "reference", cpu, None) is False                 # tensor-core path
     tri_small = tac.MelFilterbank(num_freqs=513, num_mels=64, sample_rate=16000).get_filterbank()
-    assert F._mel_frame_major(tri_small, 1024, "reference", cpu, None) is False
+    assert F._mel_frame_major(tri_small, 1024, "reference", cpu, None) is True               # range-plan epilogue (round 2)
+    assert F._mel_frame_major(torch.rand(513, 24) + 0.1, 1024, "reference", cpu, None) is False
+    tri_4096 = tac.MelFilterbank(num_freqs=2049, num_mels=64, sample_rate=16000).get_filterbank()
+    assert F._mel_frame_major(tri_4096, 4096, "reference", cpu, None) is True
+    tri_8192 = tac.MelFilterbank(num_freqs=4097, num_mels=64, sample_rate=16000).get_filterbank()
+    assert F._mel_frame_major(tri_8192, 8192, "reference", cpu, None) is False               # two-kernel path
     monkeypatch.setenv("TAC_MELSPEC_FUSED", "0")
     assert F._mel_frame_major(tri, 2048, "reference", cpu, None) is False
 

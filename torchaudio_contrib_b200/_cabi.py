@@ -42,6 +42,7 @@ SIGNATURES = {
     "tac_fbplan_bytes": (_i64, [_int, _int]),
     "tac_fbplan_build_host": (_int, [_ptr, _int, _int, _ptr, _i64, _c.POINTER(_i64)]),
     "tac_fbplan_band_handle": (_i64, [_ptr]),
+    "tac_fbplan_fused_handle": (_i64, [_ptr, _int]),
     "tac_power_mel_f32": (_int, [_ptr, _int, _f32, _i64, _i64, _int, _ptr, _int, _int, _f32, _f32, _ptr, _ptr]),
     "tac_melspec_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),
     "tac_melspec_f32": (_int, _STFT_ARGS + [_f32, _ptr, _int, _int, _f32, _f32, _ptr, _i64, _ptr, _ptr]),

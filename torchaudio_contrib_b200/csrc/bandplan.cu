@@ -136,4 +136,48 @@ int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char*
   return used;
 }
 
+int64_t build_range_plan(const float* fb, int n_bins, int n_bands, unsigned char* dst, int64_t capacity) {
+  if (n_bins < 1 || n_bins > 65535 || n_bands < 1 || n_bands > 4096) return 0;
+  if (capacity < range_plan_capacity(n_bins, n_bands)) return 0;
+  const int pad = (n_bands + 31) / 32 * 32;
+  std::vector<int> lo(pad, 0), len(pad, 0);
+  int64_t total = 0;
+  int max_len = 0;
+  for (int b = 0; b < n_bands; ++b) {
+    int first = -1, last = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (fb[(size_t)k * n_bands + b] != 0.0f) {          // NaN != 0 too: it reaches the output as in the reference's matmul
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first >= 0) {
+      lo[b] = first;
+      len[b] = last - first + 1;
+      total += len[b];
+      if (len[b] > max_len) max_len = len[b];
+    }
+  }
+  if (total > (int64_t)4 * n_bins || max_len > 32767) return 0;   // dense: the tensor-core path is the right one
+  const int nnz_pad = (int)((total + 3) / 4 * 4);
+  RangePlanHeader* hdr = reinterpret_cast<RangePlanHeader*>(dst);
+  memset(hdr, 0, sizeof(*hdr));
+  hdr->magic = kRangePlanMagic;
+  hdr->n_bins = n_bins;
+  hdr->n_bands = n_bands;
+  hdr->n_bands_pad = pad;
+  hdr->nnz_pad = nnz_pad;
+  hdr->max_len = max_len;
+  int32_t* meta = reinterpret_cast<int32_t*>(dst + 32);
+  float* w = reinterpret_cast<float*>(dst + 32 + (size_t)pad * 8);
+  int off = 0;
+  for (int b = 0; b < pad; ++b) {
+    meta[2 * b] = lo[b] | (len[b] << 16);
+    meta[2 * b + 1] = off;
+    for (int i = 0; i < len[b]; ++i) w[off + i] = fb[(size_t)(lo[b] + i) * n_bands + b];
+    off += len[b];
+  }
+  for (int i = off; i < nnz_pad; ++i) w[i] = 0.0f;
+  return 32 + (int64_t)pad * 8 + (int64_t)nnz_pad * 4;
+}
+
 }  // namespace tac

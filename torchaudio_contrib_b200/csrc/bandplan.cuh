@@ -54,6 +54,26 @@ static inline int64_t band_plan_capacity(int n_bands) {
   return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 32 * 16 * 4 + 128;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Range plan ("CSR by band"): the form consumed by the fused STFT + filterbank epilogue of the warp kernels for
+// n_fft = 256 / 512 / 1024 / 4096 (stft_multi.cu, stft4096.cu: OUT_MEL_RANGE).  Band m is stored as the contiguous bin
+// range [lo_m, lo_m + len_m) that covers its non-zeros, with the weights of that range; a lane owns bands m = lane + 32 j
+// and sums w * |X|^p over each range from the frame's power spectrum in shared memory.  Any matrix qualifies whose
+// ranges stay short (sum of lengths <= 4 n_bins): every triangular filterbank, not dense ones.
+//   RangePlanHeader                              32 B
+//   meta [n_bands_pad] int2   (lo | len << 16, offset of the band's first weight in `w`)
+//   w    [nnz_pad]     float
+constexpr uint32_t kRangePlanMagic = 0x7ac0c5a1u;
+struct RangePlanHeader {
+  uint32_t magic;
+  int32_t n_bins, n_bands, n_bands_pad, nnz_pad, max_len, reserved[2];
+};
+static inline int64_t range_plan_capacity(int n_bins, int n_bands) {
+  return 32 + ((int64_t)(n_bands + 31) / 32 * 32) * 8 + ((int64_t)4 * n_bins + 4) * 4 + 128;
+}
+// bytes written at `dst` (multiple of 16), or 0 when the ranges are too long (dense matrix) or too large for the kernels
+int64_t build_range_plan(const float* fb, int n_bins, int n_bands, unsigned char* dst, int64_t capacity);
+
 // Returns the bytes written at `dst` (multiple of 16), or 0 when the matrix is not of the two-adjacent-bands
 // form (or needs more slots / list entries than the kernel holds).  Host code (bandplan.cu).
 int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char* dst, int64_t capacity);

@@ -47,6 +47,9 @@ struct FbPlanHeader {
   int32_t max_n;      // widest block (bands) over all K slices
   int32_t band_off;   // byte offset of the band plan (bandplan.cuh) inside this blob, 0: the matrix has no such form
   int32_t band_cmax;  // its list length (entries per band)
+  int32_t range_off;  // byte offset of the range plan (bandplan.cuh) inside this blob, 0: ranges too long (dense matrix)
+  int32_t range_bytes;
+  int32_t reserved[2];
 };
 struct FbPlanChunk {
   int32_t band_lo;    // first band of the block, relative to the band block, multiple of 16
@@ -513,7 +516,7 @@ extern "C" int64_t tac_fbplan_bytes(int n_bins, int n_bands) {
   const int64_t n_chunks = (n_bins + kMbBK - 1) / kMbBK;
   const int64_t n_bblocks = (n_bands + kMbBandBlock - 1) / kMbBandBlock;
   return 128 + (int64_t)sizeof(FbPlanHeader) + n_chunks * n_bblocks * ((int64_t)sizeof(FbPlanChunk) + 2 * kMbTileBytes) +
-         band_plan_capacity(n_bands);
+         band_plan_capacity(n_bands) + range_plan_capacity(n_bins, n_bands);
 }
 
 extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, void* plan_host, int64_t capacity,
@@ -587,8 +590,29 @@ extern "C" int tac_fbplan_build_host(const float* fb, int n_bins, int n_bands, v
     hdr->band_cmax = reinterpret_cast<const BandPlanHeader*>(base + off)->cmax;
     off += band_bytes;
   }
+  // and as per-band bin ranges for the fused epilogue of the other fft lengths
+  off = (off + 127) & ~(int64_t)127;
+  const int64_t range_bytes = build_range_plan(fb, n_bins, n_bands, base + off, capacity - off);
+  if (range_bytes > 0) {
+    hdr->range_off = (int32_t)off;
+    hdr->range_bytes = (int32_t)range_bytes;
+    off += range_bytes;
+  }
   *used = off;
   return TAC_OK;
+}
+
+// Handle of the one-kernel mel path for this plan and fft length, 0 when there is none: n_fft = 2048 -> the band plan
+// (tac_fbplan_band_handle), 256 / 512 / 1024 / 4096 -> the range plan (offset | bytes << 32).
+extern "C" int64_t tac_fbplan_fused_handle(const void* plan_host, int n_fft) {
+  using namespace tac;
+  if (!plan_host) return 0;
+  const FbPlanHeader* hdr = static_cast<const FbPlanHeader*>(plan_host);
+  if (hdr->magic != kPlanMagic || hdr->n_bins != n_fft / 2 + 1) return 0;
+  if (n_fft == 2048) return tac_fbplan_band_handle(plan_host);
+  if ((n_fft == 256 || n_fft == 512 || n_fft == 1024 || n_fft == 4096) && hdr->range_off > 0)
+    return (int64_t)hdr->range_off | ((int64_t)hdr->range_bytes << 32);
+  return 0;
 }
 
 extern "C" int64_t tac_fbplan_band_handle(const void* plan_host) {

@@ -74,11 +74,40 @@ static bool fused_enabled() {
 static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, int64_t band_handle, int n_bands, int to_db,
                               float ref, float amin, float* out, int frame_major, cudaStream_t stream,
                               float* const* peer_out = nullptr, int n_peers = 0, int64_t peer_seq0 = 0) {
-  TAC_REQUIRE(sp.n_fft == 2048, TAC_ERR_UNSUPPORTED, "melspec_banded: the fused kernel exists for n_fft = 2048 only (got %d)", sp.n_fft);
+  TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melspec_banded: plan must be 16-byte aligned");
+  if (sp.n_fft != 2048) {
+    // n_fft = 256 / 512 / 1024 / 4096: the warp kernels with the range-plan epilogue (stft_multi.cu); handle = offset | bytes << 32
+    TAC_REQUIRE(sp.n_fft == 256 || sp.n_fft == 512 || sp.n_fft == 1024 || sp.n_fft == 4096, TAC_ERR_UNSUPPORTED,
+                "melspec_banded: no one-kernel path for n_fft = %d", sp.n_fft);
+    TAC_REQUIRE(n_peers == 0, TAC_ERR_UNSUPPORTED, "melspec_banded_peers: n_fft = 2048 only");
+    const int64_t roff = band_handle & 0xffffffffLL, rbytes = band_handle >> 32;
+    TAC_REQUIRE(roff > 0 && (roff & 15) == 0 && rbytes > 32 && (rbytes & 15) == 0, TAC_ERR_INVALID, "melspec_banded: bad range handle");
+    if (sp.n_seq * sp.frames == 0) return TAC_OK;
+    sp.out = out;
+    sp.out_mode = OUT_MEL_RANGE;
+    sp.power = power;
+    sp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
+    sp.band_plan = static_cast<const unsigned char*>(plan_dev) + roff;
+    sp.band_cmax = (int)((rbytes - 32) / 16);                          // uint4 count of meta + weights
+    sp.n_bands = n_bands;
+    sp.n_bands_pad = (n_bands + 31) / 32 * 32;
+    sp.to_db = to_db ? 1 : 0;
+    sp.amin = amin;
+    sp.log10_ref = log10f(ref);
+    if (frame_major) {
+      sp.out_seq_stride = sp.frames * n_bands;
+      sp.out_t_stride = n_bands;
+      sp.out_band_stride = 1;
+    } else {
+      sp.out_seq_stride = (int64_t)n_bands * sp.frames;
+      sp.out_t_stride = 1;
+      sp.out_band_stride = sp.frames;
+    }
+    return launch_stft(sp, stream);
+  }
   const int64_t off = band_handle & (((int64_t)1 << 48) - 1);
   const int cmax = (int)(band_handle >> 48);
   TAC_REQUIRE(off > 0 && (off & 15) == 0 && cmax >= 1 && cmax <= 16, TAC_ERR_INVALID, "melspec_banded: bad band handle");
-  TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melspec_banded: plan must be 16-byte aligned");
   if (sp.n_seq * sp.frames == 0) return TAC_OK;
   sp.out = out;
   sp.out_mode = OUT_MEL_FUSED;
@@ -238,7 +267,7 @@ static int pipeline_build(tac_pipeline* p, const tac_pipeline_config* cfg, const
     if (rc == TAC_OK) {
       cudaError_t e = cudaMalloc(&p->d_plan, (size_t)used);
       if (e == cudaSuccess) e = cudaMemcpy(p->d_plan, host, (size_t)used, cudaMemcpyHostToDevice);
-      if (cfg->n_fft == 2048 && fused_enabled()) p->band_handle = tac_fbplan_band_handle(host);
+      if (fused_enabled()) p->band_handle = tac_fbplan_fused_handle(host, cfg->n_fft);
       if (e != cudaSuccess) rc = fail(TAC_ERR_CUDA, "pipeline_create: plan upload failed: %s", cudaGetErrorString(e));
     }
     free(host);

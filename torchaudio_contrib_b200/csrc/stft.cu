@@ -900,7 +900,7 @@ static int mel_kernel_variant() {
 int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
-  if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024)) return launch_stft_warp(p, stream);
+  if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024 || p.n_fft == 4096)) return launch_stft_warp(p, stream);
   if (p.n_fft == 2048 && p.onesided && (p.out_mode == OUT_MEL_FUSED || p.out_mode == OUT_MEL_FUSED_PEERS)) {
     // two frames per warp in packed fp32 pairs (stft_pair.cu); TAC_MEL_SINGLE=1 keeps the one-frame-per-warp kernel
     // below (A/B timing and the bit-equality test of the two)

@@ -1,9 +1,11 @@
-// K1b: the warp-level register FFT of stft.cu generalised to n_fft = 256 / 512 / 1024.
+// K1b: the warp-level register FFT of stft.cu generalised to n_fft = 256 / 512 / 1024 / 4096.
 //
-// A frame of n_fft real samples is a complex FFT of C = n_fft / 2 points; C = R1 x R2 with both factors at most
-// 32, so a warp handles F = 1024 / C frames at once and every lane still owns exactly 32 complex values:
+// A frame of n_fft real samples is a complex FFT of C = n_fft / 2 points; C = R1 x R2.  For the small sizes both
+// factors are at most 32, a warp handles F = 1024 / C frames at once and every lane owns 32 complex values; n_fft =
+// 4096 is one frame per warp with 64 complex values per lane (8 warps of 255 registers instead of 16 of 128):
 //
 //     n_fft   C    R1 x R2   F (frames per warp batch)   pass-1 FFTs per lane   pass-2 FFTs per lane
+//     4096  2048   32 x 64   1                           2 x 32-point           1 x 64-point
 //     1024   512   16 x 32   2                           2 x 16-point           1 x 32-point
 //      512   256   16 x 16   4                           2 x 16-point           2 x 16-point
 //      256   128    8 x 16   8                           4 x  8-point           2 x 16-point
@@ -13,27 +15,28 @@
 // pass 2 applies W_C^(n1 k2) and transforms over n1 (R2 points): Z[R1 k1 + k2].  The real-FFT untangling
 // pairs (k1, k2) with (R2-1-k1, R1-k2) inside the frame's group of R1 lanes by one shuffle.
 // Frames are staged like in stft2048_kernel: one bulk async copy per interior frame into the slab, a gather
-// for frames touching the padding.  n_fft = 2048 keeps its own kernel (stft.cu); 4096+ and the option
+// for frames touching the padding.  n_fft = 2048 keeps its own kernels (stft.cu, stft_pair.cu); 8192 and the option
 // surface that these do not cover (two-sided output) use stft_generic_kernel.
+#include "bandplan.cuh"
 #include "fft_regs.cuh"
 #include "stft_params.cuh"
 #include "tac_common.cuh"
 
 namespace tac {
 
-constexpr int kMwWarps = 16;
-constexpr int kMwThreads = kMwWarps * 32;
-constexpr int kMwSlabFloats = 2 * 64 * 17 + 32;          // >= 2048 samples and >= rows x stride complex for every size
-
 template <int LOG2N>
 struct WarpFftShape {
   static constexpr int N = 1 << LOG2N, C = N / 2;
-  static constexpr int R1 = (LOG2N == 10) ? 16 : (LOG2N == 9 ? 16 : 8);
+  static constexpr int R1 = (LOG2N == 12) ? 32 : ((LOG2N == 10) ? 16 : (LOG2N == 9 ? 16 : 8));
   static constexpr int R2 = C / R1;
-  static constexpr int F = 1024 / C;
+  static constexpr int F = (C >= 1024) ? 1 : 1024 / C;
+  static constexpr int V = F * C / 32;                   // complex values per lane: 32, or 64 at n_fft = 4096
   static constexpr int A1 = F * R2 / 32, A2 = F * R1 / 32;
   static constexpr int S = R2 + 1;                       // slab row stride (complex), odd
-  static_assert(A1 * R1 == 32 && A2 * R2 == 32 && F * R1 * S * 2 <= kMwSlabFloats && F * N <= kMwSlabFloats, "shape");
+  static constexpr int WARPS = (V > 32) ? 8 : 16;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int SLAB = (LOG2N == 12) ? 2 * 32 * 65 : 2 * 64 * 17 + 32;   // floats: >= F N samples and >= F R1 S complex
+  static_assert(A1 * R1 == V && A2 * R2 == V && F * R1 * S * 2 <= SLAB && F * N <= SLAB && F * (C + 1) <= SLAB, "shape");
 };
 
 template <int PMODE>
@@ -45,9 +48,10 @@ __device__ __forceinline__ float mw_power(float re, float im, float half_power) 
 }
 
 template <int LOG2N, int OUT_MODE, int PMODE>
-__global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftParams p) {
+__global__ void __launch_bounds__(WarpFftShape<LOG2N>::THREADS, 1) stft_warp_kernel(const StftParams p) {
   using Sh = WarpFftShape<LOG2N>;
-  constexpr int N = Sh::N, C = Sh::C, R1 = Sh::R1, R2 = Sh::R2, F = Sh::F, A1 = Sh::A1, A2 = Sh::A2, S = Sh::S;
+  constexpr int N = Sh::N, C = Sh::C, R1 = Sh::R1, R2 = Sh::R2, F = Sh::F, A1 = Sh::A1, A2 = Sh::A2, S = Sh::S, V = Sh::V;
+  constexpr int kMwWarps = Sh::WARPS, kMwThreads = Sh::THREADS, kMwSlabFloats = Sh::SLAB;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_win = reinterpret_cast<float2*>(smem_raw);        // [C]        (w[2n], w[2n+1]) * 0.5 * scale
@@ -55,6 +59,9 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
   float2* s_tw2 = s_tw1 + C;                                  // [R2][R1]   W_N^(R1 k1 + k2)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw2 + C);
   float* s_slab = reinterpret_cast<float*>(s_bar + kMwWarps);
+  // OUT_MEL_RANGE: the range plan's meta and weights (bandplan.cuh), copied once per CTA
+  const int2* s_meta = reinterpret_cast<const int2*>(s_slab + kMwWarps * kMwSlabFloats);
+  const float* s_w = reinterpret_cast<const float*>(s_meta + (OUT_MODE == OUT_MEL_RANGE ? p.n_bands_pad : 0));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < C; i += kMwThreads) {
@@ -66,6 +73,11 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
     s_tw1[i] = make_float2(cs, sn);
     sincospif(-2.0f * (float)(R1 * a + b) / (float)N, &sn, &cs);
     s_tw2[i] = make_float2(cs, sn);
+  }
+  if constexpr (OUT_MODE == OUT_MEL_RANGE) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.band_plan + 32);
+    uint4* dst = reinterpret_cast<uint4*>(s_slab + kMwWarps * kMwSlabFloats);
+    for (int i = tid; i < p.band_cmax; i += kMwThreads) dst[i] = __ldg(src + i);      // band_cmax: uint4 count of meta + weights
   }
   uint64_t* bar = s_bar + warp;
   if (lane == 0) {
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
     __syncwarp();
 
     // ---- pass 1: item i1 = a * 32 + lane = (frame f1, n1); R1-point FFT over n2 -------------------------
-    float2 v[32];
+    float2 v[V];
 #pragma unroll
     for (int a = 0; a < A1; ++a) {
       const int i1 = a * 32 + lane, f1 = i1 / R2, n1 = i1 % R2;
@@ -160,6 +172,83 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
     // ---- pass 2: item i2 = b * 32 + lane = (frame f2, k2); twiddle, R2-point FFT over n1, untangle -------
     const int kk2 = lane % R1;                                // k2 of this lane's items (R1 divides 32)
     const int partner = (lane & ~(R1 - 1)) | ((R1 - kk2) & (R1 - 1));
+    if constexpr (OUT_MODE == OUT_MEL_RANGE) {
+      // Fused filterbank (replaces apply_filterbank's transpose + matmul + transpose, functional.py:183-184, and the dB
+      // pass :291-296): every pass-2 input is taken out of the slab first, so that the slab can take the F frames' power
+      // spectra ((C + 1) floats each); then lane <-> bands lane + 32 j sum their bin ranges for all F frames at once.
+      constexpr int SP = C + 1;
+      float2 uu[V];
+#pragma unroll
+      for (int b = 0; b < A2; ++b) {
+        const int i2 = b * 32 + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < R2; ++n1) {
+          const float2 a = slab[i2 * S + n1];
+          const float2 w = s_tw1[n1 * R1 + kk2];
+          uu[b * R2 + n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < A2; ++b) {
+        const int f2 = (b * 32 + lane) / R1;
+        float2 u[R2];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) u[i] = uu[b * R2 + i];
+        dit_fft_fma<R2>(u);
+        float* ps = slab_f + f2 * SP;
+#pragma unroll
+        for (int k1 = 0; k1 < R2; ++k1) {
+          const float2 z = u[bit_reverse<R2>(k1)];
+          float2 q;
+          q.x = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].x, partner);
+          q.y = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].y, partner);
+          if (kk2 == 0) q = u[bit_reverse<R2>((R2 - k1) % R2)];
+          const float a = z.x + q.x, bb = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+          const float2 w = s_tw2[k1 * R1 + kk2];
+          ps[R1 * k1 + kk2] = mw_power<PMODE>(fmaf(w.x, gs, fmaf(-w.y, h, a)), fmaf(w.x, h, fmaf(w.y, gs, bb)), half_power);
+        }
+        if (kk2 == 0) ps[C] = mw_power<PMODE>(2.0f * (u[0].x - u[0].y), 0.0f, half_power);
+      }
+      __syncwarp();
+      uint32_t seq_f[F], t_f[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const uint32_t g = gb + f;
+        seq_f[f] = g / frames_u;
+        t_f[f] = g - seq_f[f] * frames_u;
+      }
+      const int nbj = p.n_bands_pad >> 5;
+      for (int j = 0; j < nbj; ++j) {
+        const int m = lane + 32 * j;
+        const int2 me = s_meta[m];
+        const int lo = me.x & 0xffff, len = me.x >> 16;
+        const float* w = s_w + me.y;
+        const float* pp = slab_f + lo;
+        float acc[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+        for (int i = 0; i < len; ++i) {
+          const float wv = w[i];
+#pragma unroll
+          for (int f = 0; f < F; ++f) acc[f] = fmaf(pp[f * SP + i], wv, acc[f]);
+        }
+        if (m < p.n_bands) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            if ((int64_t)(gb + f) >= p.g1) continue;
+            float r = acc[f];
+            if (p.to_db) {
+              float s2 = r * r;
+              s2 = (s2 < p.amin) ? p.amin : s2;
+              r = 10.0f * (log10f(s2) - p.log10_ref);
+            }
+            __stcs(p.out + (int64_t)seq_f[f] * p.out_seq_stride + (int64_t)t_f[f] * p.out_t_stride + (int64_t)m * p.out_band_stride, r);
+          }
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int b = 0; b < A2; ++b) {
       const int i2 = b * 32 + lane, f2 = i2 / R1;
@@ -217,7 +306,8 @@ __global__ void __launch_bounds__(kMwThreads, 1) stft_warp_kernel(const StftPara
 
 template <int LOG2N>
 static size_t warp_kernel_smem() {
-  return 3 * (size_t)WarpFftShape<LOG2N>::C * sizeof(float2) + kMwWarps * sizeof(uint64_t) + (size_t)kMwWarps * kMwSlabFloats * sizeof(float);
+  using Sh = WarpFftShape<LOG2N>;
+  return 3 * (size_t)Sh::C * sizeof(float2) + Sh::WARPS * sizeof(uint64_t) + (size_t)Sh::WARPS * Sh::SLAB * sizeof(float);
 }
 
 template <int LOG2N>
@@ -228,21 +318,25 @@ static int launch_warp_kernel(const StftParams& p, cudaStream_t stream) {
   else if (p.out_mode == OUT_POWER_PUBLIC)
     k = p.power_mode == 2 ? stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 2>
                           : (p.power_mode == 1 ? stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 1> : stft_warp_kernel<LOG2N, OUT_POWER_PUBLIC, 0>);
+  else if (p.out_mode == OUT_MEL_RANGE)
+    k = p.power_mode == 2 ? stft_warp_kernel<LOG2N, OUT_MEL_RANGE, 2>
+                          : (p.power_mode == 1 ? stft_warp_kernel<LOG2N, OUT_MEL_RANGE, 1> : stft_warp_kernel<LOG2N, OUT_MEL_RANGE, 0>);
   else
     k = p.power_mode == 2 ? stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 2>
                           : (p.power_mode == 1 ? stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 1> : stft_warp_kernel<LOG2N, OUT_POWER_ROWS, 0>);
-  const size_t smem = warp_kernel_smem<LOG2N>();
+  const size_t smem = warp_kernel_smem<LOG2N>() + (p.out_mode == OUT_MEL_RANGE ? (size_t)p.band_cmax * 16 : 0);
+  TAC_REQUIRE(smem <= 227 * 1024, TAC_ERR_UNSUPPORTED, "melspec: range plan of %d bytes does not fit beside the FFT buffers", p.band_cmax * 16);
   TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t batches = (p.g1 - p.g0 + WarpFftShape<LOG2N>::F - 1) / WarpFftShape<LOG2N>::F;
-  const int64_t want = (batches + kMwWarps - 1) / kMwWarps;
+  const int64_t want = (batches + WarpFftShape<LOG2N>::WARPS - 1) / WarpFftShape<LOG2N>::WARPS;
   const int grid = (int)(want < sm_count() ? want : sm_count());
   LaunchProbe probe(KIND_STFT, stream);
-  k<<<grid, kMwThreads, smem, stream>>>(p);
+  k<<<grid, WarpFftShape<LOG2N>::THREADS, smem, stream>>>(p);
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
 }
 
-// n_fft = 256 / 512 / 1024, one-sided output: returns TAC_ERR_UNSUPPORTED for anything else (caller falls
+// n_fft = 256 / 512 / 1024 / 4096, one-sided output: returns TAC_ERR_UNSUPPORTED for anything else (caller falls
 // through to the generic kernel)
 int launch_stft_warp(const StftParams& p, cudaStream_t stream) {
   if (!p.onesided) return TAC_ERR_UNSUPPORTED;
@@ -250,6 +344,7 @@ int launch_stft_warp(const StftParams& p, cudaStream_t stream) {
     case 256: return launch_warp_kernel<8>(p, stream);
     case 512: return launch_warp_kernel<9>(p, stream);
     case 1024: return launch_warp_kernel<10>(p, stream);
+    case 4096: return launch_warp_kernel<12>(p, stream);
     default: return TAC_ERR_UNSUPPORTED;
   }
 }

@@ -11,7 +11,8 @@ enum StftOutMode {
   OUT_POWER_PUBLIC = 1,     // (n_seq, bins, frames)      -- reference layout of `Spectrogram`
   OUT_POWER_ROWS = 2,       // |X|^p in "power tiles": the swizzled tensor-core operand layout (below)
   OUT_MEL_FUSED = 3,        // |X|^p contracted with a two-band filterbank inside the kernel (bandplan.cuh) [+ dB]
-  OUT_MEL_FUSED_PEERS = 4   // the same, every frame's bands stored into the output buffers of all ranks of the box (peers.cu)
+  OUT_MEL_FUSED_PEERS = 4,  // the same, every frame's bands stored into the output buffers of all ranks of the box (peers.cu)
+  OUT_MEL_RANGE = 5         // |X|^p contracted with a range plan (bandplan.cuh) inside the warp kernels for n_fft != 2048 [+ dB]
 };
 constexpr int kMaxPeers = 8;           // GPUs of one NVSwitch box
 

@@ -234,6 +234,10 @@ class FilterbankPlan(object):
                                               ctypes.byref(used)))
         # non-zero: the matrix is a chain of two-band rows and the one-kernel path applies (n_fft = 2048)
         self.band_handle = int(lib.tac_fbplan_band_handle(_cabi.ptr(host)))
+        # non-zero: the one-kernel mel path applies at the fft length this matrix belongs to (2048: band plan; 256 / 512 /
+        # 1024: per-band bin ranges); it is the handle tac_melspec_banded_f32 takes
+        self.fft_length = 2 * (self.num_freqs - 1)
+        self.fused_handle = int(lib.tac_fbplan_fused_handle(_cabi.ptr(host), self.fft_length))
         self.blob = host[:used.value].to(device)
         self.device = self.blob.device
         self.key = FilterbankPlan.key_of(filterbank)
@@ -411,9 +415,10 @@ def _workspace(device, nbytes):
 
 def _mel_frame_major(filterbank, fft_length, layout, device, cache):
     """True when `melspectrogram` will write a `(*, frames, num_bands)` buffer (one-kernel path, reference layout)."""
-    if layout != "reference" or int(fft_length) != 2048 or os.environ.get("TAC_MELSPEC_FUSED", "1") == "0":
+    if layout != "reference" or os.environ.get("TAC_MELSPEC_FUSED", "1") == "0":
         return False
-    return bool(_plan_for(filterbank, device, cache).band_handle)
+    plan = _plan_for(filterbank, device, cache)
+    return bool(plan.fused_handle) and plan.fft_length == int(fft_length)
 
 
 def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_length=None, window=None,
@@ -423,8 +428,10 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     (layers.py:350-381).  `(*, channel, time) -> (*, channel, num_bands, frames)`.
 
     `fft_length == 2048` and a filterbank whose rows have at most two adjacent non-zeros (every
-    triangular filterbank): ONE kernel, a warp per frame from its samples to its `num_bands` outputs,
-    the spectrum never leaves the SM (csrc/stft.cu OUT_MEL_FUSED; `TAC_MELSPEC_FUSED=0` disables).
+    triangular filterbank): ONE kernel, two frames per warp from their samples to their `num_bands` outputs,
+    the spectrum never leaves the SM (csrc/stft_pair.cu; `TAC_MELSPEC_FUSED=0` disables).  `fft_length` 256 / 512 /
+    1024 and a filterbank whose bands cover short bin ranges (again every triangular one): ONE kernel too, the warp
+    FFT kernels with the band sums as their epilogue (csrc/stft_multi.cu OUT_MEL_RANGE).
     Otherwise two back-to-back kernels: stft + |.|^power into frame-major power tiles that stay in
     L2, then the tensor-core filterbank with the dB clamp in its epilogue.
 
@@ -454,14 +461,14 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
         raise ValueError("melspectrogram: layout must be 'contiguous' or 'reference', got %r" % (layout,))
     lib = _cabi.lib()
     frames = max(frames, 0)
-    if plan.band_handle and int(fft_length) == 2048 and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0":
+    if plan.fused_handle and plan.fft_length == int(fft_length) and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0":
         frame_major = layout == "reference"
         shape = (flat.size(0), frames, plan.num_bands) if frame_major else (flat.size(0), plan.num_bands, frames)
         out = torch.empty(shape, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _cabi.check(lib.tac_melspec_banded_f32(
                 *_stft_args(flat, win, fft_length, hop, center, pad_mode, normalized),
-                float(power), _cabi.ptr(plan.blob), plan.band_handle, plan.num_bands, int(bool(to_db)), float(ref),
+                float(power), _cabi.ptr(plan.blob), plan.fused_handle, plan.num_bands, int(bool(to_db)), float(ref),
                 float(amin), _cabi.ptr(out), int(frame_major), _cabi.stream_ptr(x.device)))
         out = out.reshape(lead + out.shape[1:])
         return out if _raw_buffer else (out.transpose(-2, -1) if frame_major else out)
@@ -787,7 +794,9 @@ class PreparedMelspectrogram(object):
                                % (self.plan.num_freqs, fft_length // 2 + 1))
         if pad_mode not in _cabi.PAD_MODES:
             raise NotImplementedError("stft: pad_mode=%r" % (pad_mode,))
-        self.fused = bool(self.plan.band_handle) and int(fft_length) == 2048 and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0"
+        self.fused = (bool(self.plan.fused_handle) and self.plan.fft_length == int(fft_length)
+                      and os.environ.get("TAC_MELSPEC_FUSED", "1") != "0")
+        self.fft_length = int(fft_length)
         if layout not in ("contiguous", "reference"):
             raise ValueError("layout must be 'contiguous' or 'reference', got %r" % (layout,))
         self.frame_major = layout == "reference" and self.fused     # `out` is then (*, frames, num_bands); view it transposed
@@ -797,7 +806,7 @@ class PreparedMelspectrogram(object):
                 int(bool(center)), _cabi.PAD_MODES[pad_mode], int(bool(normalized)), float(power), _cabi.ptr(self.plan.blob)]
         tail = [self.plan.num_bands, int(bool(to_db)), float(ref), float(amin)]
         if self.fused:
-            self._fn, self._head, self._tail = lib.tac_melspec_banded_f32, head + [self.plan.band_handle] + tail, [int(self.frame_major)]
+            self._fn, self._head, self._tail = lib.tac_melspec_banded_f32, head + [self.plan.fused_handle] + tail, [int(self.frame_major)]
             self._ws = None
         else:
             nbytes = int(lib.tac_melspec_workspace_bytes(self.n_seq, self.n_samples, int(fft_length), self.hop, int(bool(center))))
@@ -824,7 +833,7 @@ class PreparedMelspectrogram(object):
         `(total_items,) + out_shape[1:]`) from the kernel's epilogue, over NVLink -- the all-gather of SURVEY 8(e)
         without a collective.  `item_offset`: this rank's first batch item in the full output (default:
         `shard_range` of equal shards).  Follow with `gathered.barrier()`.  One-kernel path only."""
-        if not self.fused:
+        if not self.fused or self.fft_length != 2048:
             raise NotImplementedError("gather_into: only the one-kernel mel path (fft_length 2048, triangular filterbank) "
                                       "stores to peer buffers")
         if tuple(x.shape) != self.shape or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:

@@ -270,8 +270,10 @@ int tac_profile_enable(int on);
 int tac_profile_read(double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
 /* Which kernel serves the one-kernel mel path (tac_melspec_banded_f32 and everything built on it):
  * 0 (default) = two frames per warp in packed fp32 pairs (csrc/stft_pair.cu), 1 = one frame per warp
- * (csrc/stft.cu, round 1).  The two agree bit for bit; the switch exists for A/B timing and that test.
- * Returns the previous value; a negative argument only queries.  Environment: TAC_MEL_SINGLE=1. */
+ * (csrc/stft.cu, round 1), 2 = the pair kernel with its second 32-point FFT pass on the tcgen05 tensor cores
+ * (3xTF32, operands through tensor memory; csrc/stft_pair_tc.cu).  0 and 1 agree bit for bit, 2 to fp32 rounding
+ * (the transform is summed in a different order); the switch exists for A/B timing and the parity tests.
+ * Returns the previous value; a negative argument only queries.  Environment: TAC_MEL_VARIANT=0|1|2. */
 int tac_mel_kernel_variant(int variant);
 
 #ifdef __cplusplus

@@ -455,6 +455,45 @@ def test_pair_kernel_matches_single(tac, oc):
     _log_parity("pair kernel vs one-frame kernel", max_rel=worst)
 
 
+def test_pair_kernel_tensor_core_pass_matches_oracle(tac, oc):
+    """tac_mel_kernel_variant(2): the pair kernel with its second 32-point FFT pass on tcgen05 (3xTF32, operands through
+    tensor memory; csrc/stft_pair_tc.cu).  Same cases as above against the oracle and the default kernel; the transform is
+    summed in a different order, so agreement is to fp32 rounding (measured 3e-6 relative), not bit for bit.  Chunk lengths
+    that are not a multiple of the eight pairs of a round (warps without a pair in the last round) are covered by the
+    ragged shapes, full rounds by the (40, 1, 160000) case."""
+    lib = tac._cabi.lib()
+    torch.manual_seed(67)
+    cases = [((3, 1, 16000), 16000, "reflect", False, 512), ((2, 2, 48001), 48000, "reflect", True, 512),
+             ((5, 1, 4096), 16000, "constant", False, 512), ((1, 1, 2049), 22050, "replicate", True, 512),
+             ((4, 1, 33333), 16000, "circular", False, 512), ((2, 1, 30000), 16000, "reflect", False, 300),
+             ((40, 1, 160000), 16000, "reflect", False, 512), ((1, 1, 2048), 16000, "reflect", False, 512)]
+    worst = 0.0
+    try:
+        for shape, sr, pad_mode, db, hop in cases:
+            x = torch.randn(*shape)
+            m = _mel_chain(tac, sr=sr, to_db=db, hop_length=hop, pad_mode=pad_mode)
+            lib.tac_mel_kernel_variant(0)
+            pair = m(dev(x)).clone()
+            lib.tac_mel_kernel_variant(2)
+            n0 = lib.tac_launch_count()
+            tc = m(dev(x)).clone()
+            assert lib.tac_launch_count() - n0 == 1
+            again = m(dev(x))
+            assert torch.equal(tc, again), (shape, "not deterministic")
+            want = oc.melspectrogram(x, 128, sr, to_db=db, fft_length=2048, hop_length=hop, pad_mode=pad_mode)
+            if db:
+                assert (tc - pair).abs().max().item() < 2e-4, (shape, pad_mode)
+                assert (tc.cpu() - want).abs().max().item() < 1e-3, (shape, pad_mode)
+            else:
+                err = pure_rel_err(tc.cpu(), pair.cpu())
+                worst = max(worst, err)
+                assert err < 2e-5, (shape, pad_mode, hop)
+                assert pure_rel_err(tc.cpu(), want) < REL, (shape, pad_mode, hop)
+    finally:
+        lib.tac_mel_kernel_variant(0)
+    _log_parity("pair kernel with tcgen05 pass vs default pair kernel", max_rel=worst)
+
+
 def test_host_pipeline_cfg1(tac):
     g = golden("cfg1_spectrogram_512_128.npz")
     hp = tac.HostPipeline(512, 128, power=1.0)

@@ -893,7 +893,11 @@ int dump_k1_trace() {
 
 static int g_mel_variant = -1;
 static int mel_kernel_variant() {
-  if (g_mel_variant < 0) g_mel_variant = getenv("TAC_MEL_SINGLE") ? 1 : 0;
+  if (g_mel_variant < 0) {
+    const char* e = getenv("TAC_MEL_VARIANT");                 // 0: pair kernel, 1: one frame per warp, 2: pair kernel + tcgen05 pass
+    g_mel_variant = e ? atoi(e) : (getenv("TAC_MEL_SINGLE") ? 1 : 0);
+    if (g_mel_variant < 0 || g_mel_variant > 2) g_mel_variant = 0;
+  }
   return g_mel_variant;
 }
 
@@ -904,7 +908,9 @@ int launch_stft(const StftParams& p, cudaStream_t stream) {
   if (p.n_fft == 2048 && p.onesided && (p.out_mode == OUT_MEL_FUSED || p.out_mode == OUT_MEL_FUSED_PEERS)) {
     // two frames per warp in packed fp32 pairs (stft_pair.cu); TAC_MEL_SINGLE=1 keeps the one-frame-per-warp kernel
     // below (A/B timing and the bit-equality test of the two)
-    if (mel_kernel_variant() == 0 && stft2048_pair_applies(p)) return launch_stft2048_pair(p, stream);
+    const int variant = mel_kernel_variant();
+    if (variant == 2 && stft2048_pair_applies(p)) return launch_stft2048_pair_tc(p, stream);
+    if (variant == 0 && stft2048_pair_applies(p)) return launch_stft2048_pair(p, stream);
   }
   if (p.n_fft == 2048 && p.onesided) {
     const bool whole = p.g0 == 0 && p.g1 == p.n_seq * p.frames;       // the tiled public kernel walks whole sequences
@@ -1007,7 +1013,7 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
 
 extern "C" int tac_mel_kernel_variant(int variant) {
   const int prev = tac::mel_kernel_variant();
-  if (variant >= 0) tac::g_mel_variant = variant ? 1 : 0;
+  if (variant >= 0) tac::g_mel_variant = variant <= 2 ? variant : 0;
   return prev;
 }
 

@@ -165,6 +165,7 @@ int launch_stft(const StftParams& p, cudaStream_t stream);
 // stft_pair.cu: the one-kernel mel path (OUT_MEL_FUSED / OUT_MEL_FUSED_PEERS, n_fft = 2048) with two frames per warp
 bool stft2048_pair_applies(const StftParams& p);    // hop <= 512 and even, whole sequences
 int launch_stft2048_pair(const StftParams& p, cudaStream_t stream);
+int launch_stft2048_pair_tc(const StftParams& p, cudaStream_t stream);   // stft_pair_tc.cu: second FFT pass on tcgen05
 // stft.cu: backward of stft + |.|^p for n_fft = 2048; gspec_fm: (frames of the launch, 1056) frame-major gradient of
 // |X|^p, frames_out: (frames of the launch, 2048) windowed frame gradients (p.power / p.power_mode as in the forward pass)
 int launch_stft2048_backward(const StftParams& p, const float* gspec_fm, float* frames_out, cudaStream_t stream);

@@ -367,7 +367,7 @@ def time_gathers(w, world, dev, steps, barrier):
     """(ms with one NCCL all_gather_into_tensor of the output per step on a side stream, ms with the kernel-side gather,
     error string or None): BASELINE config 4's optional all-gather, both ways."""
     import torch.distributed as dist
-    from torchaudio_contrib_b200.distributed import PeerGatheredOutput
+    from torchaudio_contrib_b200.distributed import MulticastGatheredOutput, PeerGatheredOutput
     full = torch.empty((world * w.batch, w.channels, N_MELS, w.frames), dtype=torch.float32, device=dev)
     comm = torch.cuda.Stream(device=dev)
     bufs = [torch.empty((w.batch, w.channels, N_MELS, w.frames), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -395,11 +395,14 @@ def time_gathers(w, world, dev, steps, barrier):
     del full, bufs
 
     # the same gather done by the mel kernel itself: every frame's bands stored into all ranks' full outputs over
-    # NVLink from the epilogue (tac_melspec_banded_peers_f32), one flag barrier per step instead of the collective
-    peer_ms, peer_err = 0.0, None
-    if w.prepared.fused:
+    # NVLink from the epilogue, one flag barrier per step instead of the collective -- with one unicast store per peer
+    # (tac_melspec_banded_peers_f32) and with ONE store to an NVSwitch multicast address (tac_melspec_banded_mc_f32)
+    def kernel_gather_leg(cls):
+        leg_ms, leg_err = 0.0, None
+        if not w.prepared.fused:
+            return leg_ms, leg_err
         try:
-            fulls = [PeerGatheredOutput((world * w.batch,) + w.prepared.out_shape[1:], dev) for _ in range(2)]
+            fulls = [cls((world * w.batch,) + w.prepared.out_shape[1:], dev) for _ in range(2)]
             with torch.no_grad():
                 def peer_step(i):
                     w.prepared.gather_into(w.inputs[i % w.n_sets], fulls[i % 2])
@@ -414,7 +417,7 @@ def time_gathers(w, world, dev, steps, barrier):
                     peer_step(i)
                 g1.record()
                 barrier()
-            peer_ms = g0.elapsed_time(g1)
+            leg_ms = g0.elapsed_time(g1)
             for f in fulls:
                 f.check()
             # the gathered tensor equals an NCCL all-gather of what the plain call returns on every rank
@@ -424,13 +427,17 @@ def time_gathers(w, world, dev, steps, barrier):
             want = torch.empty_like(fulls[0].tensor)
             dist.all_gather_into_tensor(want, local)
             if not torch.equal(want, fulls[(steps - 1) % 2].tensor):
-                peer_err = "gathered tensor differs from the all-gather of the single-GPU calls"
+                leg_err = "gathered tensor differs from the all-gather of the single-GPU calls"
             del want, local
             for f in fulls:
                 f.close()
         except Exception as exc:                                # report, do not lose the whole bench line
-            peer_err = "%s: %s" % (type(exc).__name__, exc)
-    return gather_ms, peer_ms, peer_err
+            leg_err = "%s: %s" % (type(exc).__name__, exc)
+        return leg_ms, leg_err
+
+    peer_ms, peer_err = kernel_gather_leg(PeerGatheredOutput)
+    mc_ms, mc_err = kernel_gather_leg(MulticastGatheredOutput)
+    return gather_ms, peer_ms, peer_err, mc_ms, mc_err
 
 
 def bare_copy_bound(dev, host_in, host_out, steps, barrier):
@@ -466,11 +473,13 @@ def sub_record(tac, lib, name, world, rank, dev, steps, barrier, hbm_peak, gathe
     w = MelWorkload(tac, name, world, rank, dev, n_sets=2 if name != "cfg2" else None)
     ms = w.timed(steps, 3, barrier)
     vals = [ms, 0.0, 0.0]
-    peer_err = None
+    peer_err = mc_err = None
     if gathers and world > 1:
-        g_ms, p_ms, peer_err = time_gathers(w, world, dev, steps, barrier)
-        vals = [ms, g_ms, p_ms]
-    ms, g_ms, p_ms = max_over_ranks(vals, world, dev)
+        g_ms, p_ms, peer_err, m_ms, mc_err = time_gathers(w, world, dev, steps, barrier)
+        vals = [ms, g_ms, p_ms, m_ms]
+    else:
+        vals = vals + [0.0]
+    ms, g_ms, p_ms, m_ms = max_over_ranks(vals, world, dev)
     per_step = ms / steps
     rec = {"workload": w.describe(), "scaling": w.scaling, "steps": steps, "ms_per_step": per_step,
            "value": world * w.frames_per_step / (per_step * 1e-3), "unit": "frames/s",
@@ -480,6 +489,8 @@ def sub_record(tac, lib, name, world, rank, dev, steps, barrier, hbm_peak, gathe
         rec["with_allgather"] = {"ms_per_step": g_ms / steps, "value": world * w.frames_per_step / (g_ms / steps * 1e-3)}
         rec["with_peer_gather"] = ({"error": peer_err} if peer_err is not None else
                                    {"ms_per_step": p_ms / steps, "value": world * w.frames_per_step / (p_ms / steps * 1e-3)})
+        rec["with_multicast_gather"] = ({"error": mc_err} if mc_err is not None else
+                                        {"ms_per_step": m_ms / steps, "value": world * w.frames_per_step / (m_ms / steps * 1e-3)})
     del w
     torch.cuda.empty_cache()
     return rec
@@ -616,13 +627,13 @@ def run_ours(args, rank, world, local):
         del host_in, host_out
 
     # optional output all-gather (BASELINE config 4), NCCL and kernel-side
-    gather_ms = peer_ms = 0.0
-    peer_err = None
+    gather_ms = peer_ms = mc_ms = 0.0
+    peer_err = mc_err = None
     if world > 1:
-        gather_ms, peer_ms, peer_err = time_gathers(w, world, dev, args.steps, barrier)
+        gather_ms, peer_ms, peer_err, mc_ms, mc_err = time_gathers(w, world, dev, args.steps, barrier)
 
-    ms, e2e_ms, e2e_median_ms, gather_ms, peer_ms, bound_ms = max_over_ranks(
-        [ms, e2e_s * 1e3, e2e_median_s * 1e3, gather_ms, peer_ms, bound_ms], world, dev)
+    ms, e2e_ms, e2e_median_ms, gather_ms, peer_ms, bound_ms, mc_ms = max_over_ranks(
+        [ms, e2e_s * 1e3, e2e_median_s * 1e3, gather_ms, peer_ms, bound_ms, mc_ms], world, dev)
 
     ref_gpu = None
     if rank == 0 and world == 1:
@@ -704,6 +715,16 @@ def run_ours(args, rank, world, local):
                     "bytes_sent_per_rank_per_step": (world - 1) * out_bytes}
             elif peer_err is not None:
                 line["with_peer_gather"] = {"error": peer_err}
+            if mc_ms > 0.0 and mc_err is None:
+                line["with_multicast_gather"] = {
+                    "value": world * args.steps * frames_per_step / (mc_ms * 1e-3), "unit": "frames/s",
+                    "ms_per_step": mc_ms / args.steps,
+                    "what": "tac_melspec_banded_mc_f32: the kernel's epilogue stores every frame ONCE to an NVSwitch multicast "
+                            "address (every rank's (world*batch,C,frames,128) buffer is a replica) + one flag barrier kernel per "
+                            "step; no collective",
+                    "bytes_sent_per_rank_per_step": out_bytes}
+            elif mc_err is not None:
+                line["with_multicast_gather"] = {"error": mc_err}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

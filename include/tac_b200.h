@@ -170,6 +170,34 @@ int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64_t n_sample
                                  float* const* peer_out, int n_peers, int64_t seq_offset,
                                  int frame_major, void* stream);
 
+/* ---- N3 with NVSwitch multicast (csrc/multicast.cu) ------------------------------------------
+ * The peer stores above cost one NVLink store per peer (7x egress on an 8-GPU box).  With a CUDA
+ * multicast object every rank's full output buffer is one replica, and ONE store to the multicast
+ * address is delivered to all of them by the switch.  Set-up (all ranks, in this order):
+ *   rank 0: tac_mc_create -> obj + a POSIX file descriptor; the host passes the descriptor to the
+ *           other processes (unix socket, SCM_RIGHTS); they call tac_mc_import;
+ *   all:    tac_mc_add_device; host barrier (every device added); tac_mc_bind -> local_ptr (this
+ *           rank's replica: TAC_PEER_HEADER_BYTES of flags, then the payload) and mc_ptr (same
+ *           layout, multicast address: stores only);
+ *   per step: tac_melspec_banded_mc_f32 (mc_out = mc_ptr + TAC_PEER_HEADER_BYTES), then
+ *           tac_mc_barrier (stream-ordered; epoch increasing) -- afterwards local_ptr holds every
+ *           rank's frames.  tac_mc_timed_out reads the give-up flag of a barrier (synchronises).
+ * tac_mc_supported: 1 when the current device can take part (NVSwitch + driver support). */
+int tac_mc_supported(int* supported);
+int tac_mc_create(int64_t bytes, int n_devices, void** obj, int* fd_out);
+int tac_mc_import(int fd, int64_t bytes, int n_devices, void** obj);
+int tac_mc_add_device(void* obj);
+int tac_mc_bind(void* obj, void** local_ptr, void** mc_ptr);
+int tac_mc_barrier(void* obj, int rank, uint32_t epoch, double timeout_s, void* stream);
+int tac_mc_timed_out(void* obj, int* timed_out);
+int tac_mc_free(void* obj);
+int tac_melspec_banded_mc_f32(const float* x, int64_t n_seq, int64_t n_samples,
+                              int64_t seq_stride, const float* window, int n_fft, int hop,
+                              int center, int pad_mode, int normalized, float power,
+                              const void* plan_dev, int64_t band_handle, int n_bands,
+                              int to_db, float ref, float amin,
+                              float* mc_out, int64_t seq_offset, int frame_major, void* stream);
+
 /* ---- N4 / H7: backward passes (the reference is differentiable w.r.t. the waveform) ---------
  * tac_stft_backward_f32: adjoint of tac_stft_f32.  grad_out: (n_seq, bins, frames, 2) contiguous;
  * grad_x: (n_seq, n_samples) contiguous, overwritten.

@@ -16,23 +16,27 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, layout, to_db, q):
+def _worker(rank, world, port, layout, to_db, q, kind="peer"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import torchaudio_contrib_b200 as tac
-        from torchaudio_contrib_b200.distributed import PeerGatheredOutput, shard_batch
+        from torchaudio_contrib_b200.distributed import MulticastGatheredOutput, PeerGatheredOutput, shard_batch, multicast_supported
         from oracle import ref_chain
         torch.cuda.set_device(rank)
+        if kind == "multicast" and not multicast_supported(rank):
+            q.put((rank, "unsupported"))
+            return
         dev = torch.device("cuda", rank)
         torch.manual_seed(7)
         x_all = torch.randn(2 * world, 2, 24000)                     # the whole batch, known to every rank
         fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
         mine = shard_batch(x_all, rank, world).contiguous().to(dev)
         prep = tac.PreparedMelspectrogram(mine.shape, dev, fb, 2048, 512, to_db=to_db, layout=layout)
-        buf = PeerGatheredOutput((x_all.shape[0],) + prep.out_shape[1:], dev)
+        cls = MulticastGatheredOutput if kind == "multicast" else PeerGatheredOutput
+        buf = cls((x_all.shape[0],) + prep.out_shape[1:], dev)
         ok = True
         for rounds in range(3):                                      # epochs advance, buffers are re-used
             buf.tensor.fill_(float("nan"))
@@ -78,6 +82,65 @@ def test_peer_gather_two_gpus(layout, to_db):
     assert not alive, "peer-gather worker hung"
     results = sorted(q.get(timeout=5) for _ in range(2))
     assert results == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("layout,to_db", [("reference", False), ("contiguous", True)])
+def test_multicast_gather_two_gpus(layout, to_db):
+    """The same gather with ONE store per value to a CUDA multicast address (csrc/multicast.cu): both ranks' replicas hold
+    the whole batch, equal to the oracle and bit-identical to the single-GPU call."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs of one box")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, layout, to_db, q, "multicast")) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not alive, "multicast-gather worker hung"
+    results = sorted(q.get(timeout=5) for _ in range(2))
+    if results == [(0, "unsupported"), (1, "unsupported")]:
+        pytest.skip("devices cannot join a multicast object")
+    assert results == [(0, True), (1, True)]
+
+
+def test_multicast_gather_single_rank():
+    """world_size 1: a multicast object with one device -- allocation, binding, the multimem stores of the mel kernel and
+    the flag barrier run on a single-GPU box; result identical to the plain call."""
+    import torch.distributed as dist
+    import torchaudio_contrib_b200 as tac
+    from torchaudio_contrib_b200.distributed import MulticastGatheredOutput, multicast_supported
+    if not multicast_supported(0):
+        pytest.skip("device cannot join a multicast object")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        torch.manual_seed(13)
+        dev = torch.device("cuda", 0)
+        x = torch.randn(3, 2, 20000, device=dev)
+        fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
+        for layout in ("reference", "contiguous"):
+            prep = tac.PreparedMelspectrogram(x.shape, dev, fb, 2048, 512, to_db=True, layout=layout)
+            try:
+                buf = MulticastGatheredOutput(prep.out_shape, dev)
+            except RuntimeError as exc:                              # a one-device object is refused by some drivers
+                pytest.skip("single-device multicast object not available: %s" % exc)
+            for _ in range(2):
+                buf.tensor.fill_(float("nan"))
+                got = prep.gather_into(x, buf)
+                buf.wait()
+                want = prep(x, prep.empty_output())
+                assert got.shape == want.shape and got.stride() == want.stride()
+                assert torch.equal(got, want)
+            buf.close()
+    finally:
+        dist.destroy_process_group()
 
 
 def test_peer_gather_single_rank():

@@ -54,6 +54,15 @@ SIGNATURES = {
     "tac_peer_free": (_int, [_ptr]),
     "tac_peer_barrier": (_int, [_ptr, _int, _int, _c.c_uint32, _c.c_double, _ptr]),
     "tac_peer_timed_out": (_int, [_ptr, _c.POINTER(_int)]),
+    "tac_mc_supported": (_int, [_c.POINTER(_int)]),
+    "tac_mc_create": (_int, [_i64, _int, _c.POINTER(_ptr), _c.POINTER(_int)]),
+    "tac_mc_import": (_int, [_int, _i64, _int, _c.POINTER(_ptr)]),
+    "tac_mc_add_device": (_int, [_ptr]),
+    "tac_mc_bind": (_int, [_ptr, _c.POINTER(_ptr), _c.POINTER(_ptr)]),
+    "tac_mc_barrier": (_int, [_ptr, _int, _c.c_uint32, _c.c_double, _ptr]),
+    "tac_mc_timed_out": (_int, [_ptr, _c.POINTER(_int)]),
+    "tac_mc_free": (_int, [_ptr]),
+    "tac_melspec_banded_mc_f32": (_int, _STFT_ARGS + [_f32, _ptr, _i64, _int, _int, _f32, _f32, _ptr, _i64, _int, _ptr]),
     "tac_stft_backward_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),
     "tac_stft_backward_f32": (_int, [_ptr, _i64, _i64, _ptr, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _i64, _ptr]),
     "tac_spectrogram_backward_f32": (_int, _STFT_ARGS + [_int, _f32, _ptr, _ptr, _ptr, _i64, _ptr]),

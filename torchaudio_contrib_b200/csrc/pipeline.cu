@@ -73,7 +73,7 @@ static bool fused_enabled() {
 // (stft.cu, OUT_MEL_FUSED).  n_fft = 2048 and a plan that carries a band plan (tac_fbplan_band_handle != 0).
 static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, int64_t band_handle, int n_bands, int to_db,
                               float ref, float amin, float* out, int frame_major, cudaStream_t stream,
-                              float* const* peer_out = nullptr, int n_peers = 0, int64_t peer_seq0 = 0) {
+                              float* const* peer_out = nullptr, int n_peers = 0, int64_t peer_seq0 = 0, int multicast = 0) {
   TAC_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, TAC_ERR_INVALID, "melspec_banded: plan must be 16-byte aligned");
   if (sp.n_fft != 2048) {
     // n_fft = 256 / 512 / 1024 / 4096: the warp kernels with the range-plan epilogue (stft_multi.cu); handle = offset | bytes << 32
@@ -135,6 +135,7 @@ static int run_melspec_banded(StftParams sp, float power, const void* plan_dev, 
     sp.out_mode = OUT_MEL_FUSED_PEERS;
     sp.out = nullptr;
     sp.n_peers = n_peers;
+    sp.peer_multicast = multicast;
     sp.peer_seq0 = peer_seq0;
     for (int q = 0; q < n_peers; ++q) sp.peer_out[q] = peer_out[q];
   }
@@ -160,6 +161,22 @@ extern "C" int tac_melspec_banded_peers_f32(const float* x, int64_t n_seq, int64
     TAC_REQUIRE(peer_out[q] || sp.g1 == 0, TAC_ERR_INVALID, "melspec_banded_peers: null output pointer for rank %d", q);
   return run_melspec_banded(sp, power, plan_dev, band_handle, n_bands, to_db, ref, amin, nullptr, frame_major, as_stream(stream),
                             peer_out, n_peers, seq_offset);
+}
+
+extern "C" int tac_melspec_banded_mc_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,
+                                         int n_fft, int hop, int center, int pad_mode, int normalized, float power,
+                                         const void* plan_dev, int64_t band_handle, int n_bands, int to_db, float ref, float amin,
+                                         float* mc_out, int64_t seq_offset, int frame_major, void* stream) {
+  using namespace tac;
+  StftParams sp;
+  const int rc = fill_stft_params(sp, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
+  if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(plan_dev && n_bands > 0, TAC_ERR_INVALID, "melspec_banded_mc: missing filterbank plan");
+  TAC_REQUIRE(mc_out || sp.g1 == 0, TAC_ERR_INVALID, "melspec_banded_mc: null multicast output pointer");
+  TAC_REQUIRE(seq_offset >= 0, TAC_ERR_INVALID, "melspec_banded_mc: negative sequence offset");
+  float* const one[1] = {mc_out};
+  return run_melspec_banded(sp, power, plan_dev, band_handle, n_bands, to_db, ref, amin, nullptr, frame_major, as_stream(stream),
+                            one, 1, seq_offset, 1);
 }
 
 extern "C" int tac_melspec_banded_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* window,

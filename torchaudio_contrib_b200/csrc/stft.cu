@@ -217,8 +217,12 @@ __device__ __forceinline__ void band_contract(const StftParams& p, float* stash,
   auto store = [&](int m, float r) {
     if constexpr (PEERS) {
       const int64_t o = dst_off + (int64_t)m * p.out_band_stride;
+      if (p.peer_multicast) {
+        multimem_st_f32(p.peer_out[0] + o, r);
+      } else {
 #pragma unroll 1
-      for (int q = 0; q < p.n_peers; ++q) __stcs(p.peer_out[q] + o, r);
+        for (int q = 0; q < p.n_peers; ++q) __stcs(p.peer_out[q] + o, r);
+      }
     } else {
       __stcs(dst + (int64_t)m * p.out_band_stride, r);
     }
@@ -1005,6 +1009,7 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   p.out_seq_stride = p.out_t_stride = p.out_band_stride = 0;
   for (int q = 0; q < kMaxPeers; ++q) p.peer_out[q] = nullptr;
   p.n_peers = 0;
+  p.peer_multicast = 0;
   p.peer_seq0 = 0;
   return TAC_OK;
 }

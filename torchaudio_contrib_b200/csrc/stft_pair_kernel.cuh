@@ -259,8 +259,12 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
   auto store = [&](int64_t off, int m, float r) {
     const int64_t o = off + (int64_t)m * p.out_band_stride;
     if constexpr (PEERS) {
+      if (p.peer_multicast) {
+        multimem_st_f32(p.peer_out[0] + o, r);
+      } else {
 #pragma unroll 1
-      for (int q = 0; q < p.n_peers; ++q) __stcs(p.peer_out[q] + o, r);
+        for (int q = 0; q < p.n_peers; ++q) __stcs(p.peer_out[q] + o, r);
+      }
     } else {
       __stcs(p.out + o, r);
     }

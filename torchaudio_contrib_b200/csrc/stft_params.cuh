@@ -42,6 +42,7 @@ struct StftParams {
   // others); `out` is unused and the strides above address the full (all ranks) tensor from peer_seq0 on
   float* peer_out[kMaxPeers];
   int n_peers;
+  int peer_multicast;      // peer_out[0] is a MULTICAST address (multicast.cu): one multimem store reaches every replica
   int64_t peer_seq0;       // first sequence of this rank inside the full output
 };
 

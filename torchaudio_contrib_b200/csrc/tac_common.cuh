@@ -230,6 +230,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "memory");
 }
 
+// store to a multicast address (multicast.cu): the NVSwitch delivers it to every GPU's replica
+__device__ __forceinline__ void multimem_st_f32(float* p, float v) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // streaming global accesses that should not pollute L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 v;

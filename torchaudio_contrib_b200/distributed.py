@@ -9,15 +9,23 @@ collective is the optional `all_gather_output`, NCCL over NVLink on GPUs (gloo i
 full output buffer is mapped into every other rank (CUDA IPC), `PreparedMelspectrogram.gather_into`
 stores each frame's bands into all of them over NVLink while it computes, and one flag barrier
 (`tac_peer_barrier`) replaces the collective.  torch.distributed only carries the 64-byte handles.
+
+`MulticastGatheredOutput` is the same with ONE store per value: the ranks' buffers are the replicas
+of a CUDA multicast object and the kernel stores to the multicast address; the NVSwitch delivers
+the store to every GPU (1x NVLink egress instead of world-1 x).
 """
 import ctypes
+import os
+import socket
+import time
 
 import torch
 import torch.distributed as dist
 
 from . import _cabi
 
-__all__ = ["shard_range", "shard_batch", "all_gather_output", "PeerGatheredOutput"]
+__all__ = ["shard_range", "shard_batch", "all_gather_output", "PeerGatheredOutput", "MulticastGatheredOutput",
+           "multicast_supported"]
 
 
 def shard_range(n_items, rank, world):
@@ -202,3 +210,163 @@ class PeerGatheredOutput(object):
         dist.barrier(group=self.group)
         self.tensor = None
         self._own = None
+
+
+def multicast_supported(device=None):
+    """True when the device can join a CUDA multicast object (NVSwitch box, driver support)."""
+    flag = ctypes.c_int(0)
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _cabi.check(_cabi.lib().tac_mc_supported(ctypes.byref(flag)))
+    return bool(flag.value)
+
+
+def _share_fd(fd, rank, world, group):
+    """Rank 0 hands a file descriptor to every other rank (processes of one box): unix socket + SCM_RIGHTS; the socket
+    path travels through torch.distributed.  Returns this rank's descriptor (rank 0: the one it passed in)."""
+    if world == 1:
+        return fd
+    path = [None]
+    server = None
+    if rank == 0:
+        path[0] = "/tmp/tac_mc_%d_%d.sock" % (os.getpid(), int(time.time() * 1e6) & 0xffffff)
+        if os.path.exists(path[0]):
+            os.unlink(path[0])
+        server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        server.bind(path[0])
+        server.listen(world)
+    dist.broadcast_object_list(path, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    try:
+        if rank == 0:
+            server.settimeout(60.0)
+            for _ in range(world - 1):
+                conn, _addr = server.accept()
+                with conn:
+                    socket.send_fds(conn, [b"m"], [fd])
+            return fd
+        client = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        with client:
+            client.settimeout(60.0)
+            client.connect(path[0])
+            _msg, fds, _flags, _addr = socket.recv_fds(client, 16, 1)
+        if not fds:
+            raise RuntimeError("no file descriptor received from rank 0")
+        return fds[0]
+    finally:
+        if server is not None:
+            server.close()
+            try:
+                os.unlink(path[0])
+            except OSError:
+                pass
+
+
+class MulticastGatheredOutput(object):
+    """As `PeerGatheredOutput`, on NVSwitch multicast memory (csrc/multicast.cu): `tensor` is this rank's replica of the
+    full `(n_items, ...)` output, `gather_into` stores every value ONCE to the multicast address and the switch delivers
+    it to all ranks.  Collective constructor / `close()`; `barrier()`, `wait()`, `check()` as above.  Raises
+    NotImplementedError where the devices cannot join a multicast object (no NVSwitch / driver support)."""
+
+    def __init__(self, shape, device, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("MulticastGatheredOutput needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.shape = tuple(int(d) for d in shape)
+        n = 1
+        for d in self.shape:
+            n *= d
+        lib = _cabi.lib()
+        self._obj = None
+        oks = [None] * self.world
+        dist.all_gather_object(oks, multicast_supported(self.device), group=group)
+        if not all(oks):
+            raise NotImplementedError("MulticastGatheredOutput: multicast is not supported on rank(s) %s"
+                                      % [r for r, ok in enumerate(oks) if not ok])
+        failure, fd, obj = None, -1, ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            try:
+                if self.rank == 0:
+                    cfd = ctypes.c_int(-1)
+                    _cabi.check(lib.tac_mc_create(4 * n, self.world, ctypes.byref(obj), ctypes.byref(cfd)))
+                    fd = cfd.value
+            except Exception as exc:
+                failure = "rank 0: %s" % exc
+            state = [failure]
+            dist.broadcast_object_list(state, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            if state[0]:
+                raise RuntimeError("MulticastGatheredOutput: creating the multicast object failed (%s)" % state[0])
+            try:
+                got = _share_fd(fd, self.rank, self.world, group)
+                if self.rank != 0:
+                    _cabi.check(lib.tac_mc_import(int(got), 4 * n, self.world, ctypes.byref(obj)))
+                os.close(got)
+                self._obj = obj
+                _cabi.check(lib.tac_mc_add_device(obj))
+            except Exception as exc:
+                failure = "rank %d: %s" % (self.rank, exc)
+            failure = self._agree(failure)                       # also the barrier: every device has been added
+            local, mc = ctypes.c_void_p(), ctypes.c_void_p()
+            if not failure:
+                try:
+                    _cabi.check(lib.tac_mc_bind(obj, ctypes.byref(local), ctypes.byref(mc)))
+                except Exception as exc:
+                    failure = "rank %d: %s" % (self.rank, exc)
+            failure = self._agree(failure)                       # every replica is bound before anyone stores
+            if failure:
+                self._release()
+                raise RuntimeError("MulticastGatheredOutput: set-up failed (%s)" % failure)
+        self._local, self._mc = local.value, mc.value
+        self.mc_payload = self._mc + 128                           # TAC_PEER_HEADER_BYTES
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self._local + 128, False),
+                                         "version": 2, "strides": None}
+        self.tensor = torch.as_tensor(self, device=self.device)
+        self.epoch = 0
+
+    def _agree(self, failure):
+        failures = [None] * self.world
+        dist.all_gather_object(failures, failure, group=self.group)
+        failures = [f for f in failures if f]
+        return "; ".join(failures) if failures else None
+
+    def _release(self):
+        obj, self._obj = self._obj, None
+        if obj is not None and obj.value:
+            with torch.cuda.device(self.device):
+                _cabi.lib().tac_mc_free(obj)
+
+    def barrier(self, timeout_s=20.0):
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().tac_mc_barrier(self._obj, self.rank, self.epoch, float(timeout_s), _cabi.stream_ptr(self.device)))
+
+    def check(self):
+        flag = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().tac_mc_timed_out(self._obj, ctypes.byref(flag)))
+        if flag.value:
+            raise RuntimeError("MulticastGatheredOutput: a barrier timed out waiting for a peer rank")
+
+    def wait(self, timeout_s=20.0):
+        self.barrier(timeout_s)
+        self.check()
+        return self.tensor
+
+    def close(self):
+        """Collective: every rank stops using the buffer, then releases its replica and its handle of the object."""
+        if self._obj is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.tensor = None
+        self._release()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_obj", None) is not None:
+                self.tensor = None
+                self._release()
+        except Exception:                                      # interpreter shutdown
+            pass

@@ -829,7 +829,7 @@ class PreparedMelspectrogram(object):
 
     def gather_into(self, x, gathered, item_offset=None):
         """Batch-sharded call (BASELINE config 4): compute this rank's `x` and store the result into the full
-        output of EVERY rank (`gathered`: a `distributed.PeerGatheredOutput` of shape
+        output of EVERY rank (`gathered`: a `distributed.PeerGatheredOutput` or `MulticastGatheredOutput` of shape
         `(total_items,) + out_shape[1:]`) from the kernel's epilogue, over NVLink -- the all-gather of SURVEY 8(e)
         without a collective.  `item_offset`: this rank's first batch item in the full output (default:
         `shard_range` of equal shards).  Follow with `gathered.barrier()`.  One-kernel path only."""
@@ -849,6 +849,13 @@ class PreparedMelspectrogram(object):
             raise RuntimeError("gather_into: items [%d, %d) outside the gathered batch of %d"
                                % (item_offset, item_offset + self.shape[0], full[0]))
         seq_per_item = self.n_seq // max(self.shape[0], 1)
+        if hasattr(gathered, "mc_payload"):                    # distributed.MulticastGatheredOutput: one store per value
+            with torch.cuda.device(self.device):
+                _cabi.check(_cabi.lib().tac_melspec_banded_mc_f32(
+                    _cabi.ptr(x), *self._head, ctypes.c_void_p(gathered.mc_payload),
+                    int(item_offset) * seq_per_item, int(self.frame_major),
+                    ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            return gathered.tensor.transpose(-2, -1) if self.frame_major else gathered.tensor
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().tac_melspec_banded_peers_f32(
                 _cabi.ptr(x), *self._head, ctypes.cast(gathered.payload_array, ctypes.c_void_p), gathered.world,

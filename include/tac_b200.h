@@ -250,6 +250,13 @@ int tac_complex_norm_backward_f32(const float* z, const float* grad_out, int64_t
 int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantize,
                              const float* thresholds_dev, int n_thresholds, int idx_min,
                              float x_limit, int64_t* out, void* stream);
+/* The tables, on the host (no torch needed): thresholds (capacity floats; NULL only queries the
+ * count), idx_min, x_limit for the encoder and decoded[n_quantize] for the decoder.  n_quantize =
+ * 256 returns the levels SHIPPED with the library -- found with the reference's own fp32 torch CPU
+ * chain, bit-exact with it for every float (*exact = 1); other values are bisected here with the
+ * host's libm log1pf / expf (*exact = 0: equal to the reference wherever libm and torch agree). */
+int tac_mulaw_tables_host(int n_quantize, float* thresholds, int capacity, int* n_thresholds,
+                          int* idx_min, float* x_limit, float* decoded, int* exact);
 
 /* ---- a8: mu_law_decoding (functional.py:338-354) ----------------------------------------
  * lut_dev[i] = decoded value of code i for 0 <= i < n_quantize; other codes are evaluated

@@ -359,3 +359,33 @@ def test_gradient_dispatch_helpers(tac):
     F._no_param_grad(torch.zeros(3), "window")                                             # constants without grad are fine
     with pytest.raises(RuntimeError, match="the window is a constant"):
         F._no_param_grad(x, "window")
+
+
+def test_shipped_mulaw_tables_equal_fresh_bisection():
+    """tac_mulaw_tables_host(256): the decision levels / decoded values compiled into the library (csrc/mulaw_table256.inc,
+    what a non-Python caller of the C ABI gets) are the ones a fresh bisection with the reference's fp32 torch CPU chain
+    finds on this host; other n_quantize come from the host libm and say so (*exact = 0)."""
+    import ctypes
+    from torchaudio_contrib_b200 import _cabi, _mulaw_tables
+    lib = _cabi.lib()
+
+    def tables(nq):
+        n, imin, xl, ex = ctypes.c_int(), ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
+        _cabi.check(lib.tac_mulaw_tables_host(nq, None, 0, ctypes.byref(n), ctypes.byref(imin), ctypes.byref(xl), None, ctypes.byref(ex)))
+        thr, dec = torch.empty(n.value), torch.empty(nq)
+        _cabi.check(lib.tac_mulaw_tables_host(nq, thr.data_ptr(), n.value, ctypes.byref(n), ctypes.byref(imin), ctypes.byref(xl),
+                                              dec.data_ptr(), ctypes.byref(ex)))
+        return thr, imin.value, xl.value, dec, ex.value
+
+    thr, imin, xl, dec, exact = tables(256)
+    want_thr, want_imin, want_xl = _mulaw_tables.encode_tables(256)
+    assert exact == 1 and imin == want_imin and xl == want_xl
+    assert torch.equal(thr, want_thr) and torch.equal(dec, _mulaw_tables.decode_table(256))
+    thr, imin, xl, dec, exact = tables(64)
+    want_thr, want_imin, want_xl = _mulaw_tables.encode_tables(64)
+    assert exact == 0 and imin == want_imin and xl == want_xl and thr.numel() == want_thr.numel()
+    close = (thr[1:].view(torch.int32) - want_thr[1:].view(torch.int32)).abs().max().item()
+    assert close <= 64                                         # libm vs torch log1p: the levels agree to a few ulp
+    n = ctypes.c_int()
+    with pytest.raises(_cabi.TacError):
+        _cabi.check(lib.tac_mulaw_tables_host(256, thr.data_ptr(), 10, ctypes.byref(n), ctypes.byref(n), ctypes.byref(ctypes.c_float()), None, None))

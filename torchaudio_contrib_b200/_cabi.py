@@ -72,6 +72,7 @@ SIGNATURES = {
     "tac_amplitude_to_db_backward_f32": (_int, [_ptr, _ptr, _i64, _f32, _ptr, _ptr]),
     "tac_complex_norm_backward_f32": (_int, [_ptr, _ptr, _i64, _f32, _ptr, _ptr]),
     "tac_mulaw_encode_f32_i64": (_int, [_ptr, _i64, _int, _ptr, _int, _int, _f32, _ptr, _ptr]),
+    "tac_mulaw_tables_host": (_int, [_int, _ptr, _int, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_f32), _ptr, _c.POINTER(_int)]),
     "tac_mulaw_decode_i64_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
     "tac_mulaw_decode_f32_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
     "tac_pipeline_create": (_int, [_ptr, _ptr, _ptr, _c.POINTER(_ptr)]),

@@ -14,13 +14,41 @@
 //  decode  Codes 0..n_quantize-1 index a lookup table of the reference's decoded values; anything
 //          else goes through the closed form.
 //
-// The tables are produced by the host side of the package from the reference formula
-// (torchaudio_contrib_b200/_mulaw_tables.py) and passed in as device pointers.
+// The tables are passed in as device pointers.  tac_mulaw_tables_host hands them out on the host: for n_quantize = 256
+// (the reference's default) the levels found with the reference's own fp32 torch CPU chain are SHIPPED in the library
+// (mulaw_table256.inc, scripts/gen_mulaw_table.py), so any caller of the C ABI is bit-exact without torch; other
+// n_quantize are bisected here with the host libm (the Python package passes its torch-built table instead).
+#include <math.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "tac_common.cuh"
 
 namespace tac {
+
+#include "mulaw_table256.inc"
+
+// ---- host-side decision levels (any n_quantize): the Python package's bisection, with libm ----------------------
+static inline float key_to_float(int64_t key) {          // monotone key in [0, 2^32) -> the float it denotes
+  const uint32_t bits = key >= ((int64_t)1 << 31) ? (uint32_t)(key - ((int64_t)1 << 31)) : (uint32_t)(((int64_t)1 << 32) - 1 - key);
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+static inline int64_t float_to_key(float f) {
+  uint32_t bits;
+  memcpy(&bits, &f, 4);
+  return bits >= 0x80000000u ? ((int64_t)1 << 32) - 1 - (int64_t)bits : (int64_t)bits + ((int64_t)1 << 31);
+}
+static inline int64_t quantise_host(float x, float mu) {   // functional.py:331-334 in fp32
+  const float a = fabsf(x);
+  const float sgn = x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f);
+  const float comp = sgn * log1pf(mu * a) / log1pf(mu);
+  const float v = (comp + 1.0f) / 2.0f * mu + 0.5f;
+  if (!(fabsf(v) < 9.0e18f)) return INT64_MIN;              // what the float -> int64 conversion yields for inf / NaN
+  return (int64_t)v;
+}
 
 constexpr int kMuLawThreads = 256;
 constexpr int kMuLawSmemTableMax = 12288;   // floats (48 KB) -- n_quantize = 256 needs 4081
@@ -138,6 +166,66 @@ static int streaming_grid(int64_t n_vec, int ctas_per_sm = 8) {
 }
 
 }  // namespace tac
+
+extern "C" int tac_mulaw_tables_host(int n_quantize, float* thresholds, int capacity, int* n_thresholds, int* idx_min,
+                                     float* x_limit, float* decoded, int* exact) {
+  using namespace tac;
+  TAC_REQUIRE(n_quantize >= 2 && n_quantize <= 65536, TAC_ERR_INVALID, "mulaw_tables: n_quantize %d outside [2, 65536]", n_quantize);
+  TAC_REQUIRE(n_thresholds && idx_min && x_limit, TAC_ERR_INVALID, "mulaw_tables: null output argument");
+  if (n_quantize == 256) {
+    *n_thresholds = kMuLaw256NThr;
+    *idx_min = kMuLaw256IdxMin;
+    memcpy(x_limit, &kMuLaw256XLimitBits, 4);
+    if (exact) *exact = 1;
+    if (thresholds) {
+      TAC_REQUIRE(capacity >= kMuLaw256NThr, TAC_ERR_WORKSPACE, "mulaw_tables: %d thresholds, room for %d", kMuLaw256NThr, capacity);
+      memcpy(thresholds, kMuLaw256Thr, sizeof(kMuLaw256Thr));
+    }
+    if (decoded) memcpy(decoded, kMuLaw256Dec, sizeof(kMuLaw256Dec));
+    return TAC_OK;
+  }
+  const float mu = (float)(n_quantize - 1);
+  // largest |x| whose code is still finite
+  int64_t lo = (int64_t)1 << 31, hi = float_to_key(3.4028234663852886e38f);
+  int64_t lim_key = hi;
+  if (quantise_host(key_to_float(hi), mu) == INT64_MIN) {
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) / 2;
+      if (quantise_host(key_to_float(mid), mu) != INT64_MIN) lo = mid; else hi = mid;
+    }
+    lim_key = lo;
+  }
+  const float lim = key_to_float(lim_key);
+  const int64_t neg_key = float_to_key(-lim);
+  const int64_t i_min = quantise_host(-lim, mu), i_max = quantise_host(lim, mu);
+  const int64_t count = i_max - i_min + 1;
+  TAC_REQUIRE(count >= 1 && count < ((int64_t)1 << 24), TAC_ERR_UNSUPPORTED, "mulaw_tables: %lld levels", (long long)count);
+  *n_thresholds = (int)count;
+  *idx_min = (int)i_min;
+  *x_limit = lim;
+  if (exact) *exact = 0;
+  if (thresholds) {
+    TAC_REQUIRE(capacity >= count, TAC_ERR_WORKSPACE, "mulaw_tables: %lld thresholds, room for %d", (long long)count, capacity);
+    thresholds[0] = -INFINITY;
+    for (int64_t t = i_min + 1; t <= i_max; ++t) {           // smallest float whose code is >= t
+      int64_t a = neg_key, b = lim_key;                       // code(a) < t <= code(b)
+      while (b - a > 1) {
+        const int64_t mid = (a + b) / 2;
+        if (quantise_host(key_to_float(mid), mu) >= t) b = mid; else a = mid;
+      }
+      thresholds[t - i_min] = key_to_float(b);
+    }
+  }
+  if (decoded) {
+    const float l1p = log1pf(mu);
+    for (int c = 0; c < n_quantize; ++c) {                    // functional.py:351-353
+      const float y = ((float)c / mu) * 2.0f - 1.0f;
+      const float sgn = y > 0.0f ? 1.0f : (y < 0.0f ? -1.0f : 0.0f);
+      decoded[c] = sgn * (expf(fabsf(y) * l1p) - 1.0f) / mu;
+    }
+  }
+  return TAC_OK;
+}
 
 extern "C" int tac_mulaw_encode_f32_i64(const float* x, int64_t n, int n_quantize, const float* thresholds_dev,
                                         int n_thresholds, int idx_min, float x_limit, int64_t* out, void* stream) {

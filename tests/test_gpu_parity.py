@@ -188,6 +188,31 @@ def test_stft_vs_f64(tac, shape):
     assert np.abs(got - want).max() < 5e-5
 
 
+@pytest.mark.parametrize("fft,hop", [(400, 160), (1200, 300), (441, 110), (6, 2), (1000, 250), (3000, 1000)])
+def test_stft_non_power_of_two(tac, oc, fft, hop):
+    """functional.py:99 hands any fft_length to torch.stft; sizes that are not a power of two (400 = 25 ms at 16 kHz, odd
+    sizes, tiny ones) run the direct-DFT kernel (csrc/stft.cu stft_dft_kernel).  Complex STFT (one- and two-sided),
+    spectrogram and the mel chain against the oracle; gradients of these sizes are refused, not approximated."""
+    torch.manual_seed(fft)
+    x = torch.randn(2, 2, 12000)
+    for kw in (dict(), dict(onesided=False, pad_mode="constant"), dict(center=False, normalized=True)):
+        got = tac.stft(dev(x), fft, hop, **kw).cpu()
+        want = oc.stft(x, fft, hop, **kw)
+        assert got.shape == want.shape, (fft, kw)
+        assert rel_err(got, want) < REL, (fft, kw, rel_err(got, want))
+    got = tac.Spectrogram(fft_length=fft, hop_length=hop, power=1.0).cuda()(dev(x)).cpu()
+    assert rel_err(got, oc.spectrogram(x, fft, hop, power=1.0)) < REL
+    if fft >= 400:
+        m = tac.Sequential(*tac.Melspectrogram(num_mels=40, sample_rate=16000, fft_length=fft, hop_length=hop),
+                           tac.AmplitudeToDb()).cuda()
+        got = m(dev(x)).cpu()
+        want = oc.melspectrogram(x, 40, 16000, to_db=True, fft_length=fft, hop_length=hop)
+        assert got.shape == want.shape and (got - want).abs().max().item() < 1e-3
+        xg = dev(x).requires_grad_(True)
+        with pytest.raises(NotImplementedError):
+            tac.Spectrogram(fft_length=fft, hop_length=hop).cuda()(xg).sum().backward()
+
+
 def test_stft_too_short_raises(tac):
     """tests/test_functional.py:31: reflect padding needs more samples than the pad."""
     with pytest.raises(RuntimeError):

@@ -306,8 +306,7 @@ extern "C" int tac_pipeline_create(const tac_pipeline_config* cfg, const float* 
   using namespace tac;
   TAC_REQUIRE(cfg && window_host && out, TAC_ERR_INVALID, "pipeline_create: null pointer");
   *out = nullptr;
-  TAC_REQUIRE(is_pow2(cfg->n_fft) && cfg->n_fft >= 32 && cfg->n_fft <= 8192, TAC_ERR_UNSUPPORTED,
-              "pipeline_create: n_fft=%d is not a power of two in [32, 8192]", cfg->n_fft);
+  TAC_REQUIRE(cfg->n_fft >= 2 && cfg->n_fft <= 8192, TAC_ERR_UNSUPPORTED, "pipeline_create: n_fft=%d outside [2, 8192]", cfg->n_fft);
   TAC_REQUIRE(cfg->n_bands == 0 || (fb_host && cfg->n_bins == cfg->n_fft / 2 + 1), TAC_ERR_INVALID,
               "pipeline_create: filterbank must have n_fft/2+1 = %d rows (got %d)", cfg->n_fft / 2 + 1, cfg->n_bins);
   tac_pipeline* p = static_cast<tac_pipeline*>(calloc(1, sizeof(tac_pipeline)));

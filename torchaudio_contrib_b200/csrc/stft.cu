@@ -13,6 +13,7 @@
 //      -> conflict free), each lane runs the second 32-point FFT, and the real-FFT untangling
 //      X[k] = E + W^k O pairs bin k with bin 1024-k by one shuffle exchange.  The slab is free
 //      again after the transpose read, so the next frame's bulk copy overlaps the second half.
+//  stft_dft_kernel       any n_fft in [2, 8192] that is not a power of two (400, 1200, 441 ...): direct DFT, correct-first
 //  stft_generic_kernel   any power-of-two n_fft in [32, 8192], any padding mode, one- or two-sided:
 //      one CTA per frame, radix-2 Stockham passes through shared memory.  Correct-first fallback.
 //
@@ -852,6 +853,100 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// any other n_fft (not a power of two; e.g. 400 = 25 ms at 16 kHz, 1200, 441): direct DFT, one CTA per group of F
+// frames.  The reference passes any fft_length to torch.stft (functional.py:99); this is the correct-first path for
+// the sizes the register / Stockham kernels do not cover: N (N/2 + 1) complex multiply-adds per frame from a
+// shared-memory table of exp(-2 pi i j / N) built in double precision, index (k n) mod N kept incrementally (exact),
+// F frames per pass so a table read serves F multiply-adds.  fp32 accumulation over N terms: ~sqrt(N) ulp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDftThreads = 256;
+static size_t dft_smem_bytes(int n_fft, int f) { return sizeof(float2) * (size_t)n_fft + sizeof(float) * (size_t)n_fft * (1 + f) + 16; }
+
+template <int F>
+__global__ void __launch_bounds__(kDftThreads) stft_dft_kernel(const StftParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int N = p.n_fft, nb = N / 2 + 1;
+  float2* tab = reinterpret_cast<float2*>(smem_raw);
+  float* win = reinterpret_cast<float*>(tab + N);
+  float* xw = win + N;                                   // [F][N]
+  const int tid = threadIdx.x;
+  for (int j = tid; j < N; j += kDftThreads) {
+    double sn, cs;
+    sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+    tab[j] = make_float2((float)cs, (float)sn);
+    win[j] = p.window[j] * p.scale;
+  }
+  __syncthreads();
+  const int64_t n_groups = (p.g1 - p.g0 + F - 1) / F;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int64_t gbase = p.g0 + grp * F;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const int64_t g = gbase + f;
+      if (g < p.g1) {
+        const int64_t seq = g / p.frames, t = g - seq * p.frames, start = t * p.hop - p.pad;
+        const float* row = p.x + seq * p.seq_stride;
+        for (int n = tid; n < N; n += kDftThreads) xw[f * N + n] = fetch_padded(row, start + n, p.n_samples, p.pad_mode) * win[n];
+      } else {
+        for (int n = tid; n < N; n += kDftThreads) xw[f * N + n] = 0.0f;
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < nb; k += kDftThreads) {
+      float re[F], im[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) re[f] = im[f] = 0.0f;
+      int idx = 0;
+      for (int n = 0; n < N; ++n) {
+        const float2 w = tab[idx];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float v = xw[f * N + n];
+          re[f] = fmaf(v, w.x, re[f]);
+          im[f] = fmaf(v, w.y, im[f]);
+        }
+        idx += k;
+        idx -= (idx >= N) ? N : 0;
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int64_t g = gbase + f;
+        if (g >= p.g1) continue;
+        const int64_t seq = g / p.frames, t = g - seq * p.frames;
+        const float xi = (k == 0 || 2 * k == N) ? 0.0f : im[f];
+        emit_bin(p, seq, t, g - p.g0, k, re[f], xi);
+        if (!p.onesided && k > 0 && 2 * k != N) emit_bin(p, seq, t, g - p.g0, N - k, re[f], -xi);
+      }
+    }
+    if (p.out_mode == OUT_POWER_ROWS) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int64_t g = gbase + f;
+        if (g < p.g1)
+          for (int k = p.bins + tid; k < p.kpad; k += kDftThreads) p.out[power_tile_index(g - p.g0, k, p.kpad)] = 0.0f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_stft_dft(const StftParams& p, cudaStream_t stream) {
+  const int64_t n_frames = p.g1 - p.g0;
+  const int f = p.n_fft <= 2048 ? 4 : 1;
+  const size_t smem = dft_smem_bytes(p.n_fft, f);
+  auto k = f == 4 ? stft_dft_kernel<4> : stft_dft_kernel<1>;
+  if (smem > 48 * 1024) TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)((200 * 1024) / (smem + 1024));
+  const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+  const int64_t groups = (n_frames + f - 1) / f;
+  const int grid = (int)(groups < cap ? groups : cap);
+  LaunchProbe probe(KIND_STFT, stream);
+  k<<<grid, kDftThreads, smem, stream>>>(p);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
 int dump_k1_trace() {
   long long h[64];
   TAC_CUDA_OK(cudaDeviceSynchronize());
@@ -908,6 +1003,7 @@ static int mel_kernel_variant() {
 int launch_stft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
   if (n_frames <= 0) return TAC_OK;
+  if (!is_pow2(p.n_fft) || p.n_fft < 32) return launch_stft_dft(p, stream);
   if (p.onesided && (p.n_fft == 256 || p.n_fft == 512 || p.n_fft == 1024 || p.n_fft == 4096)) return launch_stft_warp(p, stream);
   if (p.n_fft == 2048 && p.onesided && (p.out_mode == OUT_MEL_FUSED || p.out_mode == OUT_MEL_FUSED_PEERS)) {
     // two frames per warp in packed fp32 pairs (stft_pair.cu); TAC_MEL_SINGLE=1 keeps the one-frame-per-warp kernel
@@ -959,8 +1055,7 @@ int fill_stft_params(StftParams& p, const float* x, int64_t n_seq, int64_t n_sam
   TAC_REQUIRE(n_seq >= 0 && n_samples >= 0 && seq_stride >= n_samples, TAC_ERR_INVALID,
               "stft: bad shape n_seq=%lld n_samples=%lld stride=%lld", (long long)n_seq, (long long)n_samples,
               (long long)seq_stride);
-  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32 && n_fft <= 8192, TAC_ERR_UNSUPPORTED,
-              "stft: n_fft=%d is not a power of two in [32, 8192] (the sm_100a kernels cover those sizes only)", n_fft);
+  TAC_REQUIRE(n_fft >= 2 && n_fft <= 8192, TAC_ERR_UNSUPPORTED, "stft: n_fft=%d outside [2, 8192] (the sizes the sm_100a kernels cover)", n_fft);
   TAC_REQUIRE(hop >= 1, TAC_ERR_INVALID, "stft: hop_length=%d must be positive", hop);
   TAC_REQUIRE(pad_mode >= TAC_PAD_REFLECT && pad_mode <= TAC_PAD_CIRCULAR, TAC_ERR_INVALID, "stft: unknown pad_mode %d", pad_mode);
   const int pad = center ? n_fft / 2 : 0;

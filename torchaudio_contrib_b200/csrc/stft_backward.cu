@@ -497,6 +497,8 @@ extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64
   const int rc = fill_stft_params(bp.f, grad_x /* placeholder, never read */, n_seq, n_samples, n_samples, window, n_fft, hop,
                                   center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
+              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   bp.f.x = nullptr;
   bp.grad_out = grad_out;
   bp.power_mode = -1;
@@ -513,6 +515,8 @@ extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64
   TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
+              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   bp.grad_out = grad_out;
   bp.power = power;
   bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
@@ -616,6 +620,8 @@ extern "C" int tac_melspec_backward_f32(const float* x, int64_t n_seq, int64_t n
   StftBwdParams bp;
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
   if (rc != TAC_OK) return rc;
+  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
+              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   StftParams& p = bp.f;
   if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
   TAC_REQUIRE(grad_x, TAC_ERR_INVALID, "melspec_backward: null gradient pointer");

@@ -389,3 +389,27 @@ def test_shipped_mulaw_tables_equal_fresh_bisection():
     n = ctypes.c_int()
     with pytest.raises(_cabi.TacError):
         _cabi.check(lib.tac_mulaw_tables_host(256, thr.data_ptr(), 10, ctypes.byref(n), ctypes.byref(n), ctypes.byref(ctypes.c_float()), None, None))
+
+
+def test_filterbank_plan_cache_identity(tac):
+    """The plan cache (functional._plan_for): the same matrix and its aliases hit one plan, an in-place edit or another
+    tensor does not; a cached plan keeps the matrix's storage alive so its address cannot be recycled under the key."""
+    F = tac.functional
+    F.invalidate_filterbank_plans()
+    fb = tac.MelFilterbank(num_freqs=257, num_mels=40, sample_rate=16000).get_filterbank()
+    p1 = F._plan_for(fb, "cpu")
+    assert F._plan_for(fb, "cpu") is p1
+    assert F._plan_for(fb.detach(), "cpu") is p1                # what the backward pass hands in
+    fb.mul_(2.0)                                                # bumps the version counter
+    p2 = F._plan_for(fb, "cpu")
+    assert p2 is not p1
+    other = fb.clone()
+    assert F._plan_for(other, "cpu") is not p2
+    cache = {}
+    q1 = F._plan_for(fb, "cpu", cache)
+    assert F._plan_for(fb, "cpu", cache) is q1 and F._plan_for(other, "cpu", cache) is not q1
+    for _ in range(20):                                         # bounded: oldest plans are evicted
+        F._plan_for(torch.rand(33, 8), "cpu")
+    assert len(F._GLOBAL_PLANS) <= F._GLOBAL_PLANS_MAX
+    F.invalidate_filterbank_plans()
+    assert len(F._GLOBAL_PLANS) == 0

@@ -11,9 +11,11 @@ and the `filterbank` argument gets its gradient too (a learnable filterbank).  W
 instead of silently detaching: a `window` that requires grad (whether or not the signal does), `phase_vocoder`
 and `mu_law_encoding` inputs that require grad.
 """
+import collections
 import ctypes
 import math
 import os
+import threading
 
 import torch
 
@@ -240,22 +242,54 @@ class FilterbankPlan(object):
         self.fused_handle = int(lib.tac_fbplan_fused_handle(_cabi.ptr(host), self.fft_length))
         self.blob = host[:used.value].to(device)
         self.device = self.blob.device
+        # What the plan was built from: address, layout and in-place version counter of the matrix.  The plan keeps the
+        # matrix's STORAGE alive, so the address cannot be recycled for another tensor while the plan is cached (the
+        # stale-plan hazard of keying by address alone); aliases of the same storage (`.detach()`, as the backward pass
+        # passes) share address and version counter and hit the same plan.  Writes through `.data` bypass the version
+        # counter, as they do for autograd: `invalidate_filterbank_plans()` / a fresh module cache cover that case.
+        self.storage = filterbank.untyped_storage()
         self.key = FilterbankPlan.key_of(filterbank)
 
     @staticmethod
     def key_of(filterbank):
-        return (filterbank.data_ptr(), filterbank._version, tuple(filterbank.shape), str(filterbank.device))
+        return (filterbank.data_ptr(), filterbank._version, tuple(filterbank.shape), tuple(filterbank.stride()), str(filterbank.device))
+
+    def built_from(self, filterbank, device):
+        return self.key == FilterbankPlan.key_of(filterbank) and self.device == torch.device(device)
+
+
+# plans of matrices passed to the functional API (modules keep their own): a handful, evicted oldest first
+_GLOBAL_PLANS = collections.OrderedDict()
+_GLOBAL_PLANS_MAX = 8
+_plans_lock = threading.Lock()
+
+
+def invalidate_filterbank_plans():
+    """Drop every cached plan of the functional API (after editing a filterbank through `.data`)."""
+    with _plans_lock:
+        _GLOBAL_PLANS.clear()
 
 
 def _plan_for(filterbank, device, cache=None):
-    key = FilterbankPlan.key_of(filterbank)
     if cache is not None:
         plan = cache.get("plan")
-        if plan is not None and plan.key == key and plan.device == torch.device(device):
+        if plan is not None and plan.built_from(filterbank, device):
+            return plan
+        plan = FilterbankPlan(filterbank, device)
+        cache["plan"] = plan
+        return plan
+    slot = FilterbankPlan.key_of(filterbank) + (str(torch.device(device)),)
+    with _plans_lock:
+        plan = _GLOBAL_PLANS.get(slot)
+        if plan is not None and plan.built_from(filterbank, device):
+            _GLOBAL_PLANS.move_to_end(slot)
             return plan
     plan = FilterbankPlan(filterbank, device)
-    if cache is not None:
-        cache["plan"] = plan
+    with _plans_lock:
+        _GLOBAL_PLANS[slot] = plan
+        _GLOBAL_PLANS.move_to_end(slot)
+        while len(_GLOBAL_PLANS) > _GLOBAL_PLANS_MAX:
+            _GLOBAL_PLANS.popitem(last=False)
     return plan
 
 

@@ -312,7 +312,9 @@ def measured_traffic(fused):
     with open(names[-1]) as fh:
         rec = json.load(fh)
     fp = source_fingerprint()
-    if rec.get("source_fingerprint") and fp and rec["source_fingerprint"] != fp:
+    if not rec.get("source_fingerprint"):
+        return None, "%s carries no source fingerprint (taken before the kernels were stamped)" % os.path.basename(names[-1])
+    if fp and rec["source_fingerprint"] != fp:
         return None, "%s was measured on other kernel sources (%s, now %s)" % (os.path.basename(names[-1]), rec["source_fingerprint"], fp)
     return rec.get("dram_bytes_per_launch"), os.path.basename(names[-1])
 

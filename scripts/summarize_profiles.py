@@ -69,16 +69,20 @@ def main():
                 per = {}
                 fused = False
                 for r in rows[1:]:
-                    if "stft2048_kernel" in r[ki] and r[mi].startswith("dram__bytes"):
-                        fused = fused or "stft2048_kernel<3," in r[ki]        # OUT_MEL_FUSED: the one-kernel mel path
+                    if ("stft2048_kernel" in r[ki] or "stft2048_pair_kernel" in r[ki]) and r[mi].startswith("dram__bytes"):
+                        # the one-kernel mel path: the pair kernel, or stft2048_kernel<OUT_MEL_FUSED>
+                        fused = fused or "stft2048_pair_kernel" in r[ki] or "stft2048_kernel<3," in r[ki]
                         per.setdefault(r[ii], 0.0)
                         per[r[ii]] += float(r[vi].replace(",", ""))
                 vals = list(per.values())[1:] or list(per.values())      # drop the first launch (follows the RNG fill)
                 if vals:
                     with open(os.path.join(dst, "%s_%s_dram_bytes.json" % (tag, "melfused" if fused else "stft2048")), "w") as fh:
+                        sys.path.insert(0, ROOT)
+                        import build_native
                         json.dump({"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals), "source": name,
-                                   "note": "dram__bytes_read.sum + dram__bytes_write.sum per stft2048_kernel launch, ncu --cache-control none "
-                                           "(steady state of bench.py, 20032 frames per launch)"}, fh)
+                                   "source_fingerprint": build_native._fingerprint()[:16],
+                                   "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, ncu --cache-control "
+                                           "none (steady state of bench.py, 20032 frames per launch)"}, fh)
         elif name.startswith("bench_") and name.endswith(".json"):
             with open(path) as fh, open(os.path.join(dst, "%s_%s" % (tag, name)), "w") as out:
                 out.write(fh.read())

@@ -266,6 +266,26 @@ int tac_mulaw_decode_i64_f32(const int64_t* codes, int64_t n, int n_quantize,
 int tac_mulaw_decode_f32_f32(const float* codes, int64_t n, int n_quantize,
                              const float* lut_dev, float* out, void* stream);
 
+/* ---- float64 operators (csrc/f64_path.cu) -------------------------------------------------
+ * The reference computes in the dtype it is given (functional.py:99, :126-128, :183, :291-296,
+ * :310-314, :331-334, :349-353); these are the same operators on double tensors, correct-first
+ * kernels with double arithmetic throughout (forward only).  Layouts as the float entries;
+ * tac_stft_f64: any n_fft in [2, 4096], window of n_fft doubles. */
+int tac_stft_f64(const double* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                 const double* window, int n_fft, int hop, int center, int pad_mode,
+                 int normalized, int onesided, double* out, void* stream);
+int tac_complex_norm_f64(const double* z, int64_t n, double power, double* out, void* stream);
+int tac_magphase_f64(const double* z, int64_t n, double power, double* mag /* may be NULL */,
+                     double* phase, void* stream);
+int tac_amplitude_to_db_f64(const double* x, int64_t n, double ref, double amin, double* out, void* stream);
+int tac_db_to_amplitude_f64(const double* x, int64_t n, double ref, double* out, void* stream);
+/* spec: (n_seq, n_bins, frames), fb_dev: (n_bins, n_bands) row-major, out: (n_seq, n_bands, frames) */
+int tac_apply_filterbank_f64(const double* spec, const double* fb_dev, int64_t n_seq, int64_t frames,
+                             int n_bins, int n_bands, double* out, void* stream);
+int tac_mulaw_decode_i64_f64(const int64_t* codes, int64_t n, int n_quantize, const double* lut_dev,
+                             double* out, void* stream);
+int tac_mulaw_encode_f64_i64(const double* x, int64_t n, int n_quantize, int64_t* out, void* stream);
+
 /* ---- host-buffer plugin surface (what a reference-side caller with CPU tensors binds) ---
  * A pipeline owns its device staging buffers, plan, streams and events. */
 typedef struct tac_pipeline tac_pipeline;

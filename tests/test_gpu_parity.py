@@ -213,6 +213,51 @@ def test_stft_non_power_of_two(tac, oc, fft, hop):
             tac.Spectrogram(fft_length=fft, hop_length=hop).cuda()(xg).sum().backward()
 
 
+def test_float64_operators(tac, oc):
+    """The reference computes in the dtype it is given (functional.py:99 ... :353); double tensors run the double kernels
+    of csrc/f64_path.cu.  Every stage against the oracle evaluated in float64 on the CPU, to 1e-10 of the output scale;
+    dtype mismatches raise like torch.matmul does in the reference; gradients of double inputs are refused."""
+    torch.manual_seed(71)
+    x = torch.randn(2, 2, 9000, dtype=torch.float64)
+    for fft, hop, kw in ((512, 128, dict()), (400, 160, dict(onesided=False, pad_mode="constant")), (2048, 512, dict(normalized=True)),
+                         (256, 64, dict(center=False, win_length=200))):
+        got = tac.stft(dev(x), fft, hop, **kw)
+        want = oc.stft(x, fft, hop, **kw)
+        assert got.dtype == torch.float64 and got.shape == want.shape
+        assert (got.cpu() - want).abs().max().item() < 1e-10 * max(1.0, want.abs().max().item()), (fft, kw)
+    z = oc.stft(x, 512, 128)
+    for power in (1.0, 2.0, 0.7):
+        assert torch.allclose(tac.complex_norm(dev(z), power).cpu(), oc.complex_norm(z, power), rtol=1e-12, atol=1e-13)
+    mag, ph = tac.magphase(dev(z), 2.0)
+    wm, wp = oc.magphase(z, 2.0)
+    assert torch.allclose(mag.cpu(), wm, rtol=1e-12) and torch.allclose(ph.cpu(), wp, rtol=1e-12, atol=1e-14)
+    assert torch.allclose(tac.angle(dev(z)).cpu(), oc.angle(z), rtol=1e-12, atol=1e-14)
+    spec = oc.complex_norm(z, 2.0)
+    fb = tac.MelFilterbank(num_freqs=257, num_mels=40, sample_rate=16000).get_filterbank()
+    with pytest.raises(RuntimeError):
+        tac.apply_filterbank(dev(spec), dev(fb))                # float32 matrix, float64 spectrogram: as torch.matmul
+    mel = tac.apply_filterbank(dev(spec), dev(fb.double()))
+    want = oc.apply_filterbank(spec, fb.double())
+    assert mel.dtype == torch.float64 and torch.allclose(mel.cpu(), want, rtol=1e-12, atol=1e-12)
+    db = tac.amplitude_to_db(mel, ref=2.0, amin=1e-6)
+    assert torch.allclose(db.cpu(), oc.amplitude_to_db(want, ref=2.0, amin=1e-6), rtol=1e-12, atol=1e-11)
+    assert torch.allclose(tac.db_to_amplitude(db, ref=2.0).cpu(), oc.db_to_amplitude(db.cpu(), ref=2.0), rtol=1e-12)
+    # modules: .double() moves the buffers, the chain is the reference's
+    m = tac.Sequential(*tac.Melspectrogram(num_mels=40, sample_rate=16000, fft_length=512, hop_length=128), tac.AmplitudeToDb()).cuda().double()
+    got = m(dev(x)).cpu()
+    want = oc.amplitude_to_db(oc.apply_filterbank(oc.complex_norm(oc.stft(x, 512, 128), 2.0), fb.double()))
+    assert got.dtype == torch.float64 and (got - want).abs().max().item() < 1e-9
+    # mu-law in double
+    codes = torch.randint(0, 256, (3, 1000))
+    assert torch.equal(tac.mu_law_decoding(dev(codes), 256, torch.float64).cpu(), oc.mu_law_decoding(codes, 256, torch.float64))
+    sig = torch.rand(3, 50000, dtype=torch.float64) * 2 - 1
+    enc = tac.mu_law_encoding(dev(sig), 256).cpu()
+    ref = oc.mu_law_encoding(sig, 256)
+    assert (enc != ref).sum().item() <= 1                       # device log1p vs the host's: at most a boundary case
+    with pytest.raises(NotImplementedError):
+        tac.stft(dev(x).requires_grad_(True), 512, 128)
+
+
 def test_stft_too_short_raises(tac):
     """tests/test_functional.py:31: reflect padding needs more samples than the pad."""
     with pytest.raises(RuntimeError):

@@ -75,6 +75,14 @@ SIGNATURES = {
     "tac_mulaw_tables_host": (_int, [_int, _ptr, _int, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_f32), _ptr, _c.POINTER(_int)]),
     "tac_mulaw_decode_i64_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
     "tac_mulaw_decode_f32_f32": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
+    "tac_stft_f64": (_int, [_ptr, _i64, _i64, _i64, _ptr, _int, _int, _int, _int, _int, _int, _ptr, _ptr]),
+    "tac_complex_norm_f64": (_int, [_ptr, _i64, _c.c_double, _ptr, _ptr]),
+    "tac_magphase_f64": (_int, [_ptr, _i64, _c.c_double, _ptr, _ptr, _ptr]),
+    "tac_amplitude_to_db_f64": (_int, [_ptr, _i64, _c.c_double, _c.c_double, _ptr, _ptr]),
+    "tac_db_to_amplitude_f64": (_int, [_ptr, _i64, _c.c_double, _ptr, _ptr]),
+    "tac_apply_filterbank_f64": (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _ptr, _ptr]),
+    "tac_mulaw_decode_i64_f64": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
+    "tac_mulaw_encode_f64_i64": (_int, [_ptr, _i64, _int, _ptr, _ptr]),
     "tac_pipeline_create": (_int, [_ptr, _ptr, _ptr, _c.POINTER(_ptr)]),
     "tac_pipeline_run_host": (_int, [_ptr, _ptr, _i64, _i64, _ptr]),
     "tac_pipeline_destroy": (_int, [_ptr]),

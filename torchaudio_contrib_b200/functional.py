@@ -19,7 +19,7 @@ import threading
 
 import torch
 
-from . import _cabi, _mulaw_tables
+from . import _cabi, _f64, _mulaw_tables
 
 __all__ = [
     "stft", "complex_norm", "create_mel_filter", "apply_filterbank", "amplitude_to_db",
@@ -113,11 +113,14 @@ def stft(waveforms, fft_length, hop_length=None, win_length=None, window=None,
     """Short-time Fourier transform, `(*, channel, time) -> (*, channel, num_freqs, frames, 2)`.
 
     Reference: functional.py:48-113 (a reshape around `torch.stft`, :99-107).  Here: one fused
-    framing + padding + window + real-FFT kernel (csrc/stft.cu).  `fft_length` must be a power
-    of two in [32, 8192].  Unlike the reference, a missing `window` is created on the input's
-    device.  The result is a contiguous tensor of the reference's logical shape.
+    framing + padding + window + real-FFT kernel (csrc/stft.cu) for powers of two in [32, 8192], a
+    direct-DFT kernel for any other `fft_length` in [2, 8192]; float64 waveforms take the double
+    kernels of csrc/f64_path.cu (forward only).  Unlike the reference, a missing `window` is created
+    on the input's device.  The result is a contiguous tensor of the reference's logical shape.
     """
     _no_param_grad(window, "stft: window")
+    if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:
+        return _f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided)
     if _wants_grad(waveforms):
         return _StftFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided))
     x = _as_f32_cuda(waveforms, "waveforms")
@@ -137,6 +140,9 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
     """`Spectrogram(...)(x)` in one kernel: stft then `|.|^power` (layers.py:294-304), the complex
     spectrum never reaches HBM.  Returns `(*, channel, num_freqs, frames)`."""
     _no_param_grad(window, "spectrogram: window")
+    if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:
+        return _f64.complex_norm(_f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized,
+                                           onesided), float(power))
     if _wants_grad(waveforms):
         return _SpectrogramFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized,
                                                 onesided, power))
@@ -157,6 +163,8 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
 # ------------------------------------------------------------------------------------------------
 def complex_norm(complex_tensor, power=1.0):
     """`(*, 2) -> (*)`: sqrt(re^2 + im^2), then `.pow(power)` (functional.py:116-128)."""
+    if isinstance(complex_tensor, torch.Tensor) and complex_tensor.dtype == torch.float64:
+        return _f64.complex_norm(complex_tensor, float(power))
     if _wants_grad(complex_tensor):
         return _ComplexNormFn.apply(complex_tensor, float(power))
     z = _as_f32_cuda(complex_tensor, "complex_tensor")
@@ -318,6 +326,8 @@ def apply_filterbank(mag_specgrams, filterbank, _cache=None):
     """`(*, num_freqs, time) x (num_freqs, num_bands) -> (*, num_bands, time)`: contraction over
     the frequency axis (functional.py:172-184) on the tcgen05 tensor cores with 3xTF32 split
     accumulation (csrc/melbank.cu).  Any dense matrix is accepted; zero blocks are skipped."""
+    if isinstance(mag_specgrams, torch.Tensor) and mag_specgrams.dtype == torch.float64:
+        return _f64.apply_filterbank(mag_specgrams, filterbank)
     if _wants_grad(mag_specgrams) or _wants_grad(filterbank):
         return _ApplyFilterbankFn.apply(mag_specgrams, filterbank, _cache)
     spec = _as_f32_cuda(mag_specgrams, "mag_specgrams")
@@ -330,6 +340,8 @@ def apply_filterbank(mag_specgrams, filterbank, _cache=None):
 # ------------------------------------------------------------------------------------------------
 def amplitude_to_db(x, ref=1.0, amin=1e-7):
     """`10 * (log10(max(x^2, amin)) - log10(ref))` (functional.py:277-296; note the square)."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float64:
+        return _f64.amplitude_to_db(x, float(ref), float(amin))
     if _wants_grad(x):
         return _AmplitudeToDbFn.apply(x, float(ref), float(amin))
     a = _as_f32_cuda(x, "x")
@@ -342,6 +354,8 @@ def amplitude_to_db(x, ref=1.0, amin=1e-7):
 
 def db_to_amplitude(x, ref=1.0):
     """`sqrt(10 ** (x / 10 + log10(ref)))` (functional.py:299-314): the inverse of `amplitude_to_db`."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float64:
+        return _f64.db_to_amplitude(x, float(ref))
     if _wants_grad(x):
         return _DbToAmplitudeFn.apply(x, float(ref))
     a = _as_f32_cuda(x, "x")
@@ -356,6 +370,8 @@ def db_to_amplitude(x, ref=1.0):
 # N4: angle / magphase
 # ------------------------------------------------------------------------------------------------
 def _magphase(complex_tensor, power, want_mag, name):
+    if isinstance(complex_tensor, torch.Tensor) and complex_tensor.dtype == torch.float64:
+        return _f64.magphase(complex_tensor, float(power), want_mag, name)
     if _wants_grad(complex_tensor):
         mag, phase = _MagphaseFn.apply(complex_tensor, float(power), want_mag, name)
         return (mag if want_mag else None), phase
@@ -475,6 +491,11 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     `layout="contiguous"` returns a contiguous `(*, num_bands, frames)` tensor (4-byte stores, ~9 % slower
     at BASELINE config 2).  The two-kernel path always returns a contiguous tensor."""
     _no_param_grad(window, "melspectrogram: window")
+    if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:     # the stages, in double (csrc/f64_path.cu)
+        spec = _f64.complex_norm(_f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized,
+                                           True), float(power))
+        mel = _f64.apply_filterbank(spec, filterbank)
+        return _f64.amplitude_to_db(mel, float(ref), float(amin)) if to_db else mel
     if _wants_grad(waveforms) or _wants_grad(filterbank):
         # The Function returns the buffer as it lies in memory; the reference-layout view is taken out here, where
         # autograd sees an ordinary transpose (a view created inside Function.forward costs an as_strided replay:
@@ -906,6 +927,8 @@ def mu_law_encoding(x, n_quantize=256):
     Bit-exact with the reference's fp32 CPU chain for every finite float (see _mulaw_tables)."""
     _forward_only(x, "mu_law_encoding")
     _cabi.require_cuda(x, "x")
+    if x.dtype == torch.float64:                           # the reference's formula in the input's dtype (functional.py:331-334)
+        return _f64.mu_law_encoding(x, int(n_quantize))
     if not x.dtype.is_floating_point:
         x = x.to(torch.float)                              # functional.py:329-330
     a = _as_f32_cuda(x, "x")
@@ -921,8 +944,10 @@ def mu_law_encoding(x, n_quantize=256):
 def mu_law_decoding(x_mu, n_quantize=256, dtype=torch.float32):
     """mu-law expansion of codes to float32 (functional.py:338-354)."""
     _cabi.require_cuda(x_mu, "x_mu")
-    if dtype != torch.float32:
-        raise NotImplementedError("mu_law_decoding: only float32 output is implemented")
+    if dtype == torch.float64 and not x_mu.dtype.is_floating_point:
+        return _f64.mu_law_decoding(x_mu, int(n_quantize))
+    if dtype != torch.float32 and not x_mu.dtype.is_floating_point:
+        raise NotImplementedError("mu_law_decoding: float32 and float64 outputs are implemented, not %s" % dtype)
     (lut,) = _mulaw_tables.on_device("dec", n_quantize, x_mu.device)
     lib = _cabi.lib()
     if x_mu.dtype.is_floating_point:

@@ -85,6 +85,20 @@ int tac_phase_vocoder_f32(const float* spec, int64_t n_seq, int n_bins, int64_t 
 int tac_phase_vocoder_f64(const double* spec, int64_t n_seq, int n_bins, int64_t n_in,
                           const int32_t* idx0, const int32_t* idx1, const double* alpha,
                           const double* advance, int64_t n_out, double* out, void* stream);
+/* Backward of the phase vocoder w.r.t. the spectrogram (round 2).  range0 / range1: (n_in, 2) int32 tables, the
+ * contiguous ranges [lo, hi) of output steps j with idx0[j] == i / idx1[j] == i (idx0 and idx1 are monotone);
+ * workspace: 16 bytes per (row, output step); grad_spec: same shape as spec, overwritten.  float64 inside
+ * like the forward kernel; a gather per input frame, no atomics (deterministic). */
+int tac_phase_vocoder_backward_f32(const float* spec, const float* grad_out, int64_t n_seq, int n_bins,
+                                   int64_t n_in, const int32_t* idx0, const int32_t* idx1,
+                                   const double* alpha, const float* advance, int64_t n_out,
+                                   const int32_t* range0, const int32_t* range1, void* workspace,
+                                   int64_t workspace_bytes, float* grad_spec, void* stream);
+int tac_phase_vocoder_backward_f64(const double* spec, const double* grad_out, int64_t n_seq, int n_bins,
+                                   int64_t n_in, const int32_t* idx0, const int32_t* idx1,
+                                   const double* alpha, const double* advance, int64_t n_out,
+                                   const int32_t* range0, const int32_t* range1, void* workspace,
+                                   int64_t workspace_bytes, double* grad_spec, void* stream);
 
 /* ---- a3: apply_filterbank (functional.py:172-184) on tcgen05 tensor cores ---------------
  * The (n_bins, n_bands) row-major matrix is first turned into a "plan": per 32-bin K slice

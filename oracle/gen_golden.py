@@ -8,6 +8,7 @@ reference was written against -- torch 2.x refuses the legacy call).  No referen
 touched or copied.  For every fixture the script also asserts that `oracle.ref_chain`
 reproduces the reference output bit for bit (`torch.equal`), which is what pins the oracle.
 """
+import math
 import os
 import sys
 
@@ -252,6 +253,38 @@ def grads_more(ref, oc):
     print("round-2 gradient fixtures reproduce under oracle.ref_chain autograd")
 
 
+def grads_pv(ref, oc):
+    """Phase-vocoder gradient fixtures (functional.py:204-274 under torch autograd), float64 with float64 as torch's default
+    dtype like the reference's own value test (tests/test_functional.py:76-93): stretch and compress rates, a rate with
+    several output steps per input frame.  `python oracle/gen_golden.py grads_pv` writes tests/golden/grads_pv.npz only."""
+    g = torch.Generator().manual_seed(20261018)
+    blob = {}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        for tag, rate, shape, hop in (("r07", 0.7, (2, 33, 41, 2), 16), ("r13", 1.3, (1, 2, 65, 50, 2), 32), ("r20", 2.0, (3, 17, 37, 2), 8),
+                                      ("r03", 0.3, (1, 9, 12, 2), 4)):
+            z = torch.randn(*shape, generator=g, dtype=torch.float64)
+            adv = torch.linspace(0, math.pi * hop, shape[-3], dtype=torch.float64)[..., None]
+            zr = z.clone().requires_grad_(True)
+            with _shimmed(ref):
+                yr = ref.phase_vocoder(zr, rate, adv)
+            gy = torch.randn(*yr.shape, generator=g, dtype=torch.float64)
+            (gr,) = torch.autograd.grad(yr, zr, gy)
+            zo = z.clone().requires_grad_(True)
+            yo = oc.phase_vocoder(zo, rate, adv)
+            (go,) = torch.autograd.grad(yo, zo, gy)
+            _same(yr.detach(), yo.detach(), "grads_pv/%s forward" % tag)
+            _same(gr, go, "grads_pv/%s backward" % tag)
+            blob[tag + "_z"], blob[tag + "_adv"], blob[tag + "_gy"], blob[tag + "_gz"], blob[tag + "_y"] = \
+                z.numpy(), adv.numpy(), gy.numpy(), gr.numpy(), yr.detach().numpy()
+            blob[tag + "_rate"] = np.array(rate)
+    finally:
+        torch.set_default_dtype(old)
+    _save("grads_pv.npz", **blob)
+    print("phase-vocoder gradient fixtures reproduce under oracle.ref_chain autograd")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
@@ -265,8 +298,11 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads_more":
         grads_more(ref, oc)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "grads_pv":
+        grads_pv(ref, oc)
+        return
     if len(sys.argv) > 1:
-        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more]   (no argument: the forward fixtures)")
+        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more | grads_pv]   (no argument: the forward fixtures)")
     g = torch.Generator().manual_seed(20260925)
 
     def randn(*shape):

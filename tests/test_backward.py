@@ -351,3 +351,50 @@ def test_filterbank_parameter_gradient(tac):
     assert y.requires_grad
     (gfb2,) = torch.autograd.grad(y, [fb], gy)
     assert rel_err(gfb2.cpu(), g["melchain_param_g_fb"]) < REL
+
+
+# --------------------------------------------------------------------------------------------- round 2: phase vocoder
+def test_oracle_autograd_reproduces_phase_vocoder_gradients():
+    """tests/golden/grads_pv.npz (oracle/gen_golden.py grads_pv): the unmodified reference's float64 gradients."""
+    g = golden("grads_pv.npz")
+    prior = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        for tag in ("r07", "r13", "r20", "r03"):
+            z = g[tag + "_z"].clone().requires_grad_(True)
+            y = oc.phase_vocoder(z, float(g[tag + "_rate"]), g[tag + "_adv"])
+            (gz,) = torch.autograd.grad(y, z, g[tag + "_gy"])
+            assert torch.allclose(gz, g[tag + "_gz"], rtol=1e-10, atol=1e-10), tag
+    finally:
+        torch.set_default_dtype(prior)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["r07", "r13", "r20", "r03"])
+def test_phase_vocoder_backward(tac, tag):
+    """functional.py:204-274 under autograd: the gather kernel (csrc/phase_vocoder.cu) against the reference's float64
+    gradient -- float64 tensors to 1e-9 of the gradient's scale, float32 tensors (float64 inside) to float32 rounding;
+    deterministic; the TimeStretch module differentiates too."""
+    g = golden("grads_pv.npz")
+    rate = float(g[tag + "_rate"])
+    want = g[tag + "_gz"]
+    scale = want.abs().max().item()
+    prior = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)                      # the reference's time steps are built in the default dtype
+    try:
+        z = g[tag + "_z"].cuda().requires_grad_(True)
+        y = tac.phase_vocoder(z, rate, g[tag + "_adv"].cuda())
+        assert (y.detach().cpu() - g[tag + "_y"]).abs().max().item() < 1e-8
+        (gz,) = torch.autograd.grad(y, z, g[tag + "_gy"].cuda())
+        assert gz.dtype == torch.float64 and gz.shape == want.shape
+        assert (gz.cpu() - want).abs().max().item() < 1e-9 * scale, tag
+        z2 = g[tag + "_z"].cuda().requires_grad_(True)
+        (again,) = torch.autograd.grad(tac.phase_vocoder(z2, rate, g[tag + "_adv"].cuda()), z2, g[tag + "_gy"].cuda())
+        assert torch.equal(gz, again)
+        z32 = g[tag + "_z"].float().cuda().requires_grad_(True)
+        (g32,) = torch.autograd.grad(tac.phase_vocoder(z32, rate, g[tag + "_adv"].float().cuda()), z32, g[tag + "_gy"].float().cuda())
+        assert g32.dtype == torch.float32 and (g32.cpu().double() - want).abs().max().item() < 2e-4 * scale, tag
+    finally:
+        torch.set_default_dtype(prior)
+    with pytest.raises(RuntimeError):
+        tac.phase_vocoder(g[tag + "_z"].cuda(), rate, g[tag + "_adv"].cuda().requires_grad_(True))

@@ -39,6 +39,8 @@ SIGNATURES = {
     "tac_magphase_f32": (_int, [_ptr, _i64, _f32, _ptr, _ptr, _ptr]),
     "tac_phase_vocoder_f32": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
     "tac_phase_vocoder_f64": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "tac_phase_vocoder_backward_f32": (_int, [_ptr, _ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "tac_phase_vocoder_backward_f64": (_int, [_ptr, _ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
     "tac_fbplan_bytes": (_i64, [_int, _int]),
     "tac_fbplan_build_host": (_int, [_ptr, _int, _int, _ptr, _i64, _c.POINTER(_i64)]),
     "tac_fbplan_band_handle": (_i64, [_ptr]),

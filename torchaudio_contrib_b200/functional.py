@@ -8,8 +8,9 @@ each call enqueues kernels of libtac_b200.so on the current stream.  There is no
 Autograd: the signal path (stft, complex_norm, apply_filterbank, amplitude_to_db, spectrogram, melspectrogram,
 db_to_amplitude, magphase / angle, float-input mu_law_decoding) is differentiated by hand-written adjoint kernels,
 and the `filterbank` argument gets its gradient too (a learnable filterbank).  What is not differentiated raises
-instead of silently detaching: a `window` that requires grad (whether or not the signal does), `phase_vocoder`
-and `mu_law_encoding` inputs that require grad.
+instead of silently detaching: a `window` that requires grad (whether or not the signal does), `mu_law_encoding`
+inputs that require grad, float64 inputs (forward only, except `phase_vocoder`) and `fft_length`s that are not a power
+of two.  `phase_vocoder` is differentiated w.r.t. the spectrogram by its own gather kernel.
 """
 import collections
 import ctypes
@@ -420,14 +421,19 @@ def _phase_vocoder_tables(n_in, rate, device):
     return hit
 
 
-def phase_vocoder(complex_specgrams, rate, phase_advance):
-    """Time-stretch a complex STFT by `rate` without changing pitch (functional.py:204-274).
-    `(*, channel, num_freqs, time, 2) -> (*, channel, num_freqs, ceil(time / rate), 2)`; `phase_advance` is the
-    `(num_freqs, 1)` expected phase advance per bin.  float32 or float64 tensors; angles, the phase wrap, the
-    running phase sum and sin / cos are evaluated in float64 either way (the reference's float32 evaluation
-    loses the accumulated phase, which is why its own test runs in float64 -- tests/test_functional.py:85-88),
-    so the result matches the reference called in float64 on the same values."""
-    _forward_only(complex_specgrams, "phase_vocoder")
+def _phase_vocoder_ranges(idx0, idx1, n_in):
+    """(n_in, 2) int32 tables: the range [lo, hi) of output steps whose idx0 / idx1 equals each input frame (both index
+    tables are monotone), for the gather of the backward kernel."""
+    frames = torch.arange(n_in, device=idx0.device, dtype=torch.int32)
+    out = []
+    for idx in (idx0, idx1):
+        lo = torch.searchsorted(idx, frames, right=False)
+        hi = torch.searchsorted(idx, frames, right=True)
+        out.append(torch.stack([lo, hi], dim=1).to(torch.int32).contiguous())
+    return out
+
+
+def _phase_vocoder_prepare(complex_specgrams, rate, phase_advance):
     _cabi.require_cuda(complex_specgrams, "complex_specgrams")
     if complex_specgrams.dtype not in (torch.float32, torch.float64):
         raise NotImplementedError("phase_vocoder: dtype %s (float32 and float64 are implemented)" % complex_specgrams.dtype)
@@ -437,21 +443,67 @@ def phase_vocoder(complex_specgrams, rate, phase_advance):
     if not rate > 0:
         raise ValueError("phase_vocoder: rate must be positive, got %r" % (rate,))
     n_bins, n_in = int(spec.size(-3)), int(spec.size(-2))
-    adv = phase_advance.to(device=spec.device, dtype=spec.dtype).reshape(-1).contiguous()
+    adv = phase_advance.detach().to(device=spec.device, dtype=spec.dtype).reshape(-1).contiguous()
     if adv.numel() != n_bins:
         raise RuntimeError("phase_vocoder: phase_advance has %d entries for %d frequency bins" % (adv.numel(), n_bins))
     idx0, idx1, alphas = _phase_vocoder_tables(n_in, rate, spec.device)
-    n_out = int(idx0.numel())
     lead = tuple(spec.shape[:-3])
     n_seq = 1
     for d in lead:
         n_seq *= int(d)
+    return spec, adv, idx0, idx1, alphas, lead, n_seq, n_bins, n_in
+
+
+def _phase_vocoder_forward(complex_specgrams, rate, phase_advance):
+    spec, adv, idx0, idx1, alphas, lead, n_seq, n_bins, n_in = _phase_vocoder_prepare(complex_specgrams, rate, phase_advance)
+    n_out = int(idx0.numel())
     out = torch.empty(lead + (n_bins, n_out, 2), dtype=spec.dtype, device=spec.device)
     fn = _cabi.lib().tac_phase_vocoder_f32 if spec.dtype == torch.float32 else _cabi.lib().tac_phase_vocoder_f64
     with torch.cuda.device(spec.device):
         _cabi.check(fn(_cabi.ptr(spec), n_seq, n_bins, n_in, _cabi.ptr(idx0), _cabi.ptr(idx1), _cabi.ptr(alphas),
                        _cabi.ptr(adv), n_out, _cabi.ptr(out), _cabi.stream_ptr(spec.device)))
     return out
+
+
+class _PhaseVocoderFn(torch.autograd.Function):
+    """functional.py:204-274 differentiates through index_select / atan2 / norm / cumsum / cos / sin; here one gather
+    kernel (csrc/phase_vocoder.cu: phase_vocoder_backward_kernel), float64 inside like the forward pass."""
+
+    @staticmethod
+    def forward(ctx, complex_specgrams, rate, phase_advance):
+        ctx.save_for_backward(complex_specgrams)
+        ctx.rate, ctx.phase_advance = rate, phase_advance
+        return _phase_vocoder_forward(complex_specgrams.detach(), rate, phase_advance)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (z,) = ctx.saved_tensors
+        spec, adv, idx0, idx1, alphas, lead, n_seq, n_bins, n_in = _phase_vocoder_prepare(z.detach(), ctx.rate, ctx.phase_advance)
+        n_out = int(idx0.numel())
+        g = grad_out.to(dtype=spec.dtype).contiguous()
+        range0, range1 = _phase_vocoder_ranges(idx0, idx1, n_in)
+        ws = torch.empty(max(n_seq * n_bins * n_out * 16, 1), dtype=torch.uint8, device=spec.device)
+        grad = torch.empty_like(spec)
+        fn = _cabi.lib().tac_phase_vocoder_backward_f32 if spec.dtype == torch.float32 else _cabi.lib().tac_phase_vocoder_backward_f64
+        with torch.cuda.device(spec.device):
+            _cabi.check(fn(_cabi.ptr(spec), _cabi.ptr(g), n_seq, n_bins, n_in, _cabi.ptr(idx0), _cabi.ptr(idx1), _cabi.ptr(alphas),
+                           _cabi.ptr(adv), n_out, _cabi.ptr(range0), _cabi.ptr(range1), _cabi.ptr(ws), ws.numel(), _cabi.ptr(grad),
+                           _cabi.stream_ptr(spec.device)))
+        return grad, None, None
+
+
+def phase_vocoder(complex_specgrams, rate, phase_advance):
+    """Time-stretch a complex STFT by `rate` without changing pitch (functional.py:204-274).
+    `(*, channel, num_freqs, time, 2) -> (*, channel, num_freqs, ceil(time / rate), 2)`; `phase_advance` is the
+    `(num_freqs, 1)` expected phase advance per bin.  float32 or float64 tensors; angles, the phase wrap, the
+    running phase sum and sin / cos are evaluated in float64 either way (the reference's float32 evaluation
+    loses the accumulated phase, which is why its own test runs in float64 -- tests/test_functional.py:85-88),
+    so the result matches the reference called in float64 on the same values.  Differentiable w.r.t. the spectrogram
+    (one gather kernel, deterministic); `phase_advance` is a constant (it raises if it requires grad)."""
+    _no_param_grad(phase_advance, "phase_vocoder: phase_advance")
+    if _wants_grad(complex_specgrams):
+        return _PhaseVocoderFn.apply(complex_specgrams, rate, phase_advance)
+    return _phase_vocoder_forward(complex_specgrams, rate, phase_advance)
 
 
 # ------------------------------------------------------------------------------------------------

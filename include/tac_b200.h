@@ -231,6 +231,13 @@ int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64_t n_sample
                           const float* window, int n_fft, int hop, int center, int pad_mode,
                           int normalized, int onesided, float* grad_x,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* Gradient w.r.t. the window of tac_stft_f32 (round 2): run tac_stft_backward_f32 with a window of ONES first -- its
+ * workspace then holds, per frame, scale * (gradient of the windowed frame before the window multiply) -- and hand
+ * that workspace in as frames_ws; grad_window: n_fft floats (the centre-padded window), scratch: 256 * n_fft bytes.
+ * Deterministic (two-step reduction in fixed order). */
+int tac_window_grad_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                        const float* frames_ws, int n_fft, int hop, int center, int pad_mode,
+                        float* grad_window, void* scratch, int64_t scratch_bytes, void* stream);
 int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                                  const float* window, int n_fft, int hop, int center, int pad_mode,
                                  int normalized, int onesided, float power,

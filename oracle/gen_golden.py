@@ -285,6 +285,54 @@ def grads_pv(ref, oc):
     print("phase-vocoder gradient fixtures reproduce under oracle.ref_chain autograd")
 
 
+def grads_win(ref, oc):
+    """Gradients w.r.t. a learnable window (functional.py:93-107 under torch autograd) from the UNMODIFIED reference: the
+    complex stft (full-length and win_length < fft_length windows, normalized, no centring), the Spectrogram chain and the
+    mel + dB chain, each with the waveform's gradient alongside.  `python oracle/gen_golden.py grads_win` writes
+    tests/golden/grads_win.npz only."""
+    g = torch.Generator().manual_seed(20261019)
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g)
+
+    blob = {}
+
+    def record(tag, x, w, run_ref, run_oc):
+        def run(fn):
+            xl, wl = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            return (xl, wl), fn(xl, wl)
+        with _shimmed(ref):
+            lr, yr = run(run_ref)
+        gy = randn(*yr.shape)
+        gr = torch.autograd.grad(yr, lr, gy)
+        lo, yo = run(run_oc)
+        go = torch.autograd.grad(yo, lo, gy)
+        _same(yr.detach(), yo.detach(), "grads_win/%s forward" % tag)
+        for a, b in zip(gr, go):
+            _same(a, b, "grads_win/%s backward" % tag)
+        blob[tag + "_x"], blob[tag + "_w"], blob[tag + "_gy"], blob[tag + "_gx"], blob[tag + "_gw"] = \
+            x.numpy(), w.numpy(), gy.numpy(), gr[0].numpy(), gr[1].numpy()
+
+    x = randn(2, 2, 6000)
+    w512 = torch.hann_window(512) + 0.05 * randn(512)
+    record("stft512", x, w512, lambda x, w: ref.stft(x, 512, 128, window=w), lambda x, w: oc.stft(x, 512, 128, window=w))
+    w200 = torch.hann_window(200) + 0.05 * randn(200)
+    record("stft256_win200", x, w200, lambda x, w: ref.stft(x, 256, 64, win_length=200, window=w, normalized=True),
+           lambda x, w: oc.stft(x, 256, 64, win_length=200, window=w, normalized=True))
+    record("stft512_nocenter_two", x, w512, lambda x, w: ref.stft(x, 512, 200, window=w, center=False, onesided=False),
+           lambda x, w: oc.stft(x, 512, 200, window=w, center=False, onesided=False))
+    record("spec512_p1", x, w512, lambda x, w: ref.complex_norm(ref.stft(x, 512, 128, window=w), 1.0),
+           lambda x, w: oc.complex_norm(oc.stft(x, 512, 128, window=w), 1.0))
+    w2048 = torch.hann_window(2048) + 0.05 * randn(2048)
+    x2 = randn(2, 1, 12000)
+    fb = oc.mel_filterbank_for(64, 16000, fft_length=2048)
+    record("meldb2048", x2, w2048,
+           lambda x, w: ref.amplitude_to_db(ref.apply_filterbank(ref.complex_norm(ref.stft(x, 2048, 512, window=w), 2.0), fb)),
+           lambda x, w: oc.amplitude_to_db(oc.apply_filterbank(oc.complex_norm(oc.stft(x, 2048, 512, window=w), 2.0), fb)))
+    _save("grads_win.npz", **blob)
+    print("window-gradient fixtures reproduce under oracle.ref_chain autograd")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
@@ -298,11 +346,14 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads_more":
         grads_more(ref, oc)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "grads_win":
+        grads_win(ref, oc)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "grads_pv":
         grads_pv(ref, oc)
         return
     if len(sys.argv) > 1:
-        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more | grads_pv]   (no argument: the forward fixtures)")
+        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more | grads_pv | grads_win]   (no argument: the forward fixtures)")
     g = torch.Generator().manual_seed(20260925)
 
     def randn(*shape):

@@ -42,15 +42,18 @@ def test_oracle_autograd_reproduces_reference_gradients():
 
 
 def test_requires_grad_on_constants_is_refused_without_a_gpu_call():
+    """Where an argument is a constant of the path taken (the window of the float64 path, phase_advance), requiring a gradient
+    for it raises before any library call -- never a silent detach.  (The float32 window IS differentiated: test_window_gradient.)"""
     import torchaudio_contrib_b200.functional as F
     w = torch.hann_window(512).requires_grad_(True)
-    with pytest.raises(RuntimeError, match="the window is a constant"):
+    with pytest.raises(RuntimeError, match="is a constant on this path"):
         F._no_param_grad(w, "stft: window")
-    x = torch.zeros(1, 1, 4096)                         # the check comes first: signal without grad, CPU tensor, no library call
-    for fn in (lambda: F.stft(x, 512, window=w), lambda: F.spectrogram(x, 512, window=w),
-               lambda: F.melspectrogram(x, torch.zeros(257, 8), 512, window=w)):
-        with pytest.raises(RuntimeError, match="the window is a constant"):
+    x = torch.zeros(1, 1, 4096, dtype=torch.float64)    # the check comes first: CPU tensor, no library call
+    for fn in (lambda: F.stft(x, 512, window=w), lambda: F.spectrogram(x, 512, window=w)):
+        with pytest.raises(RuntimeError, match="is a constant on this path"):
             fn()
+    with pytest.raises(RuntimeError, match="is a constant on this path"):
+        F.phase_vocoder(torch.zeros(1, 5, 8, 2), 1.3, torch.zeros(5, 1, requires_grad=True))
 
 
 def test_oracle_autograd_reproduces_round2_gradients():
@@ -398,3 +401,42 @@ def test_phase_vocoder_backward(tac, tag):
         torch.set_default_dtype(prior)
     with pytest.raises(RuntimeError):
         tac.phase_vocoder(g[tag + "_z"].cuda(), rate, g[tag + "_adv"].cuda().requires_grad_(True))
+
+
+# --------------------------------------------------------------------------------------------- round 2: learnable window
+@pytest.mark.gpu
+def test_window_gradient(tac):
+    """A window that requires grad gets the reference's gradient (tests/golden/grads_win.npz, from the unmodified reference):
+    complex stft with a full-length and a shorter (centre-padded) window, normalized, two-sided without centring; the
+    Spectrogram and mel + dB chains (functional and modules), with and without a gradient for the waveform."""
+    g = golden("grads_win.npz")
+    F = tac.functional
+
+    def run(tag, fn, want_x=True):
+        x = g[tag + "_x"].cuda().requires_grad_(want_x)
+        w = g[tag + "_w"].cuda().requires_grad_(True)
+        y = fn(x, w)
+        assert y.requires_grad
+        grads = torch.autograd.grad(y, [x, w] if want_x else [w], g[tag + "_gy"].cuda())
+        gw = grads[-1]
+        assert gw.shape == g[tag + "_gw"].shape
+        assert rel_err(gw.cpu(), g[tag + "_gw"]) < REL, (tag, "window", rel_err(gw.cpu(), g[tag + "_gw"]))
+        if want_x:
+            assert rel_err(grads[0].cpu(), g[tag + "_gx"]) < REL, (tag, "waveform")
+
+    for want_x in (True, False):
+        run("stft512", lambda x, w: F.stft(x, 512, 128, window=w), want_x)
+        run("stft256_win200", lambda x, w: F.stft(x, 256, 64, win_length=200, window=w, normalized=True), want_x)
+        run("stft512_nocenter_two", lambda x, w: F.stft(x, 512, 200, window=w, center=False, onesided=False), want_x)
+        run("spec512_p1", lambda x, w: F.spectrogram(x, 512, 128, window=w, power=1.0), want_x)
+    fb = oc.mel_filterbank_for(64, 16000, fft_length=2048).cuda()
+    run("meldb2048", lambda x, w: F.melspectrogram(x, fb, 2048, 512, window=w, to_db=True))
+    # module: a window turned into a parameter
+    mel = tac.Melspectrogram(num_mels=64, sample_rate=16000, fft_length=2048, hop_length=512).cuda()
+    stft_mod = mel[0]
+    del stft_mod._buffers["window"]
+    stft_mod.window = torch.nn.Parameter(g["meldb2048_w"].cuda())
+    x = g["meldb2048_x"].cuda()
+    y = tac.AmplitudeToDb().cuda()(mel(x))
+    (gw,) = torch.autograd.grad(y, [stft_mod.window], g["meldb2048_gy"].cuda())
+    assert rel_err(gw.cpu(), g["meldb2048_gw"]) < REL

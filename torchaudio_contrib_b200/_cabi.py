@@ -67,6 +67,7 @@ SIGNATURES = {
     "tac_melspec_banded_mc_f32": (_int, _STFT_ARGS + [_f32, _ptr, _i64, _int, _int, _f32, _f32, _ptr, _i64, _int, _ptr]),
     "tac_stft_backward_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),
     "tac_stft_backward_f32": (_int, [_ptr, _i64, _i64, _ptr, _int, _int, _int, _int, _int, _int, _ptr, _ptr, _i64, _ptr]),
+    "tac_window_grad_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _int, _int, _int, _int, _ptr, _ptr, _i64, _ptr]),
     "tac_spectrogram_backward_f32": (_int, _STFT_ARGS + [_int, _f32, _ptr, _ptr, _ptr, _i64, _ptr]),
     "tac_filterbank_backward_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _int, _ptr, _ptr]),
     "tac_melspec_backward_workspace_bytes": (_i64, [_i64, _i64, _int, _int, _int]),

@@ -481,6 +481,61 @@ static int pointwise_grid(int64_t n) {
 
 }  // namespace tac
 
+namespace tac {
+
+// ---- gradient w.r.t. the window (round 2) ---------------------------------------------------------------------------
+// X = FFT(x_frame * w * scale): dL/dw[n] = sum over frames of x_padded[start + n] * d[n], d = the frame gradient BEFORE the
+// window multiply.  The caller runs tac_stft_backward_f32 with a window of ones, which leaves scale * d in the frame
+// workspace; this reduces it against the padded waveform.  Two deterministic steps: partial sums over slices of the
+// frames (one thread per window sample, coalesced along n), then the slices in fixed order.
+constexpr int kWgSlices = 64;
+__global__ void __launch_bounds__(256) window_grad_partial_kernel(const float* __restrict__ x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
+                                                                  const float* __restrict__ frames_ws, int64_t frames, int n_fft, int hop, int pad,
+                                                                  int pad_mode, float* __restrict__ partial) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= n_fft) return;
+  const int64_t total = n_seq * frames;
+  const int64_t per = (total + kWgSlices - 1) / kWgSlices;
+  const int64_t g0 = (int64_t)blockIdx.y * per, g1 = (g0 + per < total) ? g0 + per : total;
+  float acc = 0.0f;
+  for (int64_t g = g0; g < g1; ++g) {
+    const int64_t seq = g / frames, t = g - seq * frames;
+    const float xv = fetch_padded(x + seq * seq_stride, t * hop - pad + n, n_samples, pad_mode);
+    acc = fmaf(xv, frames_ws[g * n_fft + n], acc);
+  }
+  partial[(int64_t)blockIdx.y * n_fft + n] = acc;
+}
+__global__ void __launch_bounds__(256) window_grad_final_kernel(const float* __restrict__ partial, int n_fft, float* __restrict__ grad_window) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= n_fft) return;
+  float acc = 0.0f;
+  for (int s = 0; s < kWgSlices; ++s) acc += partial[(int64_t)s * n_fft + n];
+  grad_window[n] = acc;
+}
+
+}  // namespace tac
+
+extern "C" int tac_window_grad_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride, const float* frames_ws, int n_fft,
+                                   int hop, int center, int pad_mode, float* grad_window, void* scratch, int64_t scratch_bytes, void* stream) {
+  using namespace tac;
+  TAC_REQUIRE(grad_window && n_fft >= 2 && hop >= 1 && n_seq >= 0, TAC_ERR_INVALID, "window_grad: bad arguments");
+  const int64_t frames = tac_stft_num_frames(n_samples, n_fft, hop, center);
+  const int blocks = (n_fft + 255) / 256;
+  if (n_seq * frames <= 0) {
+    TAC_CUDA_OK(cudaMemsetAsync(grad_window, 0, sizeof(float) * (size_t)n_fft, as_stream(stream)));
+    return TAC_OK;
+  }
+  TAC_REQUIRE(x && frames_ws, TAC_ERR_INVALID, "window_grad: null pointer");
+  TAC_REQUIRE(scratch && scratch_bytes >= (int64_t)kWgSlices * n_fft * 4, TAC_ERR_WORKSPACE, "window_grad: scratch of %lld bytes needed",
+              (long long)kWgSlices * n_fft * 4);
+  LaunchProbe probe(KIND_STFT, as_stream(stream));
+  window_grad_partial_kernel<<<dim3(blocks, kWgSlices), 256, 0, as_stream(stream)>>>(x, n_seq, n_samples, seq_stride, frames_ws, frames, n_fft, hop,
+                                                                                   center ? n_fft / 2 : 0, pad_mode, static_cast<float*>(scratch));
+  window_grad_final_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(scratch), n_fft, grad_window);
+  TAC_CUDA_OK(cudaGetLastError());
+  return TAC_OK;
+}
+
 extern "C" int64_t tac_stft_backward_workspace_bytes(int64_t n_seq, int64_t n_samples, int n_fft, int hop, int center) {
   if (n_fft <= 0 || hop <= 0 || n_seq <= 0) return 0;
   const int64_t rows = n_seq * tac_stft_num_frames(n_samples, n_fft, hop, center);

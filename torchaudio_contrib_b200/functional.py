@@ -7,8 +7,8 @@ each call enqueues kernels of libtac_b200.so on the current stream.  There is no
 
 Autograd: the signal path (stft, complex_norm, apply_filterbank, amplitude_to_db, spectrogram, melspectrogram,
 db_to_amplitude, magphase / angle, float-input mu_law_decoding) is differentiated by hand-written adjoint kernels,
-and the `filterbank` argument gets its gradient too (a learnable filterbank).  What is not differentiated raises
-instead of silently detaching: a `window` that requires grad (whether or not the signal does), `mu_law_encoding`
+and the `filterbank` and `window` arguments get their gradients too (a learnable filterbank / window).  What is not differentiated raises
+instead of silently detaching: `mu_law_encoding`
 inputs that require grad, float64 inputs (forward only, except `phase_vocoder`) and `fft_length`s that are not a power
 of two.  `phase_vocoder` is differentiated w.r.t. the spectrogram by its own gather kernel.
 """
@@ -38,8 +38,8 @@ def _wants_grad(t):
 
 def _no_param_grad(t, name):
     if isinstance(t, torch.Tensor) and torch.is_grad_enabled() and t.requires_grad:
-        raise RuntimeError("%s requires grad: the B200 backward kernels differentiate w.r.t. the signal and the "
-                           "filterbank; the window is a constant (a buffer in the reference's layers)" % name)
+        raise RuntimeError("%s requires grad, but it is a constant on this path (the adjoint kernels differentiate w.r.t. the "
+                           "signal, the filterbank and the float32 window)" % name)
 
 
 def _forward_only(t, name):
@@ -119,11 +119,12 @@ def stft(waveforms, fft_length, hop_length=None, win_length=None, window=None,
     kernels of csrc/f64_path.cu (forward only).  Unlike the reference, a missing `window` is created
     on the input's device.  The result is a contiguous tensor of the reference's logical shape.
     """
-    _no_param_grad(window, "stft: window")
     if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:
+        _no_param_grad(window, "stft (float64): window")
         return _f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided)
-    if _wants_grad(waveforms):
-        return _StftFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided))
+    if _wants_grad(waveforms) or _wants_grad(window):
+        return _StftFn.apply(waveforms, window if _wants_grad(window) else None,
+                             (fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided))
     x = _as_f32_cuda(waveforms, "waveforms")
     hop, lead, flat, frames = _stft_geometry(x, fft_length, hop_length, center)
     win = _frame_window(window, win_length, fft_length, x.device)
@@ -140,10 +141,12 @@ def spectrogram(waveforms, fft_length, hop_length=None, win_length=None, window=
                 pad_mode='reflect', normalized=False, onesided=True, power=1.):
     """`Spectrogram(...)(x)` in one kernel: stft then `|.|^power` (layers.py:294-304), the complex
     spectrum never reaches HBM.  Returns `(*, channel, num_freqs, frames)`."""
-    _no_param_grad(window, "spectrogram: window")
     if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:
+        _no_param_grad(window, "spectrogram (float64): window")
         return _f64.complex_norm(_f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized,
                                            onesided), float(power))
+    if _wants_grad(window):        # a learnable window: the stages, each with its own adjoint kernels (the fused adjoint treats it as a constant)
+        return complex_norm(stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided), power)
     if _wants_grad(waveforms):
         return _SpectrogramFn.apply(waveforms, (fft_length, hop_length, win_length, window, center, pad_mode, normalized,
                                                 onesided, power))
@@ -542,8 +545,13 @@ def melspectrogram(waveforms, filterbank, fft_length, hop_length=None, win_lengt
     `matmul(...).transpose(-2, -1)` (functional.py:183-184; a frame's bands are one 512-byte store);
     `layout="contiguous"` returns a contiguous `(*, num_bands, frames)` tensor (4-byte stores, ~9 % slower
     at BASELINE config 2).  The two-kernel path always returns a contiguous tensor."""
-    _no_param_grad(window, "melspectrogram: window")
+    if _wants_grad(window) and not (isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64):
+        # a learnable window: the stages, each with its own adjoint kernels; contiguous (*, bands, frames) result
+        spec = complex_norm(stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized, True), power)
+        mel = apply_filterbank(spec, filterbank, _cache=_cache)
+        return amplitude_to_db(mel, ref, amin) if to_db else mel
     if isinstance(waveforms, torch.Tensor) and waveforms.dtype == torch.float64:     # the stages, in double (csrc/f64_path.cu)
+        _no_param_grad(window, "melspectrogram (float64): window")
         spec = _f64.complex_norm(_f64.stft(waveforms, fft_length, hop_length, win_length, window, center, pad_mode, normalized,
                                            True), float(power))
         mel = _f64.apply_filterbank(spec, filterbank)
@@ -631,18 +639,64 @@ def _stft_backward_call(x_or_none, grad_out, shape, fft_length, hop_length, win_
     return gx.reshape(shape)
 
 
+def _window_grad_call(x, grad_out, shape, fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided):
+    """dL/d window of `stft` (functional.py:93-107 under autograd): the frame gradients before the window multiply
+    (tac_stft_backward_f32 run with a window of ones leaves them, times the normalisation, in its workspace), reduced
+    against the padded waveform by tac_window_grad_f32; returned in the window's own shape (win_length) and dtype."""
+    device = grad_out.device
+    n_samples = int(shape[-1])
+    n_seq = 1
+    for d in shape[:-1]:
+        n_seq *= int(d)
+    hop = fft_length // 4 if hop_length is None else int(hop_length)
+    g = _grad_f32(grad_out).contiguous()
+    flat = x.reshape(-1, n_samples)
+    lib = _cabi.lib()
+    ones = torch.ones(fft_length, dtype=torch.float32, device=device)
+    gx = torch.empty((n_seq, n_samples), dtype=torch.float32, device=device)           # by-product, discarded
+    ws_bytes = int(lib.tac_stft_backward_workspace_bytes(n_seq, n_samples, int(fft_length), hop, int(bool(center))))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)
+    scratch = torch.empty(256 * int(fft_length), dtype=torch.uint8, device=device)
+    gw = torch.empty(fft_length, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _cabi.check(lib.tac_stft_backward_f32(
+            _cabi.ptr(g), n_seq, n_samples, _cabi.ptr(ones), int(fft_length), hop, int(bool(center)),
+            _cabi.PAD_MODES[pad_mode], int(bool(normalized)), int(bool(onesided)), _cabi.ptr(gx), _cabi.ptr(ws), ws_bytes,
+            _cabi.stream_ptr(device)))
+        _cabi.check(lib.tac_window_grad_f32(
+            _cabi.ptr(flat), n_seq, n_samples, flat.stride(0) if n_seq > 1 else n_samples, _cabi.ptr(ws), int(fft_length), hop,
+            int(bool(center)), _cabi.PAD_MODES[pad_mode], _cabi.ptr(gw), _cabi.ptr(scratch), scratch.numel(), _cabi.stream_ptr(device)))
+    wl = fft_length if win_length is None else int(win_length)
+    left = (fft_length - wl) // 2                                  # the window sits in the middle of the frame (_frame_window)
+    return gw[left:left + wl].to(device=window.device, dtype=window.dtype)
+
+
 class _StftFn(torch.autograd.Function):
+    """`window_param` is the window when it requires grad (a learnable window), else None."""
+
     @staticmethod
-    def forward(ctx, waveforms, args):
+    def forward(ctx, waveforms, window_param, args):
         ctx.args, ctx.shape, ctx.in_dtype = args, tuple(waveforms.shape), waveforms.dtype
-        return stft(waveforms.detach(), *args)
+        ctx.has_window = window_param is not None
+        fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided = args
+        if ctx.has_window:
+            ctx.save_for_backward(_as_f32_cuda(waveforms.detach(), "waveforms"))
+        ctx.args = (fft_length, hop_length, win_length, window.detach() if isinstance(window, torch.Tensor) else window, center,
+                    pad_mode, normalized, onesided)
+        return stft(waveforms.detach(), *ctx.args)
 
     @staticmethod
     def backward(ctx, grad_out):
         fft_length, hop_length, win_length, window, center, pad_mode, normalized, onesided = ctx.args
-        gx = _stft_backward_call(None, grad_out, ctx.shape, fft_length, hop_length, win_length, window, center, pad_mode,
-                                 normalized, onesided, None)
-        return gx.to(ctx.in_dtype), None
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = _stft_backward_call(None, grad_out, ctx.shape, fft_length, hop_length, win_length, window, center, pad_mode,
+                                     normalized, onesided, None).to(ctx.in_dtype)
+        if ctx.has_window and ctx.needs_input_grad[1]:
+            (x,) = ctx.saved_tensors
+            gw = _window_grad_call(x, grad_out, ctx.shape, fft_length, hop_length, win_length, window, center, pad_mode,
+                                   normalized, onesided)
+        return gx, gw, None
 
 
 class _SpectrogramFn(torch.autograd.Function):

@@ -109,36 +109,17 @@ def test_multicast_gather_two_gpus(layout, to_db):
     assert results == [(0, True), (1, True)]
 
 
-def test_multicast_gather_single_rank():
-    """world_size 1: a multicast object with one device -- allocation, binding, the multimem stores of the mel kernel and
-    the flag barrier run on a single-GPU box; result identical to the plain call."""
+def test_multicast_gather_single_rank_is_refused():
+    """The driver refuses a multicast object with one device (cuMulticastCreate: invalid argument): the class says so
+    up front instead of surfacing a driver error."""
     import torch.distributed as dist
-    import torchaudio_contrib_b200 as tac
-    from torchaudio_contrib_b200.distributed import MulticastGatheredOutput, multicast_supported
-    if not multicast_supported(0):
-        pytest.skip("device cannot join a multicast object")
+    from torchaudio_contrib_b200.distributed import MulticastGatheredOutput
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(_free_port())
     dist.init_process_group("gloo", rank=0, world_size=1)
     try:
-        torch.manual_seed(13)
-        dev = torch.device("cuda", 0)
-        x = torch.randn(3, 2, 20000, device=dev)
-        fb = tac.MelFilterbank(num_freqs=1025, num_mels=128, sample_rate=16000).get_filterbank()
-        for layout in ("reference", "contiguous"):
-            prep = tac.PreparedMelspectrogram(x.shape, dev, fb, 2048, 512, to_db=True, layout=layout)
-            try:
-                buf = MulticastGatheredOutput(prep.out_shape, dev)
-            except RuntimeError as exc:                              # a one-device object is refused by some drivers
-                pytest.skip("single-device multicast object not available: %s" % exc)
-            for _ in range(2):
-                buf.tensor.fill_(float("nan"))
-                got = prep.gather_into(x, buf)
-                buf.wait()
-                want = prep(x, prep.empty_output())
-                assert got.shape == want.shape and got.stride() == want.stride()
-                assert torch.equal(got, want)
-            buf.close()
+        with pytest.raises(NotImplementedError):
+            MulticastGatheredOutput((2, 1, 10, 128), torch.device("cuda", 0))
     finally:
         dist.destroy_process_group()
 

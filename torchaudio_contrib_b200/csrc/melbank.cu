@@ -130,7 +130,7 @@ constexpr int kMbGroup = 2;                  // slices per stage
 template <int SRC>
 __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  __shared__ uint64_t s_full[kMbMaxStages], s_a_ready[kMbMaxStages], s_empty[kMbMaxStages], s_accum;
+  __shared__ uint64_t s_full[kMbMaxStages], s_a_ready[kMbMaxStages], s_empty[kMbMaxStages], s_accum, s_zeroed;
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) FbPlanChunk s_chunks[kMbMaxChunks + kMbGroup];   // slice table (global reads cost ~500 cycles per step)
 
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_accum, 1);
+    mbar_init(&s_zeroed, kMbProducerWarps + 1);
     fence_mbar_init();
   }
   if (warp == kMbProducerWarps + 1) {
@@ -179,11 +180,16 @@ __global__ void __launch_bounds__(kMbThreads, 1) melbank_kernel(const MelbankPar
   if (tid == 0) MB_TRACE(3, 0);
 
   // Per tile the accumulator is zeroed first (blocks of different K slices touch different column ranges, so
-  // every MMA accumulates -- there is no single "first" MMA per column); producers and the MMA warp meet on
-  // named barrier 1 for that, the loader warp never waits for it.
+  // every MMA accumulates -- there is no single "first" MMA per column); producers and the MMA warp meet on an
+  // mbarrier for that (one arrival per warp, phase = tile parity), the loader warp never waits for it.  (Round 1 used
+  // named barrier 1 with a partial thread count here, which compute-sanitizer's synccheck reports as divergence.)
+  uint32_t zeroed_parity = 0;
   auto accumulator_ready = [&]() {
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"n"((kMbProducerWarps + 1) * 32) : "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_zeroed);
+    mbar_wait(&s_zeroed, zeroed_parity);
+    zeroed_parity ^= 1u;
     tc_fence_after();
   };
 

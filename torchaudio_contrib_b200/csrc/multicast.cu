@@ -150,6 +150,7 @@ extern "C" int tac_mc_supported(int* supported) {
 extern "C" int tac_mc_create(int64_t bytes, int n_devices, void** obj, int* fd_out) {
   using namespace tac;
   TAC_REQUIRE(obj && fd_out, TAC_ERR_INVALID, "mc_create: null argument");
+  TAC_REQUIRE(n_devices >= 2, TAC_ERR_UNSUPPORTED, "mc_create: a multicast object needs at least two devices (the driver refuses one)");
   McObject* o = nullptr;
   int rc = mc_begin(bytes, n_devices, &o);
   if (rc != TAC_OK) return rc;

@@ -280,6 +280,9 @@ class MulticastGatheredOutput(object):
             n *= d
         lib = _cabi.lib()
         self._obj = None
+        if self.world < 2:
+            raise NotImplementedError("MulticastGatheredOutput: a multicast object needs at least two devices "
+                                      "(use PeerGatheredOutput, or no gather, on one GPU)")
         oks = [None] * self.world
         dist.all_gather_object(oks, multicast_supported(self.device), group=group)
         if not all(oks):

@@ -32,3 +32,17 @@ with torch.no_grad():
           % (timeit(lambda: cn(z)), timeit(lambda: fb(p)), timeit(lambda: tac.amplitude_to_db(p))))
     chain = torch.nn.Sequential(st, cn, fb)
     print("unfused chain (plain nn.Sequential) %.3f ms" % timeit(lambda: chain(x)))
+    # round 2: sizes that are not a power of two (direct-DFT kernel), the dense-filterbank path, double tensors
+    for fft, hop in ((400, 160), (1200, 300), (441, 110)):
+        frames = 64 * (1 + 160000 // hop)
+        sp = tac.Spectrogram(fft, hop, power=2.0).cuda()
+        mel = tac.Melspectrogram(num_mels=80, sample_rate=16000, fft_length=fft, hop_length=hop).cuda()
+        t2, t3 = timeit(lambda: sp(x), 5), timeit(lambda: mel(x), 5)
+        print("fft %4d hop %4d frames %7d | spectrogram %.3f ms %.2e f/s | mel(80) %.3f ms %.2e f/s   (direct DFT)"
+              % (fft, hop, frames, t2, frames / t2 * 1e3, t3, frames / t3 * 1e3))
+    dense = torch.randn(1025, 128, device="cuda").abs()
+    t = timeit(lambda: tac.functional.melspectrogram(x, dense, 2048, 512))
+    print("dense 1025 x 128 filterbank, fft 2048 (K1 -> K2, tcgen05): %.3f ms %.2e f/s" % (t, 64 * 313 / t * 1e3))
+    xd = x[:8].double()
+    t = timeit(lambda: tac.stft(xd, 512, 128), 3)
+    print("float64 stft 512/128 on (8,1,160000): %.3f ms" % t)

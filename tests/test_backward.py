@@ -200,12 +200,19 @@ def test_backward_large_shape_linearity(tac):
 
 @pytest.mark.gpu
 def test_no_grad_paths_still_refuse_silent_detach(tac):
+    """What has no adjoint kernel raises instead of silently detaching: mu_law_encoding (integer output), phase_advance,
+    double inputs of the signal path, fft lengths that are not a power of two."""
     x = torch.randn(2, 1, 4000, device="cuda", requires_grad=True)
-    z = tac.stft(x.detach(), 512, 128).requires_grad_(True)
+    z = tac.stft(x.detach(), 512, 128)
+    adv = torch.linspace(0, 3.14159 * 128, 257, device="cuda")[..., None]
     with pytest.raises(RuntimeError):
-        tac.phase_vocoder(z, 1.3, torch.linspace(0, 3.14159 * 128, 257, device="cuda")[..., None])
+        tac.phase_vocoder(z, 1.3, adv.requires_grad_(True))
     with pytest.raises(RuntimeError):
         tac.mu_law_encoding(x)
+    with pytest.raises(NotImplementedError):
+        tac.stft(x.double(), 512, 128)
+    with pytest.raises(NotImplementedError):
+        tac.stft(x, 400, 160).sum().backward()
 
 
 @pytest.mark.gpu

@@ -854,63 +854,90 @@ __global__ void __launch_bounds__(kGenThreads) stft_generic_kernel(const StftPar
 }
 
 // ---------------------------------------------------------------------------------------------
-// any other n_fft (not a power of two; e.g. 400 = 25 ms at 16 kHz, 1200, 441): direct DFT, one CTA per group of F
-// frames.  The reference passes any fft_length to torch.stft (functional.py:99); this is the correct-first path for
-// the sizes the register / Stockham kernels do not cover: N (N/2 + 1) complex multiply-adds per frame from a
-// shared-memory table of exp(-2 pi i j / N) built in double precision, index (k n) mod N kept incrementally (exact),
-// F frames per pass so a table read serves F multiply-adds.  fp32 accumulation over N terms: ~sqrt(N) ulp.
+// any other n_fft (not a power of two; e.g. 400 = 25 ms at 16 kHz, 1200, 441): direct DFT, one CTA per group of G frames.
+// The reference passes any fft_length to torch.stft (functional.py:99); this is the path for the sizes the register /
+// Stockham kernels do not cover.  Per frame and bin k:
+//     X[k] = x[0] + (-1)^k x[N/2] + sum_{n=1}^{H} (x[n] + x[N-n]) cos(2 pi n k / N) - i (x[n] - x[N-n]) sin(2 pi n k / N),   H = (N-1)/2
+// (the real input folded about N/2: half the multiply-adds).  A thread owns one bin for the G frames of the group: the
+// folded samples (e, o) of the group sit in shared memory as [n][frame] so a 16-byte broadcast load serves two frames, the
+// twiddle exp(-2 pi i n k / N) is read from a double-precision-built table every 16 steps (index n k mod N kept exactly)
+// and rotated by exp(-2 pi i k / N) in between (16 steps: ~1e-6), which keeps the table gathers -- 32 different banks per
+// warp -- off the inner loop.  fp32 accumulation over N/2 terms.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDftThreads = 256;
-static size_t dft_smem_bytes(int n_fft, int f) { return sizeof(float2) * (size_t)n_fft + sizeof(float) * (size_t)n_fft * (1 + f) + 16; }
+constexpr int kDftResync = 16;
+static size_t dft_smem_bytes(int n_fft, int g) {      // table (padded to 16 bytes), folded samples, unpaired samples
+  return sizeof(float2) * (size_t)((n_fft + 1) & ~1) + sizeof(float2) * (size_t)g * (size_t)(n_fft / 2 + 1) + sizeof(float2) * (size_t)g + 64;
+}
 
-template <int F>
+template <int G>
 __global__ void __launch_bounds__(kDftThreads) stft_dft_kernel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int N = p.n_fft, nb = N / 2 + 1;
-  float2* tab = reinterpret_cast<float2*>(smem_raw);
-  float* win = reinterpret_cast<float*>(tab + N);
-  float* xw = win + N;                                   // [F][N]
+  const int N = p.n_fft, nb = N / 2 + 1, H = (N - 1) / 2;
+  const bool even = (N & 1) == 0;
+  float2* tab = reinterpret_cast<float2*>(smem_raw);                   // [N]  (cos, -sin)(2 pi j / N)
+  float2* eo = tab + ((N + 1) & ~1);                                   // [H + 1][G]  (e, o) of n = 1..H (row 0 unused); 16-byte aligned
+  float2* ends = eo + (size_t)(N / 2 + 1) * G;                         // [G]  (x[0], x[N/2] or 0)
   const int tid = threadIdx.x;
   for (int j = tid; j < N; j += kDftThreads) {
     double sn, cs;
     sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
     tab[j] = make_float2((float)cs, (float)sn);
-    win[j] = p.window[j] * p.scale;
   }
   __syncthreads();
-  const int64_t n_groups = (p.g1 - p.g0 + F - 1) / F;
+  const int64_t n_groups = (p.g1 - p.g0 + G - 1) / G;
   for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int64_t gbase = p.g0 + grp * F;
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
+    const int64_t gbase = p.g0 + grp * G;
+    for (int i = tid; i < G * (H + 1); i += kDftThreads) {            // stage: window, fold
+      const int f = i % G, n = i / G;                                  // n = 0: the unpaired samples
       const int64_t g = gbase + f;
+      float2 v = make_float2(0.0f, 0.0f);
       if (g < p.g1) {
         const int64_t seq = g / p.frames, t = g - seq * p.frames, start = t * p.hop - p.pad;
         const float* row = p.x + seq * p.seq_stride;
-        for (int n = tid; n < N; n += kDftThreads) xw[f * N + n] = fetch_padded(row, start + n, p.n_samples, p.pad_mode) * win[n];
-      } else {
-        for (int n = tid; n < N; n += kDftThreads) xw[f * N + n] = 0.0f;
+        if (n == 0) {
+          v.x = fetch_padded(row, start, p.n_samples, p.pad_mode) * (p.window[0] * p.scale);
+          v.y = even ? fetch_padded(row, start + N / 2, p.n_samples, p.pad_mode) * (p.window[N / 2] * p.scale) : 0.0f;
+        } else {
+          const float a = fetch_padded(row, start + n, p.n_samples, p.pad_mode) * (p.window[n] * p.scale);
+          const float b = fetch_padded(row, start + N - n, p.n_samples, p.pad_mode) * (p.window[N - n] * p.scale);
+          v = make_float2(a + b, a - b);
+        }
       }
+      if (n == 0) ends[f] = v; else eo[(size_t)n * G + f] = v;
     }
     __syncthreads();
     for (int k = tid; k < nb; k += kDftThreads) {
-      float re[F], im[F];
+      float re[G], im[G];
 #pragma unroll
-      for (int f = 0; f < F; ++f) re[f] = im[f] = 0.0f;
-      int idx = 0;
-      for (int n = 0; n < N; ++n) {
-        const float2 w = tab[idx];
+      for (int f = 0; f < G; ++f) {
+        const float2 e = ends[f];
+        re[f] = e.x + ((k & 1) ? -e.y : e.y);
+        im[f] = 0.0f;
+      }
+      const float2 rot = tab[k];                                       // exp(-2 pi i k / N)
+      int idx = k;                                                     // (n k) mod N at n = 1
+      const int step = (int)(((int64_t)kDftResync * k) % N);
+      for (int n0 = 1; n0 <= H; n0 += kDftResync) {
+        float2 w = tab[idx];
+        const int n1 = min(n0 + kDftResync, H + 1);
+        for (int n = n0; n < n1; ++n) {
+          const float4* row4 = reinterpret_cast<const float4*>(eo + (size_t)n * G);
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          const float v = xw[f * N + n];
-          re[f] = fmaf(v, w.x, re[f]);
-          im[f] = fmaf(v, w.y, im[f]);
+          for (int f2 = 0; f2 < G / 2; ++f2) {
+            const float4 v = row4[f2];                                 // (e, o) of frames 2 f2, 2 f2 + 1
+            re[2 * f2] = fmaf(v.x, w.x, re[2 * f2]);
+            im[2 * f2] = fmaf(v.y, w.y, im[2 * f2]);
+            re[2 * f2 + 1] = fmaf(v.z, w.x, re[2 * f2 + 1]);
+            im[2 * f2 + 1] = fmaf(v.w, w.y, im[2 * f2 + 1]);
+          }
+          w = make_float2(fmaf(w.x, rot.x, -w.y * rot.y), fmaf(w.x, rot.y, w.y * rot.x));
         }
-        idx += k;
+        idx += step;
         idx -= (idx >= N) ? N : 0;
       }
 #pragma unroll
-      for (int f = 0; f < F; ++f) {
+      for (int f = 0; f < G; ++f) {
         const int64_t g = gbase + f;
         if (g >= p.g1) continue;
         const int64_t seq = g / p.frames, t = g - seq * p.frames;
@@ -920,8 +947,7 @@ __global__ void __launch_bounds__(kDftThreads) stft_dft_kernel(const StftParams 
       }
     }
     if (p.out_mode == OUT_POWER_ROWS) {
-#pragma unroll
-      for (int f = 0; f < F; ++f) {
+      for (int f = 0; f < G; ++f) {
         const int64_t g = gbase + f;
         if (g < p.g1)
           for (int k = p.bins + tid; k < p.kpad; k += kDftThreads) p.out[power_tile_index(g - p.g0, k, p.kpad)] = 0.0f;
@@ -933,13 +959,13 @@ __global__ void __launch_bounds__(kDftThreads) stft_dft_kernel(const StftParams 
 
 static int launch_stft_dft(const StftParams& p, cudaStream_t stream) {
   const int64_t n_frames = p.g1 - p.g0;
-  const int f = p.n_fft <= 2048 ? 4 : 1;
-  const size_t smem = dft_smem_bytes(p.n_fft, f);
-  auto k = f == 4 ? stft_dft_kernel<4> : stft_dft_kernel<1>;
+  const int g = p.n_fft <= 2048 ? 8 : 2;
+  const size_t smem = dft_smem_bytes(p.n_fft, g);
+  auto k = g == 8 ? stft_dft_kernel<8> : stft_dft_kernel<2>;
   if (smem > 48 * 1024) TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = (int)((200 * 1024) / (smem + 1024));
   const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
-  const int64_t groups = (n_frames + f - 1) / f;
+  const int64_t groups = (n_frames + g - 1) / g;
   const int grid = (int)(groups < cap ? groups : cap);
   LaunchProbe probe(KIND_STFT, stream);
   k<<<grid, kDftThreads, smem, stream>>>(p);

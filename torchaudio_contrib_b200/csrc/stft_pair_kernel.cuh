@@ -71,6 +71,7 @@ constexpr size_t pair_smem_bytes() {
 static_assert(pair_smem_bytes<false>() <= 227 * 1024 && (kPairWarps != 8 || pair_smem_bytes<true>() <= 227 * 1024), "pair kernel exceeds the shared memory of one CTA");
 // tensor-memory columns: per-lane tables, and (TC) one group's pass-2 operands
 constexpr uint32_t kColWin = 0, kColTw1 = 64, kColBand = 128;
+constexpr uint32_t kColPlanCi = 192, kColPlanMeta = 208;   // (!TC) the lane's band-plan constants: 4 x uint4 list offsets, uint4 meta
 constexpr uint32_t kTcColA = 128, kTcColD = 384;          // frame slot f: A_hi at kTcColA + 128 f, A_lo 64 further, D at kTcColD + 64 f
 template <bool TC>
 constexpr uint32_t pair_tmem_cols() { return TC ? 512u : 256u; }
@@ -103,6 +104,22 @@ __device__ __forceinline__ pk pair_power(pk re, pk im, float half_power) {
 
 __device__ __forceinline__ pk pair_shfl(pk x, int src) {
   return mk2(__shfl_sync(0xffffffffu, lo(x), src), __shfl_sync(0xffffffffu, hi(x), src));
+}
+
+// 4 / 16 raw columns of this thread's tensor-memory lane (bit patterns: the band plan's integer constants)
+__device__ __forceinline__ uint4 tmem_ld4_u32(uint32_t taddr) {
+  uint4 r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(taddr) : "memory");
+  tc_wait_ld();
+  return r;
+}
+__device__ __forceinline__ void tmem_st16_u32(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
 }
 
 // 16 columns of this thread's tensor-memory lane
@@ -196,13 +213,12 @@ template <bool PEERS, bool TC>
 __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* stash, uint32_t t_lane, const float4* s_tab, int lane, int64_t off_a,
                                                    int64_t off_b, bool store_b) {
   __syncwarp();
-  uint4 ci[4];
+  // The lane's plan constants: from tensor memory (no global loads in the frame loop, so nothing here depends on L1,
+  // which the warp blocks leave little of); the TC variant has its tensor memory full of operands and reads the plan.
   const bool fast = p.band_fast != 0;
-  if (fast) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ci[j] = __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j);
-  }
-  const uint4 meta = __ldg(reinterpret_cast<const uint4*>(p.band_plan + kBandOffMeta) + lane);
+  uint4 meta;
+  if constexpr (TC) meta = __ldg(reinterpret_cast<const uint4*>(p.band_plan + kBandOffMeta) + lane);
+  else meta = tmem_ld4_u32(t_lane + kColPlanMeta);
   pk pw[32];
 #pragma unroll
   for (int i = 1; i < 32; ++i) {
@@ -270,6 +286,17 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
     }
   };
   if (fast) {
+    uint4 ci[4];
+    if constexpr (TC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ci[j] = __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j);
+    } else {
+      uint32_t raw[16];
+      tmem_ld16_nowait(t_lane + kColPlanCi, raw);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ci[j] = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+    }
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(stash);
     pk acc[4];
 #pragma unroll
@@ -452,6 +479,22 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
         }
       }
       tmem_st16(t_lane + (kind == 0 ? kColWin : (kind == 1 ? kColTw1 : kColBand)) + 16 * c, w);
+    }
+    if constexpr (!TC) {
+      if (third == 0) {                                       // one warp per quadrant: this lane's plan constants
+        uint32_t raw[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 c4 = p.band_fast ? __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+          raw[4 * j] = c4.x; raw[4 * j + 1] = c4.y; raw[4 * j + 2] = c4.z; raw[4 * j + 3] = c4.w;
+        }
+        tmem_st16_u32(t_lane + kColPlanCi, raw);
+        const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(p.band_plan + kBandOffMeta) + lane);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[j] = 0u;
+        raw[0] = m4.x; raw[1] = m4.y; raw[2] = m4.z; raw[3] = m4.w;
+        tmem_st16_u32(t_lane + kColPlanMeta, raw);
+      }
     }
     tc_wait_st();
   }

@@ -2,8 +2,9 @@
 hand-written sm_100a kernels.
 
 Same names, argument meaning and shapes as the reference; every function documents the reference
-lines it stands in for.  Tensors must live on a CUDA device and be float32 (mu-law codes int64):
-each call enqueues kernels of libtac_b200.so on the current stream.  There is no CPU path.
+lines it stands in for.  Tensors must live on a CUDA device and be float32 (the tuned kernels) or float64 (plain double
+kernels, forward only; mu-law codes int64): each call enqueues kernels of libtac_b200.so on the current stream.  There is
+no CPU path.
 
 Autograd: the signal path (stft, complex_norm, apply_filterbank, amplitude_to_db, spectrogram, melspectrogram,
 db_to_amplitude, magphase / angle, float-input mu_law_decoding) is differentiated by hand-written adjoint kernels,
@@ -51,7 +52,8 @@ def _forward_only(t, name):
 def _as_f32_cuda(t, name):
     _cabi.require_cuda(t, name)
     if t.dtype != torch.float32:
-        raise NotImplementedError("%s has dtype %s: the B200 kernels compute in float32 only" % (name, t.dtype))
+        raise NotImplementedError("%s has dtype %s: float32 (tuned kernels) and float64 (csrc/f64_path.cu) are implemented"
+                                  % (name, t.dtype))
     return t.contiguous()
 
 

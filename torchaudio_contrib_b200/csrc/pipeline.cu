@@ -235,7 +235,8 @@ struct tac_pipeline {
   float* d_window;
   void* d_plan;
   int64_t band_handle;                  // non-zero: the one-kernel path applies (n_fft = 2048, two-band matrix)
-  cudaStream_t s_in, s_run, s_out;
+  cudaStream_t s_in, s_in2, s_run, s_out;     // s_in2: second H2D stream, TAC_HOST_H2D_STREAMS=2 alternates the copies (measured
+                                              // slower: 0.905 against 0.859 ms per config-2 step, profiles/r02_e2e_h2d_streams.txt)
   cudaEvent_t ev_in[kHostSlots], ev_run[kHostSlots], ev_out[kHostSlots];
   float* d_x[kHostSlots];
   float* d_out[kHostSlots];
@@ -291,6 +292,7 @@ static int pipeline_build(tac_pipeline* p, const tac_pipeline_config* cfg, const
     if (rc != TAC_OK) return rc;
   }
   TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_in2, cudaStreamNonBlocking));
   TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
   TAC_CUDA_OK(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
   for (int i = 0; i < kHostSlots; ++i) {
@@ -360,14 +362,22 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   if (rc != TAC_OK) return rc;
   const int64_t min_tail = ((int64_t)1 << 20) / (n_samples * 4) + 1;      // sequences in ~1 MB
   int64_t used[kHostSlots] = {0};                                         // slices a slot has carried in this call
+  static int h2d_streams = -1;
+  if (h2d_streams < 0) {
+    const char* e = getenv("TAC_HOST_H2D_STREAMS");
+    h2d_streams = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  int64_t slice_no = 0;
   int slot = 0;
   for (int64_t s0 = 0, ns = 0; s0 < n_seq; s0 += ns, slot = (slot + 1) % kHostSlots) {
     const int64_t left = n_seq - s0;
     ns = left < per ? left : per;
     if (left <= per && left > 2 * min_tail) ns = (left + 1) / 2;
-    if (used[slot]) TAC_CUDA_OK(cudaStreamWaitEvent(p->s_in, p->ev_run[slot], 0));      // slot's input consumed
-    TAC_CUDA_OK(cudaMemcpyAsync(p->d_x[slot], x_host + s0 * n_samples, (size_t)(ns * n_samples * 4), cudaMemcpyHostToDevice, p->s_in));
-    TAC_CUDA_OK(cudaEventRecord(p->ev_in[slot], p->s_in));
+    cudaStream_t sin = (h2d_streams == 2 && (slice_no & 1)) ? p->s_in2 : p->s_in;
+    ++slice_no;
+    if (used[slot]) TAC_CUDA_OK(cudaStreamWaitEvent(sin, p->ev_run[slot], 0));      // slot's input consumed
+    TAC_CUDA_OK(cudaMemcpyAsync(p->d_x[slot], x_host + s0 * n_samples, (size_t)(ns * n_samples * 4), cudaMemcpyHostToDevice, sin));
+    TAC_CUDA_OK(cudaEventRecord(p->ev_in[slot], sin));
     TAC_CUDA_OK(cudaStreamWaitEvent(p->s_run, p->ev_in[slot], 0));
     if (used[slot]) TAC_CUDA_OK(cudaStreamWaitEvent(p->s_run, p->ev_out[slot], 0));     // slot's output copied out
     cudaStream_t st = p->s_run;
@@ -397,6 +407,7 @@ extern "C" int tac_pipeline_run_host(tac_pipeline* p, const float* x_host, int64
   TAC_CUDA_OK(cudaStreamSynchronize(p->s_out));          // every D2H follows its kernel, every kernel its H2D
   TAC_CUDA_OK(cudaStreamSynchronize(p->s_run));
   TAC_CUDA_OK(cudaStreamSynchronize(p->s_in));
+  TAC_CUDA_OK(cudaStreamSynchronize(p->s_in2));
   return TAC_OK;
 }
 
@@ -405,6 +416,7 @@ extern "C" int tac_pipeline_destroy(tac_pipeline* p) {
   if (!p) return TAC_OK;
   cudaSetDevice(p->device);
   if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_in2) cudaStreamDestroy(p->s_in2);
   if (p->s_run) cudaStreamDestroy(p->s_run);
   if (p->s_out) cudaStreamDestroy(p->s_out);
   for (int i = 0; i < kHostSlots; ++i) {

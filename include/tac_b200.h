@@ -48,7 +48,7 @@ int64_t tac_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center);
 /* ---- a1: stft (functional.py:48-113, call site torch.stft :99-107) ---------------------
  * x: (n_seq, n_samples) rows `seq_stride` floats apart.  window: n_fft floats, already
  * centre-padded from win_length (torch.stft semantics).  n_fft: any value in 2..8192 (powers of two
- * on the tuned kernels, everything else on the direct-DFT kernel; the backward entries need a power of two).
+ * on the tuned kernels, everything else on the direct-DFT kernel and its adjoint).
  * out: (n_seq, bins, frames, 2) contiguous, bins = n_fft/2+1 (onesided) or n_fft. */
 int tac_stft_f32(const float* x, int64_t n_seq, int64_t n_samples, int64_t seq_stride,
                  const float* window, int n_fft, int hop, int center, int pad_mode,

@@ -201,7 +201,7 @@ def test_backward_large_shape_linearity(tac):
 @pytest.mark.gpu
 def test_no_grad_paths_still_refuse_silent_detach(tac):
     """What has no adjoint kernel raises instead of silently detaching: mu_law_encoding (integer output), phase_advance,
-    double inputs of the signal path, fft lengths that are not a power of two."""
+    double inputs of the signal path."""
     x = torch.randn(2, 1, 4000, device="cuda", requires_grad=True)
     z = tac.stft(x.detach(), 512, 128)
     adv = torch.linspace(0, 3.14159 * 128, 257, device="cuda")[..., None]
@@ -211,8 +211,8 @@ def test_no_grad_paths_still_refuse_silent_detach(tac):
         tac.mu_law_encoding(x)
     with pytest.raises(NotImplementedError):
         tac.stft(x.double(), 512, 128)
-    with pytest.raises(NotImplementedError):
-        tac.stft(x, 400, 160).sum().backward()
+    tac.stft(x, 400, 160).sum().backward()                  # sizes that are not a power of two differentiate (direct-DFT adjoint)
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())
 
 
 @pytest.mark.gpu

@@ -192,7 +192,7 @@ def test_stft_vs_f64(tac, shape):
 def test_stft_non_power_of_two(tac, oc, fft, hop):
     """functional.py:99 hands any fft_length to torch.stft; sizes that are not a power of two (400 = 25 ms at 16 kHz, odd
     sizes, tiny ones) run the direct-DFT kernel (csrc/stft.cu stft_dft_kernel).  Complex STFT (one- and two-sided),
-    spectrogram and the mel chain against the oracle; gradients of these sizes are refused, not approximated."""
+    spectrogram and the mel chain against the oracle, and their gradients against the oracle under torch autograd."""
     torch.manual_seed(fft)
     x = torch.randn(2, 2, 12000)
     for kw in (dict(), dict(onesided=False, pad_mode="constant"), dict(center=False, normalized=True)):
@@ -208,9 +208,19 @@ def test_stft_non_power_of_two(tac, oc, fft, hop):
         got = m(dev(x)).cpu()
         want = oc.melspectrogram(x, 40, 16000, to_db=True, fft_length=fft, hop_length=hop)
         assert got.shape == want.shape and (got - want).abs().max().item() < 1e-3
-        xg = dev(x).requires_grad_(True)
-        with pytest.raises(NotImplementedError):
-            tac.Spectrogram(fft_length=fft, hop_length=hop).cuda()(xg).sum().backward()
+    # gradients: the direct-DFT adjoint (csrc/stft_backward.cu stft_dft_backward_kernel) against the oracle under autograd
+    xs = x[:1, :, :3000].contiguous()
+    for fn_t, fn_o in ((lambda t: tac.stft(t, fft, hop), lambda t: oc.stft(t, fft, hop)),
+                       (lambda t: tac.stft(t, fft, hop, onesided=False, pad_mode="constant"), lambda t: oc.stft(t, fft, hop, onesided=False, pad_mode="constant")),
+                       (lambda t: tac.spectrogram(t, fft, hop, power=2.0), lambda t: oc.spectrogram(t, fft, hop, power=2.0)),
+                       (lambda t: tac.spectrogram(t, fft, hop, power=1.0, normalized=True), lambda t: oc.spectrogram(t, fft, hop, power=1.0, normalized=True))):
+        xo = xs.clone().requires_grad_(True)
+        yo = fn_o(xo)
+        gy = torch.randn(yo.shape, generator=torch.Generator().manual_seed(fft + 1))
+        (want,) = torch.autograd.grad(yo, xo, gy)
+        xt = dev(xs).requires_grad_(True)
+        (got,) = torch.autograd.grad(fn_t(xt), xt, dev(gy))
+        assert rel_err(got.cpu(), want) < REL, (fft, rel_err(got.cpu(), want))
 
 
 def test_float64_operators(tac, oc):

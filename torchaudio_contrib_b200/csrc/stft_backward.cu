@@ -144,6 +144,94 @@ __global__ void __launch_bounds__(kBwdThreads) stft_backward_kernel(const StftBw
   }
 }
 
+// ---- any n_fft that is not a power of two: the adjoint of stft_dft_kernel (stft.cu), direct sums -------------------
+// X_k = sum_n xw[n] (c_nk + i s_nk), (c, s) = (cos, -sin)(2 pi n k / N): with (Gr_k, Gi_k) the gradient w.r.t. (Re X_k, Im X_k)
+// of the bins that exist (two-sided outputs folded onto k <= N/2 as in stft_backward_kernel),
+//     dL/d xw[n] = sum_{k=0}^{N/2} Gr_k c_nk + Gi_k s_nk.
+// |X|^p outputs: the spectrum is recomputed by the same direct sum, G_k = g_k p |X_k|^(p-2) X_k.  One CTA per frame,
+// O(N^2) both ways; the table index (n k) mod N is kept incrementally (exact).  Correct-first like the forward kernel.
+static size_t dft_bwd_smem_bytes(int n_fft) {
+  return sizeof(float2) * (size_t)((n_fft + 1) & ~1) + sizeof(float2) * (size_t)(n_fft / 2 + 2) + sizeof(float) * 2 * (size_t)n_fft + 32;
+}
+
+__global__ void __launch_bounds__(kBwdThreads) stft_dft_backward_kernel(const StftBwdParams bp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const StftParams& p = bp.f;
+  const int N = p.n_fft, nb = N / 2 + 1;
+  float2* tab = reinterpret_cast<float2*>(smem_raw);                   // [N] (cos, -sin)(2 pi j / N)
+  float2* spec = tab + ((N + 1) & ~1);                                 // [nb] G_k
+  float* win = reinterpret_cast<float*>(spec + nb + 1);                // [N] window * scale
+  float* xw = win + N;                                                 // [N] windowed samples (power modes)
+  const int tid = threadIdx.x;
+  for (int j = tid; j < N; j += kBwdThreads) {
+    double sn, cs;
+    sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+    tab[j] = make_float2((float)cs, (float)sn);
+    win[j] = p.window[j] * p.scale;
+  }
+  __syncthreads();
+  const int64_t plane = p.frames;
+  for (int64_t g = p.g0 + blockIdx.x; g < p.g1; g += gridDim.x) {
+    const int64_t seq = g / p.frames, t = g - seq * p.frames, start = t * p.hop - p.pad;
+    const int64_t gbase = seq * p.bins * plane + t;
+    if (bp.power_mode >= 0) {
+      const float* row = p.x + seq * p.seq_stride;
+      for (int n = tid; n < N; n += kBwdThreads) xw[n] = fetch_padded(row, start + n, p.n_samples, p.pad_mode) * win[n];
+      __syncthreads();
+      for (int k = tid; k < nb; k += kBwdThreads) {
+        float xr = 0.0f, xi = 0.0f;
+        int idx = 0;
+        for (int n = 0; n < N; ++n) {
+          const float2 w = tab[idx];
+          xr = fmaf(xw[n], w.x, xr);
+          xi = fmaf(xw[n], w.y, xi);
+          idx += k;
+          idx -= (idx >= N) ? N : 0;
+        }
+        if (k == 0 || 2 * k == N) xi = 0.0f;
+        float gk = __ldg(bp.grad_out + gbase + (int64_t)k * plane);
+        if (!p.onesided && k > 0 && 2 * k != N) gk += __ldg(bp.grad_out + gbase + (int64_t)(N - k) * plane);
+        float coef;
+        if (bp.power_mode == 2) {
+          coef = 2.0f * gk;
+        } else {
+          const float n2 = xr * xr + xi * xi;
+          if (n2 > 0.0f) coef = (bp.power_mode == 1) ? gk * rsqrtf(n2) : gk * bp.power * powf(n2, 0.5f * bp.power - 1.0f);
+          else coef = 0.0f;
+        }
+        spec[k] = make_float2(coef * xr, coef * xi);
+      }
+    } else {
+      const float2* go = reinterpret_cast<const float2*>(bp.grad_out);
+      for (int k = tid; k < nb; k += kBwdThreads) {
+        float2 gk = __ldg(go + gbase + (int64_t)k * plane);
+        if (!p.onesided && k > 0 && 2 * k != N) {
+          const float2 gm = __ldg(go + gbase + (int64_t)(N - k) * plane);
+          gk.x += gm.x;
+          gk.y -= gm.y;
+        }
+        spec[k] = gk;
+      }
+    }
+    __syncthreads();
+    float* frow = bp.frames_out + (g - p.g0) * N;
+    for (int n = tid; n < N; n += kBwdThreads) {
+      float acc = 0.0f;
+      int idx = 0;
+      for (int k = 0; k < nb; ++k) {
+        const float2 w = tab[idx];
+        const float2 gk = spec[k];
+        acc = fmaf(gk.x, w.x, acc);
+        acc = fmaf(gk.y, w.y, acc);
+        idx += n;
+        idx -= (idx >= N) ? N : 0;
+      }
+      frow[n] = acc * win[n];
+    }
+    __syncthreads();
+  }
+}
+
 // P(q) = sum over the frames t covering padded position q of frames_out[t][q - t hop]
 __device__ __forceinline__ float ola_padded(const float* __restrict__ fr, int q, int frames, int n_fft, int hop) {
   int t_lo = q - n_fft + 1;
@@ -270,14 +358,17 @@ static int launch_stft_backward(StftBwdParams& bp, float* grad_x, void* workspac
               (long long)backward_workspace_bytes(p));
   TAC_REQUIRE(p.n_seq * 2 < ((int64_t)1 << 31), TAC_ERR_UNSUPPORTED, "stft backward: too many sequences in one call");
   bp.frames_out = static_cast<float*>(workspace);
-  const size_t smem = bwd_smem_bytes(p.n_fft);
-  TAC_CUDA_OK(cudaFuncSetAttribute(stft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool dft = !is_pow2(p.n_fft) || p.n_fft < 32;                 // sizes the Stockham kernel does not cover
+  const size_t smem = dft ? dft_bwd_smem_bytes(p.n_fft) : bwd_smem_bytes(p.n_fft);
+  if (dft) TAC_CUDA_OK(cudaFuncSetAttribute(stft_dft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else TAC_CUDA_OK(cudaFuncSetAttribute(stft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = (int)((200 * 1024) / (smem + 1024));
   const int64_t cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
   const int grid = (int)(n_frames < cap ? n_frames : cap);
   {
     LaunchProbe probe(KIND_STFT, stream);
-    stft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
+    if (dft) stft_dft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
+    else stft_backward_kernel<<<grid, kBwdThreads, smem, stream>>>(bp);
   }
   TAC_CUDA_OK(cudaGetLastError());
   return launch_overlap_add(bp, grad_x, stream);
@@ -552,8 +643,6 @@ extern "C" int tac_stft_backward_f32(const float* grad_out, int64_t n_seq, int64
   const int rc = fill_stft_params(bp.f, grad_x /* placeholder, never read */, n_seq, n_samples, n_samples, window, n_fft, hop,
                                   center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
-  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
-              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   bp.f.x = nullptr;
   bp.grad_out = grad_out;
   bp.power_mode = -1;
@@ -570,8 +659,6 @@ extern "C" int tac_spectrogram_backward_f32(const float* x, int64_t n_seq, int64
   TAC_REQUIRE((grad_out && grad_x) || n_seq == 0, TAC_ERR_INVALID, "spectrogram_backward: null gradient pointer");
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, onesided);
   if (rc != TAC_OK) return rc;
-  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
-              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   bp.grad_out = grad_out;
   bp.power = power;
   bp.power_mode = power == 2.0f ? 2 : (power == 1.0f ? 1 : 0);
@@ -675,8 +762,6 @@ extern "C" int tac_melspec_backward_f32(const float* x, int64_t n_seq, int64_t n
   StftBwdParams bp;
   const int rc = fill_stft_params(bp.f, x, n_seq, n_samples, seq_stride, window, n_fft, hop, center, pad_mode, normalized, 1);
   if (rc != TAC_OK) return rc;
-  TAC_REQUIRE(is_pow2(n_fft) && n_fft >= 32, TAC_ERR_UNSUPPORTED,
-              "stft backward: n_fft=%d -- the adjoint kernels cover powers of two in [32, 8192] only", n_fft);
   StftParams& p = bp.f;
   if (p.n_seq == 0 || p.n_samples == 0) return TAC_OK;
   TAC_REQUIRE(grad_x, TAC_ERR_INVALID, "melspec_backward: null gradient pointer");

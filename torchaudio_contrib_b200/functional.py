@@ -10,8 +10,8 @@ Autograd: the signal path (stft, complex_norm, apply_filterbank, amplitude_to_db
 db_to_amplitude, magphase / angle, float-input mu_law_decoding) is differentiated by hand-written adjoint kernels,
 and the `filterbank` and `window` arguments get their gradients too (a learnable filterbank / window).  What is not differentiated raises
 instead of silently detaching: `mu_law_encoding`
-inputs that require grad, float64 inputs (forward only, except `phase_vocoder`) and `fft_length`s that are not a power
-of two.  `phase_vocoder` is differentiated w.r.t. the spectrogram by its own gather kernel.
+inputs that require grad and float64 inputs (forward only, except `phase_vocoder`).  `phase_vocoder` is differentiated
+w.r.t. the spectrogram by its own gather kernel; every `fft_length` in [2, 8192] differentiates.
 """
 import collections
 import ctypes

@@ -46,6 +46,10 @@ def kernel_model(blob, handle, power_rows, n_bands):
     if fast_off:
         assert fast_off == (OFF_COMB + cmax * pad * 2 + 15) // 16 * 16          # where pipeline.cu expects it
         fast = bp[fast_off:fast_off + 2048].view(np.uint32).reshape(32, 4, 4)
+        # the same lists once more for the frame-major layout: lane l holds the adjacent bands 4 l .. 4 l + 3
+        quad = bp[fast_off + 2048:fast_off + 4096].view(np.uint32).reshape(32, 4, 4)
+        for m in range(128):
+            assert (quad[m // 4, m % 4] == fast[m % 32, m // 32]).all()
     out = np.zeros((power_rows.shape[0], n_bands), dtype=np.float32)
     for f, p in enumerate(power_rows.astype(np.float32)):
         stash = np.full(FLOATS, np.nan, dtype=np.float32)

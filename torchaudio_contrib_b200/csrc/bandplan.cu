@@ -132,6 +132,17 @@ int64_t build_band_plan(const float* fb, int n_bins, int n_bands, unsigned char*
     hdr.reserved = (int32_t)used;
     memcpy(dst, &hdr, sizeof(hdr));
     used += 32 * 16 * 4;
+    // the same lists for the frame-major output layout: lane l sums the four ADJACENT bands 4 l .. 4 l + 3, so a frame's
+    // bands leave the lane as one 16-byte store (512 contiguous bytes per warp instruction)
+    uint32_t* quadp = reinterpret_cast<uint32_t*>(dst + used);
+    for (int l = 0; l < 32; ++l)
+      for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < 4; ++c) {
+          const int b = 4 * l + j;
+          const int idx = (b < n_bands && c < (int)lists[b].size()) ? lists[b][c] : kStashZero;
+          quadp[(l * 4 + j) * 4 + c] = (uint32_t)idx * 4u;
+        }
+    used += 32 * 16 * 4;
   }
   return used;
 }

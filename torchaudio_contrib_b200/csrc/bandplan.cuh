@@ -21,6 +21,7 @@
 //   comb  [cmax][n_bands_pad] uint16   float index into the stash, padded with zero_idx
 //   fast  [32][4][4] uint32  (header.fast_off != 0: <= 128 bands, cmax <= 4) byte offsets into the stash of the
 //                            entries of bands l, l + 32, l + 64, l + 96 for lane l
+//   quad  [32][4][4] uint32  (follows `fast`) the same for bands 4 l .. 4 l + 3: the frame-major layout stores them as one float4
 #pragma once
 
 #include <stdint.h>
@@ -40,6 +41,7 @@ constexpr int kStashEnd31 = 32 * kStashStride + 1;     // end-of-run pair of lan
 constexpr int kStashZero = 1060;                   // a float that is always 0 (padding entries of `comb`)
 constexpr int kStashFloats = 1064;                 // per warp
 constexpr int kBandMaxComb = 16;
+constexpr int kBandFastBytes = 32 * 16 * 4;        // size of the `fast` table; `quad` starts this far behind it
 
 struct BandPlanHeader {
   uint32_t magic;
@@ -51,7 +53,7 @@ constexpr int kBandOffComb = kBandOffMeta + 32 * 16;
 
 static inline int64_t band_plan_capacity(int n_bands) {
   const int64_t pad = ((int64_t)n_bands + 31) / 32 * 32;
-  return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 32 * 16 * 4 + 128;
+  return kBandOffComb + (int64_t)kBandMaxComb * pad * 2 + 2 * 32 * 16 * 4 + 128;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

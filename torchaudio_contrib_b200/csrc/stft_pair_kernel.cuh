@@ -209,9 +209,11 @@ static __device__ __noinline__ void pair_fixup_region(float* region, const float
 
 // Band contraction of both frames' power spectra (stash of float2 pairs) with the two-band plan, dB epilogue, stores.
 // Same walk as band_contract (stft.cu); weights (from tensor memory), masks and list offsets are shared by the frames.
+// quad: the lane's four sums are the ADJACENT bands 4 lane .. 4 lane + 3 (the plan's `quad` table, frame-major output):
+// one 16-byte store per frame instead of four 4-byte stores.
 template <bool PEERS, bool TC>
 __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* stash, uint32_t t_lane, const float4* s_tab, int lane, int64_t off_a,
-                                                   int64_t off_b, bool store_b) {
+                                                   int64_t off_b, bool store_b, bool quad) {
   __syncwarp();
   // The lane's plan constants: from tensor memory (no global loads in the frame loop, so nothing here depends on L1,
   // which the warp blocks leave little of); the TC variant has its tensor memory full of operands and reads the plan.
@@ -289,7 +291,8 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
     uint4 ci[4];
     if constexpr (TC) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ci[j] = __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j);
+      for (int j = 0; j < 4; ++j)
+        ci[j] = __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast + (quad ? kBandFastBytes : 0)) + lane * 4 + j);
     } else {
       uint32_t raw[16];
       tmem_ld16_nowait(t_lane + kColPlanCi, raw);
@@ -305,6 +308,29 @@ __device__ __forceinline__ void band_contract_pair(const StftParams& p, float2* 
       const float2 c = *reinterpret_cast<const float2*>(sb + 2 * ci[j].z);
       const float2 d = (p.band_cmax > 3) ? *reinterpret_cast<const float2*>(sb + 2 * ci[j].w) : make_float2(0.0f, 0.0f);
       acc[j] = ((mk2(a.x, a.y) + mk2(b.x, b.y)) + mk2(c.x, c.y)) + mk2(d.x, d.y);
+    }
+    if (quad) {                                    // n_bands % 4 == 0 and 16-byte aligned rows (checked by the caller)
+      if (4 * lane < p.n_bands) {
+        const float4 ra = make_float4(finish(lo(acc[0])), finish(lo(acc[1])), finish(lo(acc[2])), finish(lo(acc[3])));
+        const float4 rb = make_float4(finish(hi(acc[0])), finish(hi(acc[1])), finish(hi(acc[2])), finish(hi(acc[3])));
+        auto store4 = [&](int64_t off, const float4 r) {
+          const int64_t o = off + 4 * lane;
+          if constexpr (PEERS) {
+            if (p.peer_multicast) {
+              multimem_st_f32x4(p.peer_out[0] + o, r);
+            } else {
+#pragma unroll 1
+              for (int q = 0; q < p.n_peers; ++q) __stcs(reinterpret_cast<float4*>(p.peer_out[q] + o), r);
+            }
+          } else {
+            __stcs(reinterpret_cast<float4*>(p.out + o), r);
+          }
+        };
+        store4(off_a, ra);
+        if (store_b) store4(off_b, rb);
+      }
+      __syncwarp();
+      return;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -375,6 +401,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
   __syncwarp();
 
   const float half_power = 0.5f * p.power;
+  // frame-major output with whole float4 rows: the lane's four bands are adjacent (bandplan.cuh `quad`)
+  bool quad = p.band_fast != 0 && p.out_band_stride == 1 && (p.n_bands & 3) == 0 && (p.out_t_stride & 3) == 0 && (p.out_seq_stride & 3) == 0;
+  if constexpr (PEERS) {
+    for (int q = 0; q < p.n_peers; ++q) quad = quad && (reinterpret_cast<uintptr_t>(p.peer_out[q]) & 15) == 0;
+  } else {
+    quad = quad && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  }
   const uint32_t frames_u = (uint32_t)p.frames;
   const uint64_t pol_stream = l2_policy_evict_first();
   const int hop = p.hop, len = 2048 + hop, n_samples = (int)p.n_samples;
@@ -485,7 +518,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
         uint32_t raw[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 c4 = p.band_fast ? __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast) + lane * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+          const uint4 c4 = p.band_fast ? __ldg(reinterpret_cast<const uint4*>(p.band_plan + p.band_off_fast + (quad ? kBandFastBytes : 0)) + lane * 4 + j)
+                                       : make_uint4(0u, 0u, 0u, 0u);
           raw[4 * j] = c4.x; raw[4 * j + 1] = c4.y; raw[4 * j + 2] = c4.z; raw[4 * j + 3] = c4.w;
         }
         tmem_st16_u32(t_lane + kColPlanCi, raw);
@@ -722,7 +756,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
     {
       const int64_t seq0 = PEERS ? p.peer_seq0 : 0;
       const int64_t off_a = ((int64_t)seq + seq0) * p.out_seq_stride + (int64_t)t_a * p.out_t_stride;
-      band_contract_pair<PEERS, TC>(p, stash, t_lane, s_tab, lane, off_a, off_a + p.out_t_stride, has_b);
+      band_contract_pair<PEERS, TC>(p, stash, t_lane, s_tab, lane, off_a, off_a + p.out_t_stride, has_b, quad);
     }
     }   // valid
     pj = pj_next;

@@ -235,6 +235,10 @@ __device__ __forceinline__ void multimem_st_f32(float* p, float v) {
   asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void multimem_st_f32x4(float* p, const float4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // streaming global accesses that should not pollute L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 v;

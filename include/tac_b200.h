@@ -308,6 +308,15 @@ int tac_mulaw_decode_i64_f64(const int64_t* codes, int64_t n, int n_quantize, co
                              double* out, void* stream);
 int tac_mulaw_encode_f64_i64(const double* x, int64_t n, int n_quantize, int64_t* out, void* stream);
 
+/* ---- harmonic-percussive separation (beta_hpss.py:37-129; a beta module the reference does not export) ----
+ * mag: (n_seq, n_freq, n_time) magnitudes; median filters of `kernel_size` (odd, 3..63) along frequency
+ * (percussive) and time (harmonic) with reflect padding, ^power, soft masks (eps 1e-6) or hard masks
+ * (1.0 / 0.0); out_harm / out_perc = mag * mask (may be NULL with mask_only).  One kernel; medians are
+ * selections, so the result is bit-exact with the reference for power 1 and 2. */
+int tac_hpss_f32(const float* mag, int64_t n_seq, int n_freq, int n_time, int kernel_size, float power,
+                 int hard, int mask_only, float* out_harm, float* out_perc, float* mask_harm,
+                 float* mask_perc, void* stream);
+
 /* ---- host-buffer plugin surface (what a reference-side caller with CPU tensors binds) ---
  * A pipeline owns its device staging buffers, plan, streams and events. */
 typedef struct tac_pipeline tac_pipeline;

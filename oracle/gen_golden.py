@@ -333,6 +333,39 @@ def grads_win(ref, oc):
     print("window-gradient fixtures reproduce under oracle.ref_chain autograd")
 
 
+def hpss_fixtures(ref, oc):
+    """Harmonic-percussive separation (beta_hpss.py) from the UNMODIFIED reference module: soft and hard masks, powers 1 / 2 /
+    0.7, kernel sizes 5 / 17 / 31, an input with a NaN.  `python oracle/gen_golden.py hpss` writes tests/golden/hpss.npz only."""
+    import importlib
+    ref_hpss = importlib.import_module("torchaudio_contrib.beta_hpss")
+    g = torch.Generator().manual_seed(20261020)
+    blob = {}
+    x = torch.rand(2, 2, 40, 50, generator=g) ** 2 * 3.0
+    blob["x"] = x.numpy()
+    for tag, kw in (("k31_p2", dict(kernel_size=31, power=2.0)), ("k17_p1", dict(kernel_size=17, power=1.0)),
+                    ("k5_p07", dict(kernel_size=5, power=0.7)), ("k31_hard", dict(kernel_size=31, power=2.0, hard=True)),
+                    ("k9_maskonly", dict(kernel_size=(9, 9), power=2.0, mask_only=True))):
+        r = ref_hpss.hpss(x, **kw)
+        o = oc.hpss(x, **kw)
+        for i, (a, b) in enumerate(zip(r, o)):
+            if a is None:
+                assert b is None
+                continue
+            _same(a, b, "hpss/%s[%d]" % (tag, i))
+            blob["%s_%d" % (tag, i)] = a.numpy()
+    xn = x.clone()
+    xn[0, 1, 7, 9] = float("nan")
+    r = ref_hpss.hpss(xn, 5, 1.0)
+    o = oc.hpss(xn, 5, 1.0)
+    for i, (a, b) in enumerate(zip(r, o)):
+        assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+        blob["nan_%d" % i] = a.numpy()
+    blob["xn"] = xn.numpy()
+    assert repr(ref_hpss.HPSS(7, 1.0, True, False)) == "HPSS(kernel_size=7, power=1.0, hard=True, mask_only=False)"
+    _save("hpss.npz", **blob)
+    print("hpss fixtures reproduce under oracle.ref_chain")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_chain as oc
@@ -346,6 +379,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads_more":
         grads_more(ref, oc)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "hpss":
+        hpss_fixtures(ref, oc)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "grads_win":
         grads_win(ref, oc)
         return
@@ -353,7 +389,7 @@ def main():
         grads_pv(ref, oc)
         return
     if len(sys.argv) > 1:
-        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more | grads_pv | grads_win]   (no argument: the forward fixtures)")
+        raise SystemExit("usage: gen_golden.py [widen | grads | grads_more | grads_pv | grads_win | hpss]   (no argument: the forward fixtures)")
     g = torch.Generator().manual_seed(20260925)
 
     def randn(*shape):

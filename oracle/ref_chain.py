@@ -17,7 +17,7 @@ __all__ = [
     "stft", "complex_norm", "hertz_to_mel", "mel_to_hertz", "create_mel_filter",
     "apply_filterbank", "amplitude_to_db", "mu_law_encoding", "mu_law_decoding",
     "spectrogram", "melspectrogram", "mel_filterbank_for",
-    "angle", "magphase", "db_to_amplitude", "phase_vocoder",
+    "angle", "magphase", "db_to_amplitude", "phase_vocoder", "hpss",
 ]
 
 _SLANEY_HZ_PER_MEL = 200.0 / 3          # linear region slope   (functional.py:15,37)
@@ -181,3 +181,33 @@ def phase_vocoder(complex_specgrams, rate, phase_advance):
     running = torch.cumsum(dphi, -1)                                          # :268
     mag = frac * mag_hi + (1 - frac) * mag_lo                                 # :270
     return torch.stack([mag * torch.cos(running), mag * torch.sin(running)], dim=-1)   # :272-279
+
+
+def hpss(mag_specgrams, kernel_size=31, power=2.0, hard=False, mask_only=False):
+    """beta_hpss.py:37-129 (a beta module outside the reference's package namespace): median filtering along frequency
+    (percussive) and time (harmonic) of the reflect-padded magnitudes, `^power`, soft (eps 1e-6) or hard masks.
+    (batch, ch, freq, time) -> (harmonic, percussive, mask_harm, mask_perc)."""
+    if isinstance(kernel_size, int):
+        kernel_size = (kernel_size, kernel_size)                             # :100-101
+    k_perc, k_harm = kernel_size
+    pads = (k_perc // 2, k_perc // 2, k_harm // 2, k_harm // 2)               # :103-104 (time by the first size, freq by the second)
+    padded = torch.nn.functional.pad(mag_specgrams, pad=pads, mode='reflect')  # :107
+    perc = torch.empty_like(mag_specgrams)
+    harm = torch.empty_like(mag_specgrams)
+    off_t, off_f = k_harm // 2, k_perc // 2
+    for f in range(perc.shape[2]):                                            # :88-90: window over frequency, time un-padded
+        perc[:, :, f, :] = torch.median(padded[:, :, f:f + k_perc, off_t:-off_t], dim=2)[0]
+    for t in range(harm.shape[3]):                                            # :84-86: window over time, frequency un-padded
+        harm[:, :, :, t] = torch.median(padded[:, :, off_f:-off_f, t:t + k_harm], dim=3)[0]
+    if power != 1.0:                                                          # :94-95
+        perc.pow_(power)
+        harm.pow_(power)
+    eps = 1e-6                                                                # :97
+    if hard:                                                                  # :116-118
+        mask_harm, mask_perc = harm > perc, harm < perc
+    else:                                                                     # :120-121
+        mask_harm = (harm + eps) / (harm + perc + eps)
+        mask_perc = (perc + eps) / (harm + perc + eps)
+    if mask_only:                                                             # :123-124
+        return None, None, mask_harm, mask_perc
+    return mag_specgrams * mask_harm, mag_specgrams * mask_perc, mask_harm, mask_perc   # :126

@@ -898,3 +898,45 @@ def test_cuda_graph_capture_and_replay(tac, oc):
             assert torch.equal(got, eager)
         want = oc.melspectrogram(x.cpu(), 64, 16000, to_db=True, fft_length=fft, hop_length=hop)
         assert (got.cpu() - want).abs().max().item() < 1e-3
+
+
+def test_hpss_golden(tac, oc):
+    """beta_hpss.py:37-129 (unexported beta module of the reference): medians are selections, so harmonic / percussive
+    parts and masks are bit-exact for powers 1 and 2 (soft and hard masks, mask_only, several kernel sizes); a general
+    power goes through the device powf (1e-6); a NaN in a window gives NaN like torch.median; module repr and the
+    reference's failure modes (kernel halves that differ, padding not smaller than the axis)."""
+    from torchaudio_contrib_b200.beta_hpss import HPSS, hpss
+    g = golden("hpss.npz")
+    x = dev(g["x"])
+    cases = {"k31_p2": dict(kernel_size=31, power=2.0), "k17_p1": dict(kernel_size=17, power=1.0),
+             "k31_hard": dict(kernel_size=31, power=2.0, hard=True), "k9_maskonly": dict(kernel_size=(9, 9), power=2.0, mask_only=True)}
+    for tag, kw in cases.items():
+        out = hpss(x, **kw)
+        assert len(out) == 4
+        for i, o in enumerate(out):
+            if o is None:
+                assert "%s_%d" % (tag, i) not in g
+                continue
+            want = g["%s_%d" % (tag, i)]
+            assert o.dtype == want.dtype and torch.equal(o.cpu(), want), (tag, i)
+    out = HPSS(kernel_size=5, power=0.7).cuda()(x)
+    for i, o in enumerate(out):
+        assert torch.allclose(o.cpu(), g["k5_p07_%d" % i], rtol=2e-6, atol=1e-7), i
+    out = hpss(dev(g["xn"]), 5, 1.0)
+    for i, o in enumerate(out):
+        want = g["nan_%d" % i]
+        assert torch.equal(torch.isnan(o.cpu()), torch.isnan(want)) and torch.equal(torch.nan_to_num(o.cpu()), torch.nan_to_num(want)), i
+    assert repr(HPSS(7, 1.0, True, False)) == "HPSS(kernel_size=7, power=1.0, hard=True, mask_only=False)"
+    # a larger, non-square case against the oracle, kernel 63 (the widest window built)
+    torch.manual_seed(97)
+    big = torch.rand(3, 1, 257, 130) * 5.0
+    for kw in (dict(kernel_size=63, power=2.0), dict(kernel_size=3, power=1.0, hard=True)):
+        got, want = hpss(dev(big), **kw), oc.hpss(big, **kw)
+        for a, b in zip(got, want):
+            assert torch.equal(a.cpu(), b)
+    with pytest.raises(RuntimeError):
+        hpss(x, (31, 5))                                           # the reference's slices only fit when both halves agree
+    with pytest.raises(RuntimeError):
+        hpss(dev(torch.rand(1, 1, 10, 50)), 31)                    # reflect padding 15 >= 10 bins
+    with pytest.raises(TypeError):
+        hpss(x, 31.0)

@@ -171,3 +171,18 @@ def test_phase_vocoder_fixtures(tag, rate):
     lib = f64_chain.phase_vocoder(z[..., 0] + 1j * z[..., 1], rate, hop)
     got = y64[0, 1].numpy()
     assert np.allclose(got[..., 0] + 1j * got[..., 1], lib, atol=1e-7)
+
+
+def test_hpss_fixtures_bit_exact():
+    """oracle.ref_chain.hpss against tests/golden/hpss.npz (oracle/gen_golden.py hpss: the unmodified beta_hpss.py)."""
+    g = golden("hpss.npz")
+    cases = {"k31_p2": dict(kernel_size=31, power=2.0), "k17_p1": dict(kernel_size=17, power=1.0),
+             "k5_p07": dict(kernel_size=5, power=0.7), "k31_hard": dict(kernel_size=31, power=2.0, hard=True),
+             "k9_maskonly": dict(kernel_size=(9, 9), power=2.0, mask_only=True)}
+    for tag, kw in cases.items():
+        out = oc.hpss(g["x"], **kw)
+        for i, o in enumerate(out):
+            if o is None:
+                assert "%s_%d" % (tag, i) not in g
+            else:
+                assert torch.equal(o, g["%s_%d" % (tag, i)]), (tag, i)

@@ -86,6 +86,7 @@ SIGNATURES = {
     "tac_apply_filterbank_f64": (_int, [_ptr, _ptr, _i64, _i64, _int, _int, _ptr, _ptr]),
     "tac_mulaw_decode_i64_f64": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr]),
     "tac_mulaw_encode_f64_i64": (_int, [_ptr, _i64, _int, _ptr, _ptr]),
+    "tac_hpss_f32": (_int, [_ptr, _i64, _int, _int, _int, _f32, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "tac_pipeline_create": (_int, [_ptr, _ptr, _ptr, _c.POINTER(_ptr)]),
     "tac_pipeline_run_host": (_int, [_ptr, _ptr, _i64, _i64, _ptr]),
     "tac_pipeline_destroy": (_int, [_ptr]),

@@ -38,6 +38,10 @@ zg = z.clone().requires_grad_(True)
 tac.phase_vocoder(zg, 0.8, torch.linspace(0, 3.14159265 * 128, 257, device=dev)[..., None]).sum().backward()
 wg = torch.hann_window(512, device=dev).requires_grad_(True)
 tac.stft(x, 512, 128, window=wg).sum().backward()
+xs = x[:1, :1, :4000].clone().requires_grad_(True)
+tac.spectrogram(xs, 400, 160, power=1.0).sum().backward()                           # direct-DFT kernel and its adjoint
+from torchaudio_contrib_b200.beta_hpss import hpss
+hp_out = hpss(tac.Spectrogram(512, 128).to(dev)(x), 31)                              # median filters
 import torch.distributed as dist
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
 dist.init_process_group("gloo", rank=0, world_size=1)

@@ -372,6 +372,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
   // TC: the B images behind the warp blocks, on a 1 KB boundary (swizzle atoms)
   const uint32_t b_base = (smem_u32(s_blocks + (size_t)kPairWarps * kWarpBytes) + 1023u) & ~1023u;
 
+  // Programmatic dependent launch: the next launch of this kernel in the stream (launched with the stream-serialization
+  // attribute, see launch_stft2048_pair_t) may be scheduled while this grid still runs -- its CTAs take an SM as soon as
+  // this grid's CTA there has exited and do their set-up (tensor-memory allocation, barriers, twiddles) before
+  // `griddepcontrol.wait`, which holds them until this grid has completed and its stores are visible.  Hides the launch
+  // latency and the set-up behind the previous launch's tail; a no-op for any other neighbour in the stream.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int group = warp >> 2;                                 // TC: warps 0-3 / 4-7, one per lane quadrant each
   static_assert(!TC || kPairWarps == 8, "the tensor-core pass is laid out for two groups of four warps");
@@ -440,9 +446,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
       if (f.bulk) bulk_g2s_hint(region + f.lo, p.x + (int64_t)sq * p.seq_stride + (start + f.lo), bytes, bar, pol_stream);
     }
   };
-  if (pj < chunk1) stage_bulk(seq, j);
-
-  // ---- per-lane tables into tensor memory (one warp per lane quadrant writes, all warps of the quadrant read) ----
+  // ---- set-up that reads no global memory, then the dependency wait, then the first bulk copy ----
   if (warp == 0) {
     tmem_alloc(s_tmem, pair_tmem_cols<TC>());
     tmem_relinquish();
@@ -452,6 +456,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
     sincospif(-2.0f * (float)tid / 2048.0f, &sn, &cs);
     s_twb[tid] = make_float2(cs, sn);
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");           // everything before us in the stream has completed
+  if (pj < chunk1) stage_bulk(seq, j);
+
+  // ---- per-lane tables into tensor memory (one warp per lane quadrant writes, all warps of the quadrant read) ----
   if constexpr (TC) {
     // B images: element (k, n) of the K slab k / 32 at row n, 16-byte column (k % 32) / 4 of the swizzled tile
     for (int idx = tid; idx < 64 * 64; idx += kPairThreads) {
@@ -771,6 +779,14 @@ __global__ void __launch_bounds__(kPairThreads, 1) stft2048_pair_kernel(const St
 }
 
 bool stft2048_pair_applies(const StftParams& p);
+static inline bool pair_pdl_enabled() {                       // TAC_PAIR_PDL=0 switches the programmatic dependent launch off (A/B timing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAC_PAIR_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
 
 // host side of one instantiation family (stft_pair.cu: TC = false, stft_pair_tc.cu: TC = true)
 template <bool TC>
@@ -793,7 +809,18 @@ int launch_stft2048_pair_t(const StftParams& p, cudaStream_t stream) {
   }
   TAC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes<TC>()));
   LaunchProbe probe(KIND_STFT, stream);
-  k<<<grid, kPairThreads, pair_smem_bytes<TC>(), stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kPairThreads, 1, 1);
+  cfg.dynamicSmemBytes = pair_smem_bytes<TC>();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see the kernel's first lines
+  attr[0].val.programmaticStreamSerializationAllowed = pair_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TAC_CUDA_OK(cudaLaunchKernelEx(&cfg, k, p));
   TAC_CUDA_OK(cudaGetLastError());
   return TAC_OK;
 }

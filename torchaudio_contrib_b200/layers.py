@@ -5,6 +5,7 @@ exceptions; `Spectrogram` / `Melspectrogram` still return an iterable `nn.Sequen
 the fused kernels when its children form a known chain.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -251,6 +252,40 @@ class FusedSequential(nn.Sequential):
         return x
 
     @staticmethod
+    def _prepared_mel(st, power, fb, db, x):
+        """The steady-state mel call of a module chain: everything shape-independent (window on the device, filterbank plan,
+        argument marshalling) is resolved once per (shape, device, window, matrix, options) and kept on the filterbank
+        module, so a repeated call is one C-ABI call (the host side of the generic path costs about as much as the
+        config-2 kernel takes).  None when the call is not the plain float32 CUDA forward (autograd, other dtypes, CPU
+        tensors, strided inputs, the two-kernel path): the generic function then applies its own checks."""
+        if (not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.dim() < 1
+                or (torch.is_grad_enabled() and (x.requires_grad or fb.filterbank.requires_grad
+                                                 or (isinstance(st.window, torch.Tensor) and st.window.requires_grad)))):
+            return None
+        win = st.window
+        key = (tuple(x.shape), x.device, F.FilterbankPlan.key_of(fb.filterbank),
+               (win.data_ptr(), win._version, tuple(win.shape)) if isinstance(win, torch.Tensor) else None,
+               st.fft_length, st.hop_length, st.win_length, st.center, st.pad_mode, st.normalized, float(power),
+               (float(db.ref), float(db.amin)) if db is not None else None, os.environ.get("TAC_MELSPEC_FUSED", "1"))
+        cache = fb._plan_cache
+        hit = cache.get("prepared")
+        if hit is None or hit[0] != key:
+            try:
+                prep = F.PreparedMelspectrogram(x.shape, x.device, fb.filterbank, st.fft_length, st.hop_length, st.win_length,
+                                                win, st.center, st.pad_mode, st.normalized, power, db is not None,
+                                                db.ref if db is not None else 1.0, db.amin if db is not None else 1e-7)
+            except Exception:
+                return None                                   # let the generic path raise its own, reference-shaped error
+            if not prep.fused:
+                cache["prepared"] = (key, None)
+                return None
+            cache["prepared"] = hit = (key, prep)
+        prep = hit[1]
+        if prep is None:
+            return None
+        return prep(x, prep.empty_output())
+
+    @staticmethod
     def _fused_step(mods, i, x):
         def kind(j, cls):
             return j < len(mods) and type(mods[j]) is cls
@@ -260,6 +295,9 @@ class FusedSequential(nn.Sequential):
             if kind(i + 2, ApplyFilterbank):
                 fb = mods[i + 2]
                 db = mods[i + 3] if kind(i + 3, AmplitudeToDb) else None
+                y = FusedSequential._prepared_mel(st, power, fb, db, x)
+                if y is not None:
+                    return y, i + (4 if db is not None else 3)
                 y = F.melspectrogram(x, fb.filterbank, st.fft_length, power=power,
                                      to_db=db is not None, ref=db.ref if db else 1.0, amin=db.amin if db else 1e-7,
                                      _cache=fb._plan_cache, **st.stft_kwargs())

@@ -940,3 +940,32 @@ def test_hpss_golden(tac, oc):
         hpss(dev(torch.rand(1, 1, 10, 50)), 31)                    # reflect padding 15 >= 10 bins
     with pytest.raises(TypeError):
         hpss(x, 31.0)
+
+
+def test_module_chain_prepared_call_follows_its_buffers(tac, oc):
+    """The module chain keeps a prepared call per (shape, device, window, matrix, options) (layers.FusedSequential._prepared_mel);
+    it must notice when what it was prepared from changes: an in-place edit of the filterbank, a new window, another shape,
+    another device-side dtype path (float64 input), the dB module's parameters."""
+    torch.manual_seed(89)
+    x = torch.randn(3, 1, 20000)
+    mel = tac.Melspectrogram(num_mels=64, sample_rate=16000, fft_length=2048, hop_length=512).cuda()
+    y0 = mel(dev(x))
+    assert pure_rel_err(y0.cpu(), oc.melspectrogram(x, 64, 16000, fft_length=2048, hop_length=512)) < REL
+    assert torch.equal(mel(dev(x)), y0)                                   # steady state: the cached call
+    mel[2].filterbank.mul_(2.0)                                           # version counter bumps
+    assert pure_rel_err(mel(dev(x)).cpu(), 2.0 * y0.cpu()) < 1e-6
+    mel[2].filterbank.mul_(0.5)
+    w = torch.hann_window(2048) ** 2
+    mel[0].window = dev(w)                                                # another window buffer
+    want = oc.melspectrogram(x, 64, 16000, fft_length=2048, hop_length=512, window=w)
+    assert pure_rel_err(mel(dev(x)).cpu(), want) < REL
+    x2 = torch.randn(2, 2, 9000)                                          # another shape
+    assert pure_rel_err(mel(dev(x2)).cpu(), oc.melspectrogram(x2, 64, 16000, fft_length=2048, hop_length=512, window=w)) < REL
+    chain = tac.Sequential(*mel, tac.AmplitudeToDb(ref=2.0, amin=1e-6)).cuda()
+    got = chain(dev(x2)).cpu()
+    assert (got - oc.melspectrogram(x2, 64, 16000, to_db=True, ref=2.0, amin=1e-6, fft_length=2048, hop_length=512, window=w)).abs().max().item() < 1e-3
+    chain[3].ref = 1.0                                                     # the dB parameters are part of the key
+    got = chain(dev(x2)).cpu()
+    assert (got - oc.melspectrogram(x2, 64, 16000, to_db=True, ref=1.0, amin=1e-6, fft_length=2048, hop_length=512, window=w)).abs().max().item() < 1e-3
+    xg = dev(x2).requires_grad_(True)                                      # autograd bypasses the prepared call
+    assert mel(xg).requires_grad

@@ -35,8 +35,10 @@ struct WarpFftShape {
   static constexpr int S = R2 + 1;                       // slab row stride (complex), odd
   static constexpr int WARPS = (V > 32) ? 8 : 16;
   static constexpr int THREADS = WARPS * 32;
-  static constexpr int SLAB = (LOG2N == 12) ? 2 * 32 * 65 : 2 * 64 * 17 + 32;   // floats: >= F N samples and >= F R1 S complex
-  static_assert(A1 * R1 == V && A2 * R2 == V && F * R1 * S * 2 <= SLAB && F * N <= SLAB && F * (C + 1) <= SLAB, "shape");
+  // floats per warp: >= F N samples, >= F R1 S complex (transposition) and >= F (C + 1) complex (the output tile of the public
+  // layouts); for the small sizes SLAB = 4 or 8 (mod 32) so that the CTA-wide read-out of the tile spreads over the banks
+  static constexpr int SLAB = (LOG2N == 12) ? 2 * 32 * 65 : (LOG2N == 8 ? 2216 : 2212);
+  static_assert(A1 * R1 == V && A2 * R2 == V && F * R1 * S * 2 <= SLAB && F * N <= SLAB && 2 * F * (C + 1) <= SLAB && SLAB % 4 == 0, "shape");
 };
 
 template <int PMODE>
@@ -93,7 +95,20 @@ __global__ void __launch_bounds__(WarpFftShape<LOG2N>::THREADS, 1) stft_warp_ker
   const int64_t n_batches = (p.g1 - p.g0 + F - 1) / F;
   uint32_t parity = 0;
 
-  for (int64_t batch = (int64_t)blockIdx.x * kMwWarps + warp; batch < n_batches; batch += (int64_t)gridDim.x * kMwWarps) {
+  // Public layouts (complex / power, (n_seq, bins, frames[, 2])): the 16 warps of a CTA hold WARPS * F CONSECUTIVE frames per
+  // round; each warp leaves its frames' spectra in its slab and the whole CTA writes the tile out, a bin's consecutive frames
+  // as one run (a lane-per-bin store scatters 4- or 8-byte writes over `bins` rows: the complex STFT at 512 took 1.9x the
+  // power spectrogram).  The round loop is therefore uniform over the CTA; a warp without a batch only joins the barriers.
+  // (n_fft = 256 keeps the per-lane stores: its 8 frames per warp already give 32- / 64-byte runs and the two CTA barriers per
+  // round cost more than they save there: 0.101 against 0.094 ms.)
+  constexpr bool kTile = (OUT_MODE == OUT_COMPLEX_PUBLIC || OUT_MODE == OUT_POWER_PUBLIC) && LOG2N != 8;
+  constexpr int kTileFrames = kMwWarps * F;
+  int64_t* s_fr = reinterpret_cast<int64_t*>(s_slab + kMwWarps * kMwSlabFloats);      // kTile: output offset of (frame, bin 0), -1: no frame
+  for (int64_t base = (int64_t)blockIdx.x * kMwWarps; base < n_batches; base += (int64_t)gridDim.x * kMwWarps) {
+    const int64_t batch = base + warp;
+    const bool have = batch < n_batches;
+    if (!kTile && !have) continue;
+    if (have) {
     const uint32_t gb = (uint32_t)(p.g0 + batch * F);         // first frame of the batch (flattened index)
     // ---- stage the F frames: bulk copy where possible, gather otherwise ---------------------------------
     __syncwarp();                                             // previous batch is done with the slab
@@ -249,6 +264,46 @@ __global__ void __launch_bounds__(WarpFftShape<LOG2N>::THREADS, 1) stft_warp_ker
       }
       continue;
     }
+    if constexpr (kTile) {
+      // every pass-2 input leaves the slab first (as in the fused-filterbank branch), then the slab takes the tile
+      constexpr int SP = C + 1;
+      float2 uu[V];
+#pragma unroll
+      for (int b = 0; b < A2; ++b) {
+        const int i2 = b * 32 + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < R2; ++n1) {
+          const float2 a = slab[i2 * S + n1];
+          const float2 w = s_tw1[n1 * R1 + kk2];
+          uu[b * R2 + n1] = make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < A2; ++b) {
+        const int f2 = (b * 32 + lane) / R1;
+        float2 u[R2];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) u[i] = uu[b * R2 + i];
+        dit_fft_fma<R2>(u);
+        auto put = [&](int k, float re, float im) {
+          if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC) slab[f2 * SP + k] = make_float2(re, im);
+          else slab_f[f2 * SP + k] = mw_power<PMODE>(re, im, half_power);
+        };
+#pragma unroll
+        for (int k1 = 0; k1 < R2; ++k1) {
+          const float2 z = u[bit_reverse<R2>(k1)];
+          float2 q;
+          q.x = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].x, partner);
+          q.y = __shfl_sync(0xffffffffu, u[bit_reverse<R2>(R2 - 1 - k1)].y, partner);
+          if (kk2 == 0) q = u[bit_reverse<R2>((R2 - k1) % R2)];
+          const float a = z.x + q.x, bb = z.y - q.y, gs = z.y + q.y, h = q.x - z.x;
+          const float2 w = s_tw2[k1 * R1 + kk2];
+          put(R1 * k1 + kk2, fmaf(w.x, gs, fmaf(-w.y, h, a)), fmaf(w.x, h, fmaf(w.y, gs, bb)));
+        }
+        if (kk2 == 0) put(C, 2.0f * (u[0].x - u[0].y), 0.0f);
+      }
+    } else {
 #pragma unroll
     for (int b = 0; b < A2; ++b) {
       const int i2 = b * 32 + lane, f2 = i2 / R1;
@@ -301,13 +356,49 @@ __global__ void __launch_bounds__(WarpFftShape<LOG2N>::THREADS, 1) stft_warp_ker
         if (kk2 == 0) emit(C, nyq, 0.0f);
       }
     }
+    }   // !kTile
+    }   // have
+    if constexpr (kTile) {
+      constexpr int SP = C + 1;
+      __syncthreads();                                        // every warp's part of the tile is in its slab
+      for (int i = tid; i < kTileFrames; i += kMwThreads) {
+        const int64_t g = p.g0 + base * F + i;
+        int64_t off = -1;
+        if (g < p.g1) {
+          const int64_t seq = g / p.frames, t = g - seq * p.frames;
+          off = seq * p.bins * p.frames + t;
+        }
+        s_fr[i] = off;
+      }
+      __syncthreads();
+      constexpr int FPW = kTileFrames < 32 ? kTileFrames : 32;    // frames per warp instruction
+      constexpr int BPW = 32 / FPW;                               // bins per warp instruction
+      const int fl = lane % FPW, bl = lane / FPW;
+      for (int bin0 = warp * BPW; bin0 <= C; bin0 += kMwWarps * BPW) {
+        const int bin = bin0 + bl;
+#pragma unroll
+        for (int c = 0; c < kTileFrames / FPW; ++c) {
+          const int fr = c * FPW + fl;
+          const int64_t off = s_fr[fr];
+          if (bin <= C && off >= 0) {
+            const float* src = s_slab + (fr / F) * kMwSlabFloats;
+            if constexpr (OUT_MODE == OUT_COMPLEX_PUBLIC)
+              __stcs(reinterpret_cast<float2*>(p.out) + off + (int64_t)bin * p.frames, reinterpret_cast<const float2*>(src)[(fr % F) * SP + bin]);
+            else
+              __stcs(p.out + off + (int64_t)bin * p.frames, src[(fr % F) * SP + bin]);
+          }
+        }
+      }
+      __syncthreads();                                        // tile written: the slabs may take the next round's samples
+    }
   }
 }
 
 template <int LOG2N>
 static size_t warp_kernel_smem() {
   using Sh = WarpFftShape<LOG2N>;
-  return 3 * (size_t)Sh::C * sizeof(float2) + Sh::WARPS * sizeof(uint64_t) + (size_t)Sh::WARPS * Sh::SLAB * sizeof(float);
+  return 3 * (size_t)Sh::C * sizeof(float2) + Sh::WARPS * sizeof(uint64_t) + (size_t)Sh::WARPS * Sh::SLAB * sizeof(float) +
+         (size_t)Sh::WARPS * Sh::F * sizeof(int64_t);        // + the frame table of the public-layout tile
 }
 
 template <int LOG2N>

@@ -111,3 +111,61 @@ def test_in_place_pairing_of_the_backward_kernel():
     assert sorted(met) == list(range(1024))
     for k, partner in met.items():
         assert partner == (1024 - k) % 1024, (k, partner)
+
+
+def test_phase_vocoder_gather_ranges_partition_the_output_steps():
+    """The backward kernel of the phase vocoder gathers, per input frame i, the output steps j with idx0[j] == i and those
+    with idx1[j] == i; both index tables are monotone, so the steps form contiguous ranges (functional._phase_vocoder_ranges).
+    Checked here on the CPU for stretch and compress rates: every step lies in exactly the range of its frame."""
+    import torchaudio_contrib_b200.functional as F
+    for n_in, rate in ((41, 0.7), (50, 1.3), (37, 2.0), (12, 0.3), (100, 1.01), (5, 3.7)):
+        steps = torch.arange(0, n_in, rate)
+        idx0, idx1 = steps.long().to(torch.int32), (steps + 1).long().to(torch.int32)
+        r0, r1 = F._phase_vocoder_ranges(idx0, idx1, n_in)
+        assert r0.shape == r1.shape == (n_in, 2) and r0.dtype == torch.int32
+        for idx, r in ((idx0, r0), (idx1, r1)):
+            covered = torch.zeros(idx.numel(), dtype=torch.int32)
+            for i in range(n_in):
+                lo, hi = int(r[i, 0]), int(r[i, 1])
+                assert 0 <= lo <= hi <= idx.numel()
+                assert bool((idx[lo:hi] == i).all())
+                covered[lo:hi] += 1
+            inside = idx < n_in                                   # steps whose frame is one of the two appended zero frames have no gradient
+            assert bool((covered[inside] == 1).all()) and bool((covered[~inside] == 0).all())
+
+
+def test_forgetful_selection_finds_the_median():
+    """csrc/hpss.cu finds the median of 2 m + 1 values by forgetful selection (keep m + 2 candidates, drop their minimum and
+    maximum, take in the next value) on a window padded to the template size with equally many -inf and +inf.  The same
+    procedure in Python against numpy's median: random windows, ties, every odd size up to 63 in each template bucket."""
+    import numpy as np
+
+    def forgetful(v):
+        n = len(v)
+        m = n // 2 + 2
+        a = list(v[:m])
+        nxt = m
+        for s in range(m, 2, -1):
+            for i in range(s // 2):
+                if a[i] > a[s - 1 - i]:
+                    a[i], a[s - 1 - i] = a[s - 1 - i], a[i]
+            for i in range(1, (s + 1) // 2):
+                if a[0] > a[i]:
+                    a[0], a[i] = a[i], a[0]
+            for i in range(s // 2, s - 1):
+                if a[i] > a[s - 1]:
+                    a[i], a[s - 1] = a[s - 1], a[i]
+            if nxt < n:
+                a[0] = v[nxt]
+                nxt += 1
+        assert nxt == n
+        return a[1]
+
+    rng = np.random.default_rng(5)
+    for k in list(range(3, 64, 2)):
+        kmax = 7 if k <= 7 else (15 if k <= 15 else (31 if k <= 31 else 63))
+        fill = (kmax - k) // 2
+        for trial in range(6):
+            w = rng.integers(0, 9, k).astype(np.float32) if trial % 2 else rng.standard_normal(k).astype(np.float32)
+            padded = [-np.inf] * fill + list(w) + [np.inf] * fill
+            assert forgetful(padded) == np.median(w), (k, trial)

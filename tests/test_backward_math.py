@@ -169,3 +169,34 @@ def test_forgetful_selection_finds_the_median():
             w = rng.integers(0, 9, k).astype(np.float32) if trial % 2 else rng.standard_normal(k).astype(np.float32)
             padded = [-np.inf] * fill + list(w) + [np.inf] * fill
             assert forgetful(padded) == np.median(w), (k, trial)
+
+
+def test_folded_dft_and_twiddle_rotation_model():
+    """stft_dft_kernel (csrc/stft.cu) evaluates X[k] = x[0] + (-1)^k x[N/2] + sum_{n=1}^{H} (x[n] + x[N-n]) cos - i (x[n] - x[N-n]) sin,
+    H = (N - 1) / 2, with the twiddle exp(-2 pi i n k / N) re-read from a table every 16 steps (index n k mod N kept exactly)
+    and rotated by exp(-2 pi i k / N) in between.  The same procedure in float32 numpy against numpy's rfft, even and odd sizes."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for n_fft in (400, 441, 6, 7, 1200):
+        x = rng.standard_normal(n_fft).astype(np.float32)
+        tab = np.exp(-2j * np.pi * np.arange(n_fft) / n_fft)
+        tab = (tab.real.astype(np.float32), tab.imag.astype(np.float32))
+        h = (n_fft - 1) // 2
+        e = np.array([x[n] + x[n_fft - n] for n in range(1, h + 1)], dtype=np.float32)
+        o = np.array([x[n] - x[n_fft - n] for n in range(1, h + 1)], dtype=np.float32)
+        got = np.zeros(n_fft // 2 + 1, dtype=np.complex64)
+        for k in range(n_fft // 2 + 1):
+            re = np.float32(x[0] + ((-x[n_fft // 2] if k & 1 else x[n_fft // 2]) if n_fft % 2 == 0 else 0.0))
+            im = np.float32(0)
+            rot = (tab[0][k], tab[1][k])
+            idx, step = k % n_fft, (16 * k) % n_fft
+            for n0 in range(1, h + 1, 16):
+                w = (tab[0][idx], tab[1][idx])
+                for n in range(n0, min(n0 + 16, h + 1)):
+                    re = np.float32(re + e[n - 1] * w[0])
+                    im = np.float32(im + o[n - 1] * w[1])
+                    w = (np.float32(w[0] * rot[0] - w[1] * rot[1]), np.float32(w[0] * rot[1] + w[1] * rot[0]))
+                idx = (idx + step) % n_fft
+            got[k] = re + 1j * (0.0 if (k == 0 or 2 * k == n_fft) else im)
+        want = np.fft.rfft(x.astype(np.float64))
+        assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), n_fft

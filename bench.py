@@ -684,6 +684,9 @@ def run_ours(args, rank, world, local):
                 "precision": ("fp32 FFT (two frames per warp, packed FFMA2) + fp32 two-band filterbank in one kernel (%s)" % kernel if fused
                               else "fp32 FFT on CUDA cores; filterbank 3xTF32 on tcgen05 (fp32 accumulate)"),
                 "call": "tac_melspec_banded_f32" if fused else "tac_melspec_f32",
+                "launch": ("consecutive launches chained by programmatic dependent launch (set-up before griddepcontrol.wait, "
+                           "stream order kept; TAC_PAIR_PDL=0 disables)" if fused and os.environ.get("TAC_PAIR_PDL", "1") != "0"
+                           else "plain stream-ordered launches"),
             },
             "module_ms_per_step": module_ms, "module_matches_call": same,
             "output_layout": ("reference: (batch, channel, bands, frames) view of frame-major memory, strides (..., 1, bands) "

@@ -969,3 +969,18 @@ def test_module_chain_prepared_call_follows_its_buffers(tac, oc):
     assert (got - oc.melspectrogram(x2, 64, 16000, to_db=True, ref=1.0, amin=1e-6, fft_length=2048, hop_length=512, window=w)).abs().max().item() < 1e-3
     xg = dev(x2).requires_grad_(True)                                      # autograd bypasses the prepared call
     assert mel(xg).requires_grad
+
+
+def test_host_pipeline_other_sizes(tac, oc):
+    """The host-buffer entry (tac_pipeline_*) at an fft length that is not a power of two (direct-DFT kernel -> tensor-core
+    filterbank, two kernels per slice) and at 1024 (one-kernel range-plan path is not the pipeline's: it runs K1 -> K2 too)."""
+    torch.manual_seed(101)
+    x = torch.randn(5, 1, 20000)
+    for fft, hop, mels in ((400, 160, 40), (1024, 256, 64)):
+        fb = tac.MelFilterbank(num_freqs=fft // 2 + 1, num_mels=mels, sample_rate=16000).get_filterbank()
+        hp = tac.HostPipeline(fft, hop, power=2.0, filterbank=fb, to_db=True)
+        got = hp(x)
+        want = oc.melspectrogram(x, mels, 16000, to_db=True, fft_length=fft, hop_length=hop)
+        assert got.shape == want.shape and (got - want).abs().max().item() < 1e-3, fft
+        sp = tac.HostPipeline(fft, hop, power=1.0)
+        assert rel_err(sp(x), oc.spectrogram(x, fft, hop, power=1.0)) < REL, fft

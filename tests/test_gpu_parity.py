@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
 Tolerances: BASELINE.json north star -- 1e-4 relative fp32 for the mel path (dB: 1e-3 dB absolute),
 bit-exact for mu-law codes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -984,3 +986,32 @@ def test_host_pipeline_other_sizes(tac, oc):
         assert got.shape == want.shape and (got - want).abs().max().item() < 1e-3, fft
         sp = tac.HostPipeline(fft, hop, power=1.0)
         assert rel_err(sp(x), oc.spectrogram(x, fft, hop, power=1.0)) < REL, fft
+
+
+def test_c_abi_without_python(tac, oc, tmp_path):
+    """examples/c_abi_mulaw.c: a C program that links libtac_b200.so, takes the mu-law decision levels from
+    tac_mulaw_tables_host (shipped in the library) and encodes / decodes a file of samples -- no Python, no torch in that
+    process.  Its codes and decoded values equal the reference chain's bit for bit (functional.py:317-354)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no C compiler / CUDA headers on this box")
+    exe = str(tmp_path / "c_abi_mulaw")
+    libdir = os.path.join(root, "torchaudio_contrib_b200", "lib")
+    subprocess.run([cc, "-O2", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(root, "examples", "c_abi_mulaw.c"), "-o", exe, "-L", libdir, "-ltac_b200",
+                    "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
+    torch.manual_seed(103)
+    x = torch.cat([torch.rand(200000) * 2 - 1, 2 * (torch.randn(50000) - 0.5), torch.tensor([0.0, -0.0, 1.0, -1.0, 1e-30, 3e38])])
+    x.numpy().tofile(str(tmp_path / "x.f32"))
+    res = subprocess.run([exe, str(tmp_path / "x.f32"), str(tmp_path / "codes.i64"), str(tmp_path / "dec.f32")],
+                         check=True, capture_output=True, text=True)
+    assert "through the C ABI" in res.stdout
+    codes = torch.from_numpy(np.fromfile(str(tmp_path / "codes.i64"), dtype=np.int64))
+    dec = torch.from_numpy(np.fromfile(str(tmp_path / "dec.f32"), dtype=np.float32))
+    want = oc.mu_law_encoding(x, 256)
+    assert torch.equal(codes, want)
+    inside = (want >= 0) & (want < 256)
+    assert torch.equal(dec[inside], oc.mu_law_decoding(want, 256)[inside])

@@ -413,3 +413,19 @@ def test_filterbank_plan_cache_identity(tac):
     assert len(F._GLOBAL_PLANS) <= F._GLOBAL_PLANS_MAX
     F.invalidate_filterbank_plans()
     assert len(F._GLOBAL_PLANS) == 0
+
+
+def test_c_example_compiles_against_the_header():
+    """examples/c_abi_mulaw.c is plain C against include/tac_b200.h: it must compile and link here (no GPU needed to build)."""
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no C compiler / CUDA headers here")
+    libdir = os.path.join(root, "torchaudio_contrib_b200", "lib")
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([cc, "-O2", "-Wall", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(root, "examples", "c_abi_mulaw.c"), "-o", os.path.join(tmp, "c_abi_mulaw"), "-L", libdir,
+                        "-ltac_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
